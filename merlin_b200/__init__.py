@@ -1,0 +1,2 @@
+"""merlin_b200 — B200-native (sm_100a) implementation of the Merlin / mmgpt multimodal hot path."""
+__version__ = "0.1.0"

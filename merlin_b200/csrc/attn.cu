@@ -1,0 +1,70 @@
+// merlin_b200 — host launcher for the flash-attention forward kernel (attn.cuh).
+#include "attn.cuh"
+#include "host.cuh"
+
+#include <cmath>
+
+namespace mb {
+
+template <int HD, bool kCausal>
+static int launch_attn(cudaStream_t stream, const CUtensorMap& tq, const CUtensorMap& to,
+                       const AttnParams& p) {
+  using Cfg = AttnCfg<HD>;
+  static bool configured = false;
+  if (!configured) {
+    MB_CHECK_CUDA(cudaFuncSetAttribute(attn_fwd_kernel<HD, kCausal>,
+                                       cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::kSmemBytes));
+    configured = true;
+  }
+  const int nq = (p.S + kAttnBlock - 1) / kAttnBlock;
+  dim3 grid(static_cast<unsigned>(nq), static_cast<unsigned>(p.H), static_cast<unsigned>(p.B));
+  attn_fwd_kernel<HD, kCausal><<<grid, kAttnThreads, Cfg::kSmemBytes, stream>>>(tq, to, p);
+  MB_CHECK_CUDA(cudaGetLastError());
+  return MERLIN_OK;
+}
+
+}  // namespace mb
+
+extern "C" int merlin_flash_attn_fwd(void* stream, const void* qkv, int64_t ld_qkv, void* out,
+                                     int64_t ld_out, float* lse, const int* seqlens, int B, int S,
+                                     int H, int head_dim, int causal, float softmax_scale) {
+  using namespace mb;
+  MB_CHECK_ARG(qkv && out, "flash_attn_fwd: null tensor");
+  MB_CHECK_ARG(B > 0 && S > 0 && H > 0, "flash_attn_fwd: empty problem B=%d S=%d H=%d", B, S, H);
+  MB_CHECK_ARG(head_dim == 64 || head_dim == 128, "flash_attn_fwd: head_dim %d not in {64,128}",
+               head_dim);
+  MB_CHECK_ARG(ld_qkv >= 3 * static_cast<int64_t>(H) * head_dim && ld_out >= static_cast<int64_t>(H) * head_dim,
+               "flash_attn_fwd: leading dimensions too small");
+  AttnParams p = {};
+  p.B = B;
+  p.S = S;
+  p.H = H;
+  p.q_col0 = 0;
+  p.k_col0 = H * head_dim;
+  p.v_col0 = 2 * H * head_dim;
+  const float scale = softmax_scale > 0.f ? softmax_scale : 1.0f / std::sqrt(static_cast<float>(head_dim));
+  p.scale_log2e = scale * 1.4426950408889634f;
+  p.seqlens = seqlens;
+  p.lse = lse;
+
+  CUtensorMap tq, to;
+  int rc;
+  {
+    uint64_t dims[3] = {static_cast<uint64_t>(3) * H * head_dim, static_cast<uint64_t>(S),
+                        static_cast<uint64_t>(B)};
+    uint64_t str[2] = {static_cast<uint64_t>(ld_qkv) * 2, static_cast<uint64_t>(ld_qkv) * 2 * S};
+    uint32_t box[3] = {64, kAttnBlock, 1};
+    if ((rc = make_tmap_bf16(&tq, qkv, 3, dims, str, box)) != MERLIN_OK) return rc;
+  }
+  {
+    uint64_t dims[3] = {static_cast<uint64_t>(H) * head_dim, static_cast<uint64_t>(S),
+                        static_cast<uint64_t>(B)};
+    uint64_t str[2] = {static_cast<uint64_t>(ld_out) * 2, static_cast<uint64_t>(ld_out) * 2 * S};
+    uint32_t box[3] = {64, kAttnBlock, 1};
+    if ((rc = make_tmap_bf16(&to, out, 3, dims, str, box)) != MERLIN_OK) return rc;
+  }
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  if (head_dim == 128)
+    return causal ? launch_attn<128, true>(st, tq, to, p) : launch_attn<128, false>(st, tq, to, p);
+  return causal ? launch_attn<64, true>(st, tq, to, p) : launch_attn<64, false>(st, tq, to, p);
+}

@@ -1,0 +1,201 @@
+// merlin_b200 — host launcher for the tcgen05 GEMM (see gemm.cuh) and shared host helpers.
+#include "gemm.cuh"
+#include "host.cuh"
+
+#include <cstring>
+#include <mutex>
+
+namespace mb {
+
+static thread_local char g_error[512] = "";
+
+void set_error(const char* fmt, ...) {
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(g_error, sizeof(g_error), fmt, ap);
+  va_end(ap);
+}
+
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*,
+                                  const cuuint64_t*, const cuuint64_t*, const cuuint32_t*,
+                                  const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+static EncodeTiledFn encode_fn() {
+  static EncodeTiledFn fn = nullptr;
+  static std::once_flag once;
+  std::call_once(once, [] {
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) == cudaSuccess &&
+        q == cudaDriverEntryPointSuccess)
+      fn = reinterpret_cast<EncodeTiledFn>(p);
+  });
+  return fn;
+}
+
+int make_tmap_bf16(CUtensorMap* out, const void* base, int rank, const uint64_t* dims,
+                   const uint64_t* strides_bytes, const uint32_t* box) {
+  EncodeTiledFn fn = encode_fn();
+  if (!fn) {
+    set_error("cuTensorMapEncodeTiled entry point unavailable (no CUDA driver?)");
+    return MERLIN_E_CUDA;
+  }
+  cuuint64_t gdim[5];
+  cuuint64_t gstr[5];
+  cuuint32_t bdim[5];
+  cuuint32_t estr[5];
+  for (int i = 0; i < rank; ++i) {
+    gdim[i] = dims[i];
+    bdim[i] = box[i];
+    estr[i] = 1;
+    if (i > 0) gstr[i - 1] = strides_bytes[i - 1];
+  }
+  if ((reinterpret_cast<uintptr_t>(base) & 15) != 0) {
+    set_error("tensor base %p is not 16-byte aligned", base);
+    return MERLIN_E_INVALID;
+  }
+  for (int i = 0; i + 1 < rank; ++i)
+    if (gstr[i] % 16 != 0) {
+      set_error("tensor stride %llu bytes (dim %d) is not a multiple of 16",
+                static_cast<unsigned long long>(gstr[i]), i + 1);
+      return MERLIN_E_INVALID;
+    }
+  CUresult r = fn(out, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, static_cast<cuuint32_t>(rank),
+                  const_cast<void*>(base), gdim, gstr, bdim, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                  CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                  CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) {
+    set_error("cuTensorMapEncodeTiled failed with CUresult %d (rank %d dims %llu,%llu box %u,%u)",
+              static_cast<int>(r), rank, static_cast<unsigned long long>(dims[0]),
+              static_cast<unsigned long long>(rank > 1 ? dims[1] : 0), box[0], rank > 1 ? box[1] : 0);
+    return MERLIN_E_CUDA;
+  }
+  return MERLIN_OK;
+}
+
+int sm_count() {
+  static int n = 0;
+  if (n == 0) {
+    int dev = 0;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev);
+  }
+  return n;
+}
+
+template <int kCtaGroup>
+static int launch_gemm(cudaStream_t stream, const CUtensorMap& ta, const CUtensorMap& tb,
+                       const CUtensorMap& tc, const CUtensorMap& tr, const GemmParams& p) {
+  using Cfg = GemmCfg<kCtaGroup>;
+  static bool configured = false;
+  if (!configured) {
+    MB_CHECK_CUDA(cudaFuncSetAttribute(gemm_bf16_kernel<kCtaGroup>,
+                                       cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::kSmemBytes));
+    configured = true;
+  }
+  const int rows_per_tile = kBlockM * kCtaGroup;
+  const int tiles = ((p.M + rows_per_tile - 1) / rows_per_tile) * ((p.N + kBlockN - 1) / kBlockN);
+  int workers = sm_count() / kCtaGroup;
+  if (tiles < workers) workers = tiles;
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3(static_cast<unsigned>(workers * kCtaGroup));
+  cfg.blockDim = dim3(kGemmThreads);
+  cfg.dynamicSmemBytes = Cfg::kSmemBytes;
+  cfg.stream = stream;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = kCtaGroup;
+  attr[0].val.clusterDim.y = 1;
+  attr[0].val.clusterDim.z = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  MB_CHECK_CUDA(cudaLaunchKernelEx(&cfg, gemm_bf16_kernel<kCtaGroup>, ta, tb, tc, tr, p));
+  return MERLIN_OK;
+}
+
+int gemm_dispatch(cudaStream_t stream, const void* A, int64_t lda, const void* B, int64_t ldb, void* C,
+                  int64_t ldc, const void* R, int64_t ldr, const GemmParams& p, int cta_group) {
+  MB_CHECK_ARG(p.M > 0 && p.N > 0 && p.K > 0, "gemm: empty problem M=%d N=%d K=%d", p.M, p.N, p.K);
+  MB_CHECK_ARG(cta_group == 1 || cta_group == 2, "gemm: cta_group must be 1 or 2, got %d", cta_group);
+  MB_CHECK_ARG(A && B && C, "gemm: null operand");
+  if (p.epilogue == EPI_SWIGLU)
+    MB_CHECK_ARG(p.N % 256 == 0, "gemm: SwiGLU epilogue needs N %% 256 == 0 (interleaved gate/up), N=%d", p.N);
+  if (p.epilogue == EPI_ROPE)
+    MB_CHECK_ARG(p.rope_cos && p.rope_sin && p.rope_cols % 256 == 0 && p.seq_len > 0,
+                 "gemm: RoPE epilogue needs cos/sin tables, rope_cols %% 256 == 0, seq_len > 0");
+  if (p.epilogue == EPI_RESIDUAL) MB_CHECK_ARG(R != nullptr, "gemm: residual epilogue needs R");
+  const int n_out = (p.epilogue == EPI_SWIGLU) ? p.N / 2 : p.N;
+
+  CUtensorMap ta, tb, tc, tr;
+  int rc;
+  {
+    uint64_t dims[2] = {static_cast<uint64_t>(p.K), static_cast<uint64_t>(p.M)};
+    uint64_t str[1] = {static_cast<uint64_t>(lda) * 2};
+    uint32_t box[2] = {kBlockK, kBlockM};
+    if ((rc = make_tmap_bf16(&ta, A, 2, dims, str, box)) != MERLIN_OK) return rc;
+  }
+  {
+    uint64_t dims[2] = {static_cast<uint64_t>(p.K), static_cast<uint64_t>(p.N)};
+    uint64_t str[1] = {static_cast<uint64_t>(ldb) * 2};
+    uint32_t box[2] = {kBlockK, static_cast<uint32_t>(kBlockN / cta_group)};
+    if ((rc = make_tmap_bf16(&tb, B, 2, dims, str, box)) != MERLIN_OK) return rc;
+  }
+  {
+    uint64_t dims[2] = {static_cast<uint64_t>(n_out), static_cast<uint64_t>(p.M)};
+    uint64_t str[1] = {static_cast<uint64_t>(ldc) * 2};
+    uint32_t box[2] = {kEpiCols, kBlockM};
+    if ((rc = make_tmap_bf16(&tc, C, 2, dims, str, box)) != MERLIN_OK) return rc;
+  }
+  if (p.epilogue == EPI_RESIDUAL) {
+    uint64_t dims[2] = {static_cast<uint64_t>(n_out), static_cast<uint64_t>(p.M)};
+    uint64_t str[1] = {static_cast<uint64_t>(ldr) * 2};
+    uint32_t box[2] = {kEpiCols, kBlockM};
+    if ((rc = make_tmap_bf16(&tr, R, 2, dims, str, box)) != MERLIN_OK) return rc;
+  } else {
+    tr = tc;
+  }
+  return cta_group == 2 ? launch_gemm<2>(stream, ta, tb, tc, tr, p)
+                        : launch_gemm<1>(stream, ta, tb, tc, tr, p);
+}
+
+}  // namespace mb
+
+extern "C" {
+
+const char* merlin_last_error(void) { return mb::g_error; }
+
+int merlin_gemm_bf16(void* stream, const void* A, int64_t lda, const void* B, int64_t ldb, void* C,
+                     int64_t ldc, const void* R, int64_t ldr, const void* bias, int M, int N, int K,
+                     int epilogue, int cta_group) {
+  MB_CHECK_ARG(epilogue >= MERLIN_EPI_STORE && epilogue <= MERLIN_EPI_SWIGLU,
+               "merlin_gemm_bf16: unknown epilogue %d", epilogue);
+  mb::GemmParams p = {};
+  p.M = M;
+  p.N = N;
+  p.K = K;
+  p.epilogue = epilogue;
+  p.bias = static_cast<const __nv_bfloat16*>(bias);
+  return mb::gemm_dispatch(static_cast<cudaStream_t>(stream), A, lda, B, ldb, C, ldc, R, ldr, p,
+                           cta_group);
+}
+
+int merlin_gemm_qkv_rope(void* stream, const void* A, int64_t lda, const void* Wqkv, int64_t ldb,
+                         void* qkv, int64_t ldc, const float* rope_cos, const float* rope_sin,
+                         const int* positions, int M, int N, int K, int rope_cols, int seq_len,
+                         int cta_group) {
+  mb::GemmParams p = {};
+  p.M = M;
+  p.N = N;
+  p.K = K;
+  p.epilogue = mb::EPI_ROPE;
+  p.rope_cos = rope_cos;
+  p.rope_sin = rope_sin;
+  p.positions = positions;
+  p.rope_cols = rope_cols;
+  p.seq_len = seq_len;
+  return mb::gemm_dispatch(static_cast<cudaStream_t>(stream), A, lda, Wqkv, ldb, qkv, ldc, nullptr, 0,
+                           p, cta_group);
+}
+
+}  // extern "C"

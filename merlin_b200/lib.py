@@ -1,0 +1,80 @@
+"""ctypes binding of libmerlin_b200.so (the C ABI declared in include/merlin_b200.h).
+
+The product path has no fallback: if the shared library is missing or a call fails, we raise.
+`MERLIN_B200_LIB` may point at an alternative build (e.g. the bring-up build with bounded
+mbarrier spins, libmerlin_b200_dbg.so).
+"""
+from __future__ import annotations
+
+import ctypes
+import os
+import re
+from ctypes import c_char_p, c_float, c_int, c_int64, c_void_p
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+_HEADER = os.path.join(os.path.dirname(_HERE), "include", "merlin_b200.h")
+
+MERLIN_OK = 0
+EPI_STORE, EPI_RESIDUAL, EPI_QUICKGELU, EPI_SWIGLU = 0, 1, 2, 3
+
+
+class MerlinError(RuntimeError):
+    """Raised when a libmerlin_b200 entry point returns a non-zero status."""
+
+
+_P = c_void_p
+_PROTOTYPES = {
+    "merlin_gemm_bf16": [_P, _P, c_int64, _P, c_int64, _P, c_int64, _P, c_int64, _P, c_int, c_int, c_int, c_int, c_int],
+    "merlin_gemm_qkv_rope": [_P, _P, c_int64, _P, c_int64, _P, c_int64, _P, _P, _P, c_int, c_int, c_int, c_int, c_int, c_int],
+    "merlin_flash_attn_fwd": [_P, _P, c_int64, _P, c_int64, _P, _P, c_int, c_int, c_int, c_int, c_int, c_float],
+    "merlin_rmsnorm": [_P, _P, c_int64, _P, _P, c_int64, c_int, c_int, c_float],
+    "merlin_layernorm": [_P, _P, c_int64, _P, _P, _P, c_int64, c_int, c_int, c_float],
+    "merlin_patch_im2col": [_P, _P, _P, c_int, c_int, c_int, c_int],
+    "merlin_vit_embed_ln": [_P, _P, _P, _P, _P, _P, _P, c_int, c_int, c_int, c_float],
+    "merlin_conv3x3_im2col": [_P, _P, _P, c_int, c_int, c_int, c_int, c_int, c_int],
+    "merlin_embed_splice": [_P, _P, _P, _P, _P, _P, c_int, c_int, c_int, c_int64, c_int64],
+    "merlin_rope_qk_inplace": [_P, _P, c_int64, _P, _P, _P, c_int, c_int, c_int],
+    "merlin_cross_entropy_fwd": [_P, _P, c_int64, _P, c_int, c_int, c_int, c_int64, _P, _P],
+    "merlin_argmax": [_P, _P, c_int64, c_int, c_int, _P],
+}
+
+
+def declared_symbols(header: str = _HEADER) -> list[str]:
+    """Every function name declared in include/merlin_b200.h (used by the symbol-export test)."""
+    text = open(header).read()
+    text = re.sub(r"/\*.*?\*/", "", text, flags=re.S)
+    return sorted(set(re.findall(r"\b(merlin_[a-z0-9_]+)\s*\(", text)))
+
+
+def library_path() -> str:
+    return os.environ.get("MERLIN_B200_LIB", os.path.join(_HERE, "libmerlin_b200.so"))
+
+
+_lib = None
+
+
+def load() -> ctypes.CDLL:
+    """Load the shared library (once) and attach prototypes.  Raises if it is not built."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    path = library_path()
+    if not os.path.exists(path):
+        raise MerlinError(
+            f"{path} not found: build it with `python -c 'import __graft_entry__ as g; g.build()'` "
+            "or `make -C merlin_b200/csrc` — there is no CPU/PyTorch fallback for the hot path")
+    lib = ctypes.CDLL(path)
+    lib.merlin_last_error.restype = c_char_p
+    lib.merlin_last_error.argtypes = []
+    for name, argtypes in _PROTOTYPES.items():
+        fn = getattr(lib, name)
+        fn.restype = c_int
+        fn.argtypes = argtypes
+    _lib = lib
+    return lib
+
+
+def check(status: int, what: str) -> None:
+    if status != MERLIN_OK:
+        msg = load().merlin_last_error().decode("utf-8", "replace")
+        raise MerlinError(f"{what} failed with status {status}: {msg}")

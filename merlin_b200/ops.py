@@ -1,0 +1,234 @@
+"""Thin torch-facing wrappers over the C ABI: torch owns memory and streams, the library computes.
+
+Every function takes CUDA bf16 tensors (unless noted), passes raw pointers + the current stream to
+libmerlin_b200.so and returns torch tensors.  No op here has a PyTorch fallback.
+"""
+from __future__ import annotations
+
+import math
+from typing import Optional
+
+import torch
+
+from . import lib as _lib
+from .lib import EPI_QUICKGELU, EPI_RESIDUAL, EPI_STORE, EPI_SWIGLU, check
+
+DEFAULT_CTA_GROUP = 2  # CTA-pair (cta_group::2) GEMM tiles unless overridden
+
+_BF16 = torch.bfloat16
+
+
+def _stream() -> int:
+    return torch.cuda.current_stream().cuda_stream
+
+
+def _ptr(t: Optional[torch.Tensor]) -> Optional[int]:
+    return None if t is None else t.data_ptr()
+
+
+def _rows2d(t: torch.Tensor, name: str) -> tuple[int, int, int]:
+    """(rows, cols, leading dimension) of a 2-D bf16 CUDA tensor with unit inner stride."""
+    if t.dtype != _BF16 or not t.is_cuda:
+        raise TypeError(f"{name}: expected a CUDA bfloat16 tensor, got {t.dtype} on {t.device}")
+    if t.dim() != 2 or t.stride(1) != 1:
+        raise ValueError(f"{name}: expected a 2-D tensor with contiguous rows, got {tuple(t.shape)} strides {t.stride()}")
+    return t.shape[0], t.shape[1], t.stride(0)
+
+
+def gemm(a: torch.Tensor, w: torch.Tensor, *, bias: Optional[torch.Tensor] = None,
+         residual: Optional[torch.Tensor] = None, out: Optional[torch.Tensor] = None,
+         epilogue: int = EPI_STORE, cta_group: Optional[int] = None) -> torch.Tensor:
+    """out = epilogue(a @ w.T): a [M,K], w [N,K] (nn.Linear layout).  See merlin_gemm_bf16."""
+    M, K, lda = _rows2d(a, "a")
+    N, Kw, ldb = _rows2d(w, "w")
+    if K != Kw:
+        raise ValueError(f"gemm: K mismatch {K} vs {Kw}")
+    n_out = N // 2 if epilogue == EPI_SWIGLU else N
+    if out is None:
+        ld = (n_out + 7) // 8 * 8  # TMA needs a 16-byte row pitch
+        out = torch.empty((M, ld), dtype=_BF16, device=a.device)[:, :n_out]
+    Mo, No, ldc = _rows2d(out, "out")
+    if (Mo, No) != (M, n_out):
+        raise ValueError(f"gemm: out shape {(Mo, No)} != {(M, n_out)}")
+    ldr = 0
+    if epilogue == EPI_RESIDUAL:
+        if residual is None:
+            raise ValueError("gemm: residual epilogue without residual tensor")
+        Mr, Nr, ldr = _rows2d(residual, "residual")
+        if (Mr, Nr) != (M, n_out):
+            raise ValueError("gemm: residual shape mismatch")
+    if bias is not None and (bias.dtype != _BF16 or bias.numel() != N or not bias.is_contiguous()):
+        raise ValueError("gemm: bias must be a contiguous bf16 vector of length N")
+    if M == 0:
+        return out
+    L = _lib.load()
+    check(L.merlin_gemm_bf16(_stream(), a.data_ptr(), lda, w.data_ptr(), ldb, out.data_ptr(), ldc,
+                             _ptr(residual), ldr, _ptr(bias), M, N, K, epilogue,
+                             cta_group or DEFAULT_CTA_GROUP), "merlin_gemm_bf16")
+    return out
+
+
+def gemm_qkv_rope(a: torch.Tensor, w_qkv: torch.Tensor, rope_cos: torch.Tensor, rope_sin: torch.Tensor,
+                  seq_len: int, *, positions: Optional[torch.Tensor] = None,
+                  out: Optional[torch.Tensor] = None, cta_group: Optional[int] = None) -> torch.Tensor:
+    """Packed qkv = a @ w_qkv.T with RoPE applied to the q and k blocks in the GEMM epilogue."""
+    M, K, lda = _rows2d(a, "a")
+    N, Kw, ldb = _rows2d(w_qkv, "w_qkv")
+    if K != Kw or N % 3 != 0:
+        raise ValueError("gemm_qkv_rope: bad shapes")
+    if rope_cos.dtype != torch.float32 or rope_sin.dtype != torch.float32 or rope_cos.shape[-1] != 64:
+        raise ValueError("gemm_qkv_rope: cos/sin tables must be fp32 [max_pos, 64]")
+    if out is None:
+        out = torch.empty((M, N), dtype=_BF16, device=a.device)
+    _, _, ldc = _rows2d(out, "out")
+    if positions is not None and positions.dtype != torch.int32:
+        raise ValueError("positions must be int32")
+    L = _lib.load()
+    check(L.merlin_gemm_qkv_rope(_stream(), a.data_ptr(), lda, w_qkv.data_ptr(), ldb, out.data_ptr(), ldc,
+                                 rope_cos.data_ptr(), rope_sin.data_ptr(), _ptr(positions), M, N, K,
+                                 2 * N // 3, seq_len, cta_group or DEFAULT_CTA_GROUP),
+          "merlin_gemm_qkv_rope")
+    return out
+
+
+def flash_attn(qkv: torch.Tensor, batch: int, seq: int, heads: int, head_dim: int, *, causal: bool,
+               seqlens: Optional[torch.Tensor] = None, return_lse: bool = False,
+               softmax_scale: float = 0.0, out: Optional[torch.Tensor] = None):
+    """qkv [batch*seq, 3*heads*head_dim] packed [q|k|v] -> out [batch*seq, heads*head_dim]."""
+    M, N, ld = _rows2d(qkv, "qkv")
+    if M != batch * seq or N != 3 * heads * head_dim:
+        raise ValueError(f"flash_attn: qkv shape {tuple(qkv.shape)} != ({batch * seq}, {3 * heads * head_dim})")
+    if out is None:
+        out = torch.empty((M, heads * head_dim), dtype=_BF16, device=qkv.device)
+    _, _, ldo = _rows2d(out, "out")
+    lse = torch.empty((batch, heads, seq), dtype=torch.float32, device=qkv.device) if return_lse else None
+    if seqlens is not None and (seqlens.dtype != torch.int32 or seqlens.numel() != batch):
+        raise ValueError("flash_attn: seqlens must be int32 [batch]")
+    L = _lib.load()
+    check(L.merlin_flash_attn_fwd(_stream(), qkv.data_ptr(), ld, out.data_ptr(), ldo, _ptr(lse),
+                                  _ptr(seqlens), batch, seq, heads, head_dim, int(causal),
+                                  float(softmax_scale)), "merlin_flash_attn_fwd")
+    return (out, lse) if return_lse else out
+
+
+def rmsnorm(x: torch.Tensor, weight: torch.Tensor, eps: float, out: Optional[torch.Tensor] = None) -> torch.Tensor:
+    M, D, ldx = _rows2d(x, "x")
+    if out is None:
+        out = torch.empty((M, D), dtype=_BF16, device=x.device)
+    _, _, ldy = _rows2d(out, "out")
+    check(_lib.load().merlin_rmsnorm(_stream(), x.data_ptr(), ldx, weight.data_ptr(), out.data_ptr(), ldy,
+                                     M, D, float(eps)), "merlin_rmsnorm")
+    return out
+
+
+def layernorm(x: torch.Tensor, weight: torch.Tensor, bias: torch.Tensor, eps: float,
+              out: Optional[torch.Tensor] = None) -> torch.Tensor:
+    M, D, ldx = _rows2d(x, "x")
+    if out is None:
+        out = torch.empty((M, D), dtype=_BF16, device=x.device)
+    _, _, ldy = _rows2d(out, "out")
+    check(_lib.load().merlin_layernorm(_stream(), x.data_ptr(), ldx, weight.data_ptr(), bias.data_ptr(),
+                                       out.data_ptr(), ldy, M, D, float(eps)), "merlin_layernorm")
+    return out
+
+
+def patch_im2col(pixels: torch.Tensor, patch: int, ld_col: int) -> torch.Tensor:
+    """pixels [n,3,HW,HW] bf16 -> col [n*(HW/patch)^2, ld_col] (zero padded beyond 3*patch*patch)."""
+    if pixels.dtype != _BF16 or not pixels.is_contiguous() or pixels.dim() != 4 or pixels.shape[1] != 3:
+        raise ValueError("patch_im2col: pixels must be contiguous bf16 [n,3,H,W]")
+    n, _, hw, hw2 = pixels.shape
+    if hw != hw2:
+        raise ValueError("patch_im2col: square images only")
+    g = hw // patch
+    col = torch.empty((n * g * g, ld_col), dtype=_BF16, device=pixels.device)
+    check(_lib.load().merlin_patch_im2col(_stream(), pixels.data_ptr(), col.data_ptr(), n, hw, patch, ld_col),
+          "merlin_patch_im2col")
+    return col
+
+
+def vit_embed_ln(patch_out: torch.Tensor, class_embedding: torch.Tensor, position_embedding: torch.Tensor,
+                 ln_w: torch.Tensor, ln_b: torch.Tensor, n_img: int, eps: float) -> torch.Tensor:
+    tokens, D = position_embedding.shape
+    hidden = torch.empty((n_img * tokens, D), dtype=_BF16, device=patch_out.device)
+    check(_lib.load().merlin_vit_embed_ln(_stream(), patch_out.data_ptr(), class_embedding.data_ptr(),
+                                          position_embedding.data_ptr(), ln_w.data_ptr(), ln_b.data_ptr(),
+                                          hidden.data_ptr(), n_img, tokens, D, float(eps)),
+          "merlin_vit_embed_ln")
+    return hidden
+
+
+def conv3x3_im2col(feat: torch.Tensor, n_img: int, grid: int, C: int, stride: int, tok_stride: int,
+                   tok_off: int) -> torch.Tensor:
+    go = (grid + 2 - 3) // stride + 1
+    col = torch.empty((n_img * go * go, 9 * C), dtype=_BF16, device=feat.device)
+    check(_lib.load().merlin_conv3x3_im2col(_stream(), feat.data_ptr(), col.data_ptr(), n_img, grid, C,
+                                            stride, tok_stride, tok_off), "merlin_conv3x3_im2col")
+    return col
+
+
+def embed_splice(input_ids: torch.Tensor, embed_table: torch.Tensor, image_features: Optional[torch.Tensor],
+                 im_patch_token: int) -> tuple[torch.Tensor, torch.Tensor]:
+    """Returns (inputs_embeds [T, D], rank_ws) — rank_ws[T] holds the number of <im_patch> tokens."""
+    if input_ids.dtype != torch.int64 or not input_ids.is_contiguous():
+        raise ValueError("embed_splice: input_ids must be contiguous int64")
+    T = input_ids.numel()
+    V, D = embed_table.shape
+    out = torch.empty((T, D), dtype=_BF16, device=embed_table.device)
+    ws = torch.empty((T + 1,), dtype=torch.int32, device=embed_table.device)
+    nfeat = 0 if image_features is None else image_features.shape[0]
+    if image_features is not None and (not image_features.is_contiguous() or image_features.shape[1] != D):
+        raise ValueError("embed_splice: image_features must be contiguous [rows, D]")
+    check(_lib.load().merlin_embed_splice(_stream(), input_ids.data_ptr(), embed_table.data_ptr(),
+                                          _ptr(image_features), out.data_ptr(), ws.data_ptr(), T, D, nfeat,
+                                          V, im_patch_token), "merlin_embed_splice")
+    return out, ws
+
+
+def rope_qk_inplace(qkv: torch.Tensor, rope_cos: torch.Tensor, rope_sin: torch.Tensor, heads: int,
+                    seq_len: int, positions: Optional[torch.Tensor] = None) -> torch.Tensor:
+    M, _, ld = _rows2d(qkv, "qkv")
+    check(_lib.load().merlin_rope_qk_inplace(_stream(), qkv.data_ptr(), ld, rope_cos.data_ptr(),
+                                             rope_sin.data_ptr(), _ptr(positions), M, heads, seq_len),
+          "merlin_rope_qk_inplace")
+    return qkv
+
+
+def cross_entropy(logits: torch.Tensor, labels: torch.Tensor, batch: int, seq: int,
+                  ignore_index: int = -100) -> tuple[torch.Tensor, torch.Tensor]:
+    """Shifted CE over logits [batch*seq, V].  Returns (mean loss (fp32 scalar), per-row nll)."""
+    M, V, ld = _rows2d(logits, "logits")
+    if labels.dtype != torch.int64 or not labels.is_contiguous() or labels.numel() != M:
+        raise ValueError("cross_entropy: labels must be contiguous int64 [batch, seq]")
+    row = torch.empty((M,), dtype=torch.float32, device=logits.device)
+    acc = torch.empty((2,), dtype=torch.float32, device=logits.device)
+    check(_lib.load().merlin_cross_entropy_fwd(_stream(), logits.data_ptr(), ld, labels.data_ptr(), batch, seq,
+                                               V, ignore_index, row.data_ptr(), acc.data_ptr()),
+          "merlin_cross_entropy_fwd")
+    return acc[0] / acc[1], row
+
+
+def argmax(logits: torch.Tensor) -> torch.Tensor:
+    M, V, ld = _rows2d(logits, "logits")
+    out = torch.empty((M,), dtype=torch.int64, device=logits.device)
+    check(_lib.load().merlin_argmax(_stream(), logits.data_ptr(), ld, M, V, out.data_ptr()), "merlin_argmax")
+    return out
+
+
+def rope_tables(max_pos: int, head_dim: int = 128, theta: float = 10000.0, device="cuda"):
+    """fp32 cos/sin tables [max_pos, head_dim/2] from fp32 inv_freq (SURVEY §0 fact 10:
+    HF:llama/modeling_llama.py:117-135 builds inv_freq / angles in fp32; never round inv_freq to bf16)."""
+    inv_freq = 1.0 / (theta ** (torch.arange(0, head_dim, 2, dtype=torch.float32, device=device) / head_dim))
+    t = torch.arange(max_pos, dtype=torch.float32, device=device)
+    freqs = torch.outer(t, inv_freq)
+    return freqs.cos().contiguous(), freqs.sin().contiguous()
+
+
+def swiglu_interleave(gate_w: torch.Tensor, up_w: torch.Tensor) -> torch.Tensor:
+    """Pack gate/up weights [FF, D] into the [2*FF, D] layout the SwiGLU epilogue expects:
+    per 256-row tile, 128 gate rows then the matching 128 up rows.  FF must be a multiple of 128."""
+    FF, D = gate_w.shape
+    if FF % 128 != 0:
+        raise ValueError("swiglu_interleave: intermediate size must be a multiple of 128")
+    g = gate_w.view(FF // 128, 128, D)
+    u = up_w.view(FF // 128, 128, D)
+    return torch.stack((g, u), dim=1).reshape(2 * FF, D).contiguous()
