@@ -1,0 +1,327 @@
+#!/usr/bin/env python
+"""bench.py — Merlin-7B interpair prefill+decode throughput on N B200s (one process per GPU).
+
+Workload (BASELINE.json metric; SURVEY.md §8d, config C3 per GPU): one interpair sample per rank =
+5 frames of 336 px through CLIP-ViT-L/14 (23 layers used) + ConvProjector(stride 2) -> 720 visual tokens
+spliced into a 4096-token sequence -> Vicuna-7B decoder (32 layers) -> full-sequence lm_head, followed by
+32 greedy decode tokens against the KV cache.  Random-init bf16 weights (seed 0), synthetic inputs
+(seed 1234 + rank).  Ranks are independent replicas (inference has no collective):
+weak scaling, `value` = tokens all ranks processed / max-over-ranks device time.
+
+  value : inputs already resident in HBM when the timed region starts
+  e2e   : same step through the public API (model.generate) with pinned HOST inputs, H2D + D2H inside
+  roofline : the tcgen05 GEMM kernel (dominant), algorithmic FLOPs / CUDA-event time of its launches
+             inside the timed region, vs MEASURED_PEAKS.json
+  cpu_baseline / --impl reference : the oracle port of the reference's CPU path on the host cores.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import statistics
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+import torch  # noqa: E402
+
+SEQ_LEN = 4096
+N_FRAMES = 5
+DECODE_TOKENS = 32
+WORKLOAD = "Merlin-7B interpair 5-frame 336px + trajectory prompt, seq_len=4096 prefill + 32 greedy decode tokens, batch 1 per GPU"
+
+
+# ----------------------------------------------------------------------------- helpers
+def algorithmic_flops_prefill(S, n_img, D=4096, FF=11008, L=32, V=32003):
+    """forward FLOPs of the whole sample (causal attention counted at half)."""
+    dec = S * (L * (8 * D * D + 6 * D * FF + 2 * S * D) + 2 * D * V)
+    vit = n_img * (577 * 23 * (8 * 1024 ** 2 + 4 * 1024 * 4096 + 4 * 577 * 1024) + 576 * 2 * 588 * 1024)
+    proj = n_img * 144 * 2 * 9216 * D
+    return dec + vit + proj
+
+
+def read_peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        d = json.load(open(p))
+        return dict(tflops_burst=d.get("bf16_tflops", 1590.0), tflops=d.get("bf16_tflops_sustained", 1400.0),
+                    hbm=d.get("hbm_gbs", 6650.0), source="measured (MEASURED_PEAKS.json, sustained bf16)")
+    return dict(tflops_burst=1590.0, tflops=1400.0, hbm=6650.0, source="fallback (B200_PROFILING.md)")
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled DURING the timed region."""
+    Q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.index, self.rows, self.proc = index, [], None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
+                                          "-i", str(self.index), "-lms", "100"], stdout=subprocess.PIPE, text=True)
+            self.t = threading.Thread(target=self._read, daemon=True)
+            self.t.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([c.strip() for c in line.split(",")])
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except Exception:
+            self.proc.kill()
+        sm = [float(r[0]) for r in self.rows if len(r) >= 6 and r[0].replace(".", "").isdigit()]
+        mx = [float(r[1]) for r in self.rows if len(r) >= 6 and r[1].replace(".", "").isdigit()]
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        reasons = [n for i, n in enumerate(names) if any(len(r) >= 6 and r[2 + i].lower() == "active" for r in self.rows)]
+        return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": reasons, "samples": len(sm)}
+
+
+# ----------------------------------------------------------------------------- reference / CPU arm
+def cpu_reference_sample(threads=None):
+    """Oracle port of the reference CPU path, bounded sample of the SAME workload: one CLIP layer on the
+    5 frames, one Vicuna-7B decoder layer at S=4096, the lm_head on 256 rows, and one cached decode layer
+    step at context 4096 — bf16 weights/activations like the reference's training cast (builder.py:163),
+    all host threads.  Extrapolated to the whole step by layer counts (stated in `sample`)."""
+    from oracle import merlin_oracle as O
+    threads = threads or os.cpu_count()
+    torch.set_num_threads(threads)
+    cfg = O.OracleConfig(num_layers=1, vit_layers=2)
+    g = torch.Generator().manual_seed(0)
+    bf = torch.bfloat16
+
+    def rnd(*shape, std=0.02):
+        return torch.empty(*shape, dtype=torch.float32).normal_(0, std, generator=g).to(bf)
+
+    D, FF, d, ff = 4096, 11008, 1024, 4096
+    sd = {}
+    p = "model.layers.0."
+    for n in "qkvo":
+        sd[p + f"self_attn.{n}_proj.weight"] = rnd(D, D)
+    sd[p + "mlp.gate_proj.weight"], sd[p + "mlp.up_proj.weight"], sd[p + "mlp.down_proj.weight"] = rnd(FF, D), rnd(FF, D), rnd(D, FF)
+    sd[p + "input_layernorm.weight"] = sd[p + "post_attention_layernorm.weight"] = torch.ones(D, dtype=bf)
+    sd["model.norm.weight"] = torch.ones(D, dtype=bf)
+    vp = O.VT + "encoder.layers.0."
+    for n in ("q", "k", "v", "out"):
+        sd[vp + f"self_attn.{n}_proj.weight"], sd[vp + f"self_attn.{n}_proj.bias"] = rnd(d, d, std=0.03), torch.zeros(d, dtype=bf)
+    for n in ("layer_norm1", "layer_norm2"):
+        sd[vp + n + ".weight"], sd[vp + n + ".bias"] = torch.ones(d, dtype=bf), torch.zeros(d, dtype=bf)
+    sd[vp + "mlp.fc1.weight"], sd[vp + "mlp.fc1.bias"] = rnd(ff, d, std=0.03), torch.zeros(ff, dtype=bf)
+    sd[vp + "mlp.fc2.weight"], sd[vp + "mlp.fc2.bias"] = rnd(d, ff, std=0.015), torch.zeros(d, dtype=bf)
+    head = rnd(32003, D)
+    x = rnd(1, SEQ_LEN, D, std=1.0)
+    xv = rnd(N_FRAMES, 577, d, std=1.0)
+    with torch.no_grad():
+        t0 = time.perf_counter()
+        O.clip_encoder_layer(sd, cfg, 0, xv)
+        t_vit = time.perf_counter() - t0
+        t0 = time.perf_counter()
+        cache = [None]
+        h = O.decoder_forward(sd, cfg, x, None, torch.arange(SEQ_LEN), cache)
+        t_dec = time.perf_counter() - t0
+        t0 = time.perf_counter()
+        torch.nn.functional.linear(h[:, :256], head)
+        t_head = (time.perf_counter() - t0) * (SEQ_LEN / 256)
+        t0 = time.perf_counter()
+        O.decoder_forward(sd, cfg, x[:, :1], None, torch.tensor([SEQ_LEN]), cache)
+        torch.nn.functional.linear(h[:, :1], head)
+        t_step = time.perf_counter() - t0
+    total = 23 * t_vit + 32 * t_dec + t_head + DECODE_TOKENS * (32 * t_step)
+    sample = (f"1 of 23 CLIP layers x{N_FRAMES} frames ({t_vit:.2f}s), 1 of 32 decoder layers at S={SEQ_LEN} ({t_dec:.2f}s), "
+              f"lm_head on 256 of {SEQ_LEN} rows, 1 cached decode layer step at ctx {SEQ_LEN} ({t_step * 1e3:.0f}ms); "
+              f"step time extrapolated by layer counts = {total:.1f}s; oracle port, bf16, {threads} threads")
+    return (SEQ_LEN + DECODE_TOKENS) / total, total, sample, threads
+
+
+def run_reference_arm(args, rank):
+    if rank != 0:
+        return
+    vals = []
+    for i in range(args.warmup + args.steps):
+        v, total, sample, threads = cpu_reference_sample()
+        if i >= args.warmup:
+            vals.append((v, total))
+    v = statistics.mean(x[0] for x in vals)
+    ms = statistics.mean(x[1] for x in vals) * 1e3
+    line = {"impl": "reference", "metric": "tokens/sec (prefill+decode) Merlin-7B 5-frame interpair", "value": v,
+            "unit": "tokens/s", "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms,
+            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
+            "config": {"workload": WORKLOAD, "timing": "host wall clock, extrapolated from a bounded per-layer sample"},
+            "cpu_baseline": {"value": v, "unit": "tokens/s", "cores": threads, "kind": "port", "sample": sample},
+            "e2e": {"value": v, "unit": "tokens/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+            "gpu_launches": 0}
+    print(json.dumps(line), flush=True)
+
+
+# ----------------------------------------------------------------------------- our arm
+def build_model(device):
+    from types import SimpleNamespace
+
+    from merlin_b200.mmgpt.model.mmgpt.llama_mmgpt import MMGPTLlamaForCausalLM, vicuna_7b_config
+    from merlin_b200.mmgpt.model.projector.builder import build_projector
+    from merlin_b200.mmgpt.model.vision_encoder.builder import build_vision_tower
+    torch.manual_seed(0)
+    prev = torch.get_default_dtype()
+    torch.set_default_dtype(torch.bfloat16)
+    try:
+        with torch.device(device):
+            model = MMGPTLlamaForCausalLM(vicuna_7b_config())
+            margs = SimpleNamespace(vision_tower="clip-vit-large-patch14-336", vision_select_layer=-2,
+                                    vision_select_feature="patch", freeze_vision_tower=True, freeze_projector=True,
+                                    conv_stride=2, projector="conv", model_name_or_path=None)
+            tower = build_vision_tower(margs)
+            for prm in tower.parameters():  # CLIP-like random init (zeros would make the ViT degenerate)
+                if prm.dim() >= 2:
+                    prm.data.normal_(0.0, 0.02)
+            for lst in (tower.ln1_w, tower.ln2_w):
+                for prm in lst:
+                    prm.data.fill_(1.0)
+            tower.pre_ln_w.data.fill_(1.0)
+            tower.patch_weight.data[:, tower.k_patch:] = 0
+            model.get_model().vision_tower = tower
+            model.get_model().projector = build_projector(margs, tower.hidden_size, 4096)
+    finally:
+        torch.set_default_dtype(prev)
+    model.eval()
+    return model
+
+
+def make_inputs(rank):
+    g = torch.Generator().manual_seed(1234 + rank)
+    ids = [1]
+    for _ in range(N_FRAMES):
+        ids += [32001] + [32000] * 144 + [32002, 13]
+    n_text = SEQ_LEN - len(ids) - 1
+    ids += torch.randint(3, 32000, (n_text,), generator=g).tolist() + [2]
+    input_ids = torch.tensor([ids], dtype=torch.int64).pin_memory()
+    images = torch.empty(N_FRAMES, 3, 336, 336).normal_(0, 1, generator=g).pin_memory()
+    return input_ids, images
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    args = ap.parse_args()
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if args.impl == "reference":
+        run_reference_arm(args, rank)
+        return
+    if args.warmup < 3:
+        args.warmup = 3
+    import torch.distributed as dist
+    from merlin_b200 import ops
+    torch.cuda.set_device(local)
+    device = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=device)
+
+    model = build_model(device)
+    input_ids_h, images_h = make_inputs(rank)
+    ids_d = input_ids_h.to(device)
+    img_d = images_h.to(device=device, dtype=torch.bfloat16)
+
+    def step_device():
+        return model.generate(ids_d, images=[img_d], max_new_tokens=DECODE_TOKENS, eos_token_id=None)
+
+    def step_host():
+        ids = input_ids_h.to(device, non_blocking=True)
+        img = images_h.to(device, non_blocking=True).to(torch.bfloat16)
+        out = model.generate(ids, images=[img], max_new_tokens=DECODE_TOKENS, eos_token_id=None)
+        return out[:, SEQ_LEN:].cpu()   # device -> host read of the step's result (generated ids)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def timed(fn, steps, profile=False):
+        barrier()
+        ops.PROFILE.reset(enabled=profile)
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        launches0 = ops.PROFILE.launches
+        e0.record()
+        for _ in range(steps):
+            fn()
+        e1.record()
+        barrier()
+        ms = e0.elapsed_time(e1)
+        t = torch.tensor([ms], device=device)
+        if world > 1:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return t.item(), ops.PROFILE.launches - launches0
+
+    for _ in range(args.warmup):
+        step_device()
+    sampler = ClockSampler(local)
+    sampler.start()
+    total_ms, launches = timed(step_device, args.steps, profile=True)
+    clocks = sampler.stop()
+    gemm_flops, gemm_ms, gemm_n = ops.PROFILE.gemm_summary()
+    # sub-metrics (untimed region of the contract: extra information only)
+    pre_ms, _ = timed(lambda: model(input_ids=ids_d, images=[img_d]), max(2, args.steps // 2))
+    pre_ms /= max(2, args.steps // 2)
+    step_host()
+    e2e_ms, _ = timed(step_host, args.steps)
+
+    tokens = SEQ_LEN + DECODE_TOKENS
+    ms_per_step = total_ms / args.steps
+    value = world * tokens / (ms_per_step / 1e3)
+    e2e_value = world * tokens / (e2e_ms / args.steps / 1e3)
+    peaks = read_peaks()
+    achieved = gemm_flops / (gemm_ms / 1e3) / 1e12 if gemm_ms > 0 else 0.0
+    dec_ms = max(ms_per_step - pre_ms, 1e-6)
+    fl = algorithmic_flops_prefill(SEQ_LEN, N_FRAMES)
+    line = {
+        "metric": "tokens/sec (prefill+decode) Merlin-7B 5-frame interpair", "value": value, "unit": "tokens/s",
+        "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_per_step,
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
+        "config": {"workload": WORKLOAD, "parallelism": f"replicas x{world} (inference: no collective)",
+                   "l2": "inputs larger than L2: 14 GB of bf16 weights are streamed every step",
+                   "weights": "random-init seed 0, Vicuna-7B-v1.5 + CLIP-L/14-336 + ConvProjector(s=2) dims"},
+        "e2e": {"value": e2e_value, "unit": "tokens/s", "h2d_bytes_per_step": input_ids_h.numel() * 8 + images_h.numel() * 4,
+                "d2h_bytes_per_step": DECODE_TOKENS * 8},
+        "gpu_launches": launches,
+        "clocks": clocks,
+        "roofline": {"bound": "tensor", "achieved": achieved, "peak": peaks["tflops"], "unit": "TFLOP/s",
+                     "frac": achieved / peaks["tflops"], "traffic": None, "kernel": "gemm_bf16_kernel<2> (tcgen05, cta_group::2)",
+                     "launches_timed": gemm_n, "peak_source": peaks["source"], "frac_of_burst": achieved / peaks["tflops_burst"]},
+        "detail": {"prefill_ms": pre_ms, "prefill_tokens_per_s_per_gpu": SEQ_LEN / (pre_ms / 1e3),
+                   "prefill_model_tflops": fl / (pre_ms / 1e3) / 1e12,
+                   "prefill_frac_of_sustained_peak": fl / (pre_ms / 1e3) / 1e12 / peaks["tflops"],
+                   "decode_ms_per_token": dec_ms / DECODE_TOKENS, "decode_tokens_per_s": DECODE_TOKENS / (dec_ms / 1e3),
+                   "decode_hbm_frac": (13.48e9 + 0.524e6 * SEQ_LEN) / (dec_ms / DECODE_TOKENS / 1e3) / 1e9 / peaks["hbm"]},
+    }
+    if rank == 0 and world == 1:
+        try:
+            v, total, sample, threads = cpu_reference_sample()
+            line["cpu_baseline"] = {"value": v, "unit": "tokens/s", "cores": threads, "kind": "port", "sample": sample}
+        except Exception as e:  # the checker must never break the bench line
+            line["cpu_baseline"] = {"value": None, "unit": "tokens/s", "cores": os.cpu_count(), "kind": "port",
+                                    "sample": f"failed: {e}"}
+    if rank == 0:
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

@@ -13,6 +13,7 @@
 #ifndef MERLIN_B200_H_
 #define MERLIN_B200_H_
 
+#include <stddef.h>
 #include <stdint.h>
 
 #ifdef __cplusplus
@@ -94,14 +95,17 @@ int merlin_vit_embed_ln(void* stream, const void* patch_out, const void* class_e
 int merlin_conv3x3_im2col(void* stream, const void* feat, void* col, int n_img, int grid, int C,
                           int stride, int tok_stride, int tok_off);
 
-/* inputs_embeds[t] = image_features[rank(t)] if input_ids[t] == im_patch_token (rank = number of
- * earlier <im_patch> tokens in flattened batch order) else embed_table[input_ids[t]].  Bit-exact row
- * copies.  rank_ws: T+1 ints of scratch; rank_ws[T] receives the number of <im_patch> tokens.
- * Replaces embed_tokens + the per-image torch.cat splice of prepare_inputs_labels_for_multimodal
- * (mmgpt/model/mmgpt/base_mmgpt.py:99-160). */
+/* inputs_embeds[b,t] = image_features[feat_offset[b] + r] if input_ids[b,t] == im_patch_token, where
+ * r = number of earlier <im_patch> tokens of sample b (and r < feat_limit[b]); otherwise
+ * embed_table[input_ids[b,t]].  Bit-exact row copies.  feat_offset / feat_limit: int32 [B] device
+ * arrays (NULL = 0 / unlimited).  rank_ws: B*S + B ints of scratch; rank_ws[B*S + b] receives the
+ * number of <im_patch> tokens of sample b (the host checks it against the image count).
+ * Replaces embed_tokens + the per-sample / per-image torch.cat splice of
+ * prepare_inputs_labels_for_multimodal (mmgpt/model/mmgpt/base_mmgpt.py:99-160). */
 int merlin_embed_splice(void* stream, const int64_t* input_ids, const void* embed_table,
-                        const void* image_features, void* inputs_embeds, int* rank_ws, int T, int D,
-                        int n_feature_rows, int64_t vocab, int64_t im_patch_token);
+                        const void* image_features, void* inputs_embeds, int* rank_ws, int B, int S, int D,
+                        int n_feature_rows, const int* feat_offset, const int* feat_limit, int64_t vocab,
+                        int64_t im_patch_token);
 
 /* In-place half-split RoPE on the q and k blocks (H heads of 128 each) of packed qkv rows.
  * Stand-alone form of the merlin_gemm_qkv_rope epilogue (HF:llama/modeling_llama.py:138-168). */
@@ -118,6 +122,43 @@ int merlin_cross_entropy_fwd(void* stream, const void* logits, int64_t ld, const
 
 /* out[r] = argmax_v logits[r, v] (lowest index on ties, as torch.argmax): greedy decoding. */
 int merlin_argmax(void* stream, const void* logits, int64_t ld, int rows, int V, int64_t* out);
+
+/* ---- decode (one new token against the KV cache; HBM-bound GEMV + split-K flash-decode kernels) ----
+ * Replaces the HF eager decode step the reference reaches through generate()
+ * (llama_mmgpt.py:114-134 -> LlamaModel with past_key_values).  Batch 1, head_dim 128. */
+typedef struct merlin_decoder_weights {
+  int num_layers, hidden, heads, intermediate, vocab;
+  float rms_eps;
+  const void* const* qkv_w;     /* [L] -> [3*hidden, hidden]   q|k|v rows                          */
+  const void* const* o_w;       /* [L] -> [hidden, hidden]                                        */
+  const void* const* gate_up_w; /* [L] -> [2*intermediate, hidden], gate/up interleaved per 128   */
+  const void* const* down_w;    /* [L] -> [hidden, intermediate]                                  */
+  const void* const* ln1_w;     /* [L] -> [hidden] input_layernorm                                */
+  const void* const* ln2_w;     /* [L] -> [hidden] post_attention_layernorm                       */
+  const void* norm_w;           /* [hidden] final norm                                            */
+  const void* lm_head_w;        /* [vocab, hidden]                                                */
+  void* const* kv_cache;        /* [L] -> [capacity, 2*hidden] bf16, row t = [k_t (rotated) | v_t] */
+  const float* rope_cos;        /* [max_pos, 64] fp32                                             */
+  const float* rope_sin;
+} merlin_decoder_weights;
+
+/* Bytes of scratch merlin_decode_step needs. */
+size_t merlin_decode_workspace_bytes(int hidden, int intermediate, int heads, int n_splits);
+
+/* One decoder pass for the token whose embedding is x[hidden] (bf16, overwritten with the final
+ * residual stream) at position *pos_dev: appends its k/v to every layer's cache row *pos_dev, attends
+ * over rows 0..*pos_dev, and writes logits[vocab] (bf16).  The position lives in device memory so
+ * the call can be captured in a CUDA graph and replayed. */
+int merlin_decode_step(void* stream, const merlin_decoder_weights* w, void* x, const int* pos_dev,
+                       void* workspace, void* logits, int n_splits);
+
+/* x[D] = embed_table[*token_dev] (token id read on the device). */
+int merlin_embed_token(void* stream, const void* embed_table, const int64_t* token_dev, void* x, int D,
+                       int64_t vocab);
+
+/* out_ids[*n_out_dev] = *token_dev; ++*n_out_dev; ++*pos_dev  — closes one greedy step on the device. */
+int merlin_record_advance(void* stream, const int64_t* token_dev, int64_t* out_ids, int* n_out_dev,
+                          int* pos_dev, int capacity);
 
 #ifdef __cplusplus
 }

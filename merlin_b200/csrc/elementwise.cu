@@ -243,18 +243,24 @@ __global__ void conv3x3_im2col_kernel(const __nv_bfloat16* __restrict__ feat, __
     dst[i] = inside ? src[i] : make_uint4(0, 0, 0, 0);
 }
 
-// Exclusive rank of every <im_patch> token (flattened batch order); rank[t] = -1 for other tokens.
-// Single block; total = number of patch tokens.
+// Per sample b (one block each): exclusive rank of every <im_patch> token inside the sample, offset by
+// feat_offset[b] into the flat feature buffer; tokens that are not <im_patch>, or whose rank exceeds
+// feat_limit[b] (more placeholders than feature rows), get -1.  counts[b] = #<im_patch> in sample b.
 __global__ void __launch_bounds__(1024)
-patch_rank_kernel(const int64_t* __restrict__ ids, int* __restrict__ rank, int* __restrict__ total, int T,
-                  int64_t patch_id) {
+patch_rank_kernel(const int64_t* __restrict__ ids, int* __restrict__ rank, int* __restrict__ counts, int S,
+                  int64_t patch_id, const int* __restrict__ feat_offset, const int* __restrict__ feat_limit) {
   __shared__ int warp_tot[32];
   __shared__ int carry;
+  const int b = blockIdx.x;
+  const int64_t* row_ids = ids + static_cast<size_t>(b) * S;
+  int* row_rank = rank + static_cast<size_t>(b) * S;
+  const int off = feat_offset ? feat_offset[b] : 0;
+  const int lim = feat_limit ? feat_limit[b] : 0x7fffffff;
   if (threadIdx.x == 0) carry = 0;
   __syncthreads();
-  for (int base = 0; base < T; base += 1024) {
+  for (int base = 0; base < S; base += 1024) {
     const int t = base + threadIdx.x;
-    const int flag = (t < T && ids[t] == patch_id) ? 1 : 0;
+    const int flag = (t < S && row_ids[t] == patch_id) ? 1 : 0;
     int incl = flag;
 #pragma unroll
     for (int o = 1; o < 32; o <<= 1) {
@@ -275,12 +281,12 @@ patch_rank_kernel(const int64_t* __restrict__ ids, int* __restrict__ rank, int* 
     __syncthreads();
     const int warp_excl = (threadIdx.x >> 5) ? warp_tot[(threadIdx.x >> 5) - 1] : 0;
     const int excl = carry + warp_excl + incl - flag;
-    if (t < T) rank[t] = flag ? excl : -1;
+    if (t < S) row_rank[t] = (flag && excl < lim) ? off + excl : -1;
     __syncthreads();
     if (threadIdx.x == 0) carry += warp_tot[31];
     __syncthreads();
   }
-  if (threadIdx.x == 0) *total = carry;
+  if (threadIdx.x == 0) counts[b] = carry;
 }
 
 // inputs_embeds[t] = (rank[t] >= 0) ? image_features[rank[t]] : embed_tokens[ids[t]]
@@ -473,18 +479,20 @@ int merlin_conv3x3_im2col(void* stream, const void* feat, void* col, int n_img, 
 }
 
 int merlin_embed_splice(void* stream, const int64_t* input_ids, const void* embed_table,
-                        const void* image_features, void* inputs_embeds, int* rank_ws, int T, int D,
-                        int n_feature_rows, int64_t vocab, int64_t im_patch_token) {
+                        const void* image_features, void* inputs_embeds, int* rank_ws, int B, int S, int D,
+                        int n_feature_rows, const int* feat_offset, const int* feat_limit, int64_t vocab,
+                        int64_t im_patch_token) {
   MB_CHECK_ARG(input_ids && embed_table && inputs_embeds && rank_ws, "embed_splice: null tensor");
-  MB_CHECK_ARG(T >= 0 && D % 8 == 0, "embed_splice: D %% 8 != 0");
+  MB_CHECK_ARG(B >= 0 && S >= 0 && D % 8 == 0, "embed_splice: D %% 8 != 0");
   MB_CHECK_ARG(n_feature_rows == 0 || image_features, "embed_splice: feature rows without a tensor");
-  if (T == 0) return MERLIN_OK;
+  if (B * S == 0) return MERLIN_OK;
   cudaStream_t st = static_cast<cudaStream_t>(stream);
-  patch_rank_kernel<<<1, 1024, 0, st>>>(input_ids, rank_ws, rank_ws + T, T, im_patch_token);
-  embed_splice_kernel<<<T, 256, 0, st>>>(input_ids, rank_ws, static_cast<const __nv_bfloat16*>(embed_table),
-                                         static_cast<const __nv_bfloat16*>(image_features),
-                                         static_cast<__nv_bfloat16*>(inputs_embeds), D, n_feature_rows,
-                                         vocab);
+  patch_rank_kernel<<<B, 1024, 0, st>>>(input_ids, rank_ws, rank_ws + static_cast<size_t>(B) * S, S,
+                                        im_patch_token, feat_offset, feat_limit);
+  embed_splice_kernel<<<B * S, 256, 0, st>>>(input_ids, rank_ws, static_cast<const __nv_bfloat16*>(embed_table),
+                                             static_cast<const __nv_bfloat16*>(image_features),
+                                             static_cast<__nv_bfloat16*>(inputs_embeds), D, n_feature_rows,
+                                             vocab);
   MB_CHECK_CUDA(cudaGetLastError());
   return MERLIN_OK;
 }

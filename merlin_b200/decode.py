@@ -1,0 +1,123 @@
+"""Decode-step driver: binds a model + KV cache to merlin_decode_step and (for greedy decoding)
+captures embed -> decoder -> argmax -> advance into one CUDA graph that is replayed per token, so the
+launch-bound loop of 32 layers x 5 kernels costs one graph launch (SURVEY.md K12 / §3.3 hot loop #4).
+"""
+from __future__ import annotations
+
+import ctypes
+from ctypes import c_void_p
+
+import torch
+
+from . import lib as _lib
+from . import ops as _ops
+from .lib import DecoderWeights, check
+
+N_SPLITS = 16  # flash-decode key splits: 32 heads x 16 = 512 CTAs per layer
+
+
+def _ptr_array(tensors):
+    arr = (c_void_p * len(tensors))(*[t.data_ptr() for t in tensors])
+    return arr
+
+
+class DecodeRunner:
+    def __init__(self, lm, cache):
+        m, cfg = lm.model, lm.config
+        self.lm, self.cache = lm, cache
+        dev = lm.device
+        if cache.kv[0].shape[0] != 1:
+            raise NotImplementedError("decode kernels handle batch 1")
+        L = cfg.num_hidden_layers
+        cos, sin = m.rope_tables(cache.capacity)
+        self._keep = [_ptr_array(list(m.qkv_w)), _ptr_array(list(m.o_w)), _ptr_array(list(m.gate_up_w)),
+                      _ptr_array(list(m.down_w)), _ptr_array(list(m.ln1_w)), _ptr_array(list(m.ln2_w)),
+                      _ptr_array(cache.kv), cos, sin]
+        cast = lambda a: ctypes.cast(a, ctypes.POINTER(c_void_p))
+        self.w = DecoderWeights(L, cfg.hidden_size, cfg.num_attention_heads, cfg.intermediate_size,
+                                cfg.vocab_size, float(cfg.rms_norm_eps), cast(self._keep[0]), cast(self._keep[1]),
+                                cast(self._keep[2]), cast(self._keep[3]), cast(self._keep[4]), cast(self._keep[5]),
+                                m.norm_w.data_ptr(), lm.lm_head_w.data_ptr(), cast(self._keep[6]),
+                                cos.data_ptr(), sin.data_ptr())
+        L_ = _lib.load()
+        nbytes = L_.merlin_decode_workspace_bytes(cfg.hidden_size, cfg.intermediate_size,
+                                                  cfg.num_attention_heads, N_SPLITS)
+        self.ws = torch.empty(nbytes, dtype=torch.uint8, device=dev)
+        self.x = torch.empty(cfg.hidden_size, dtype=torch.bfloat16, device=dev)
+        self.logits = torch.empty((1, (cfg.vocab_size + 7) // 8 * 8), dtype=torch.bfloat16, device=dev)[:, :cfg.vocab_size]
+        self.pos = torch.zeros(1, dtype=torch.int32, device=dev)
+        self.token = torch.zeros(1, dtype=torch.int64, device=dev)
+        self.n_out = torch.zeros(1, dtype=torch.int32, device=dev)
+        self.out_ids = torch.zeros(max(cache.capacity, 16), dtype=torch.int64, device=dev)
+        self.graph = None
+        self.launches_per_step = 5 * L + 1 + 2 * L  # gemv x4 + flash partial/combine per layer + lm_head
+
+    # -- one decoder pass for an externally supplied embedding (used by forward(past_key_values=...))
+    def step_logits(self, embeds: torch.Tensor) -> torch.Tensor:
+        """embeds [1, D] -> logits [1, V]; appends to the cache at position cache.seq_len."""
+        if self.cache.seq_len >= self.cache.capacity:
+            raise RuntimeError("KV cache is full")
+        self.x.copy_(embeds.reshape(-1))
+        self.pos.fill_(self.cache.seq_len)
+        L_ = _lib.load()
+        check(L_.merlin_decode_step(torch.cuda.current_stream().cuda_stream, ctypes.byref(self.w),
+                                    self.x.data_ptr(), self.pos.data_ptr(), self.ws.data_ptr(),
+                                    self.logits.data_ptr(), N_SPLITS), "merlin_decode_step")
+        self.cache.seq_len += 1
+        _ops.PROFILE.launches += self.launches_per_step
+        return self.logits
+
+    # -- device-resident greedy loop
+    def _greedy_body(self):
+        L_ = _lib.load()
+        st = torch.cuda.current_stream().cuda_stream
+        cfg = self.lm.config
+        check(L_.merlin_embed_token(st, self.lm.model.embed_tokens.data_ptr(), self.token.data_ptr(),
+                                    self.x.data_ptr(), cfg.hidden_size, cfg.vocab_size), "merlin_embed_token")
+        check(L_.merlin_decode_step(st, ctypes.byref(self.w), self.x.data_ptr(), self.pos.data_ptr(),
+                                    self.ws.data_ptr(), self.logits.data_ptr(), N_SPLITS), "merlin_decode_step")
+        check(L_.merlin_argmax(st, self.logits.data_ptr(), self.logits.stride(0), 1, cfg.vocab_size,
+                               self.token.data_ptr()), "merlin_argmax")
+        check(L_.merlin_record_advance(st, self.token.data_ptr(), self.out_ids.data_ptr(),
+                                       self.n_out.data_ptr(), self.pos.data_ptr(), self.out_ids.numel()),
+              "merlin_record_advance")
+
+    def greedy(self, first_token: torch.Tensor, n_tokens: int, eos_token_id=None, check_every: int = 16,
+               use_graph: bool = True) -> torch.Tensor:
+        """Feeds `first_token` (already chosen from the prefill logits) and decodes n_tokens more
+        greedily without host round trips; returns the generated ids (truncated after eos)."""
+        n_tokens = min(n_tokens, self.cache.capacity - self.cache.seq_len)
+        self.token.copy_(first_token.reshape(1))
+        self.pos.fill_(self.cache.seq_len)
+        self.n_out.zero_()
+        if use_graph and self.graph is None:
+            self._greedy_body()  # warm-up outside capture (one-time kernel attributes)
+            self.token.copy_(first_token.reshape(1))
+            self.pos.fill_(self.cache.seq_len)
+            self.n_out.zero_()
+            torch.cuda.synchronize()
+            g = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(g):
+                self._greedy_body()
+            self.graph = g
+            self.token.copy_(first_token.reshape(1))
+            self.pos.fill_(self.cache.seq_len)
+            self.n_out.zero_()
+        done = 0
+        while done < n_tokens:
+            chunk = min(check_every, n_tokens - done)
+            for _ in range(chunk):
+                if use_graph:
+                    self.graph.replay()
+                else:
+                    self._greedy_body()
+                _ops.PROFILE.launches += self.launches_per_step + 3
+            done += chunk
+            if eos_token_id is not None:
+                ids = self.out_ids[:done]
+                hit = (ids == eos_token_id).nonzero()
+                if hit.numel():
+                    done = int(hit[0]) + 1
+                    break
+        self.cache.seq_len += done
+        return self.out_ids[:done].clone()

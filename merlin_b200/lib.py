@@ -32,11 +32,26 @@ _PROTOTYPES = {
     "merlin_patch_im2col": [_P, _P, _P, c_int, c_int, c_int, c_int],
     "merlin_vit_embed_ln": [_P, _P, _P, _P, _P, _P, _P, c_int, c_int, c_int, c_float],
     "merlin_conv3x3_im2col": [_P, _P, _P, c_int, c_int, c_int, c_int, c_int, c_int],
-    "merlin_embed_splice": [_P, _P, _P, _P, _P, _P, c_int, c_int, c_int, c_int64, c_int64],
+    "merlin_embed_splice": [_P, _P, _P, _P, _P, _P, c_int, c_int, c_int, c_int, _P, _P, c_int64, c_int64],
     "merlin_rope_qk_inplace": [_P, _P, c_int64, _P, _P, _P, c_int, c_int, c_int],
     "merlin_cross_entropy_fwd": [_P, _P, c_int64, _P, c_int, c_int, c_int, c_int64, _P, _P],
     "merlin_argmax": [_P, _P, c_int64, c_int, c_int, _P],
+    "merlin_decode_step": [_P, _P, _P, _P, _P, _P, c_int],
+    "merlin_embed_token": [_P, _P, _P, _P, c_int, c_int64],
+    "merlin_record_advance": [_P, _P, _P, _P, _P, c_int],
 }
+
+
+class DecoderWeights(ctypes.Structure):
+    """struct merlin_decoder_weights (include/merlin_b200.h)."""
+    _fields_ = [("num_layers", c_int), ("hidden", c_int), ("heads", c_int), ("intermediate", c_int),
+                ("vocab", c_int), ("rms_eps", c_float),
+                ("qkv_w", ctypes.POINTER(c_void_p)), ("o_w", ctypes.POINTER(c_void_p)),
+                ("gate_up_w", ctypes.POINTER(c_void_p)), ("down_w", ctypes.POINTER(c_void_p)),
+                ("ln1_w", ctypes.POINTER(c_void_p)), ("ln2_w", ctypes.POINTER(c_void_p)),
+                ("norm_w", c_void_p), ("lm_head_w", c_void_p),
+                ("kv_cache", ctypes.POINTER(c_void_p)),
+                ("rope_cos", c_void_p), ("rope_sin", c_void_p)]
 
 
 def declared_symbols(header: str = _HEADER) -> list[str]:
@@ -66,6 +81,8 @@ def load() -> ctypes.CDLL:
     lib = ctypes.CDLL(path)
     lib.merlin_last_error.restype = c_char_p
     lib.merlin_last_error.argtypes = []
+    lib.merlin_decode_workspace_bytes.restype = ctypes.c_size_t
+    lib.merlin_decode_workspace_bytes.argtypes = [c_int, c_int, c_int, c_int]
     for name, argtypes in _PROTOTYPES.items():
         fn = getattr(lib, name)
         fn.restype = c_int

@@ -1,0 +1,438 @@
+"""MMGPTLlamaForCausalLM (alias MerlinForCausalLM) on B200 kernels.
+
+Mirror of mmgpt/model/mmgpt/llama_mmgpt.py:27-138 — `MMGPTConfig`, `MMGPTLlamaModel`,
+`MMGPTLlamaForCausalLM.forward(input_ids, attention_mask, past_key_values, inputs_embeds, labels,
+use_cache, output_attentions, output_hidden_states, images, return_dict)`,
+`prepare_inputs_for_generation`, and a `generate(input_ids, images=..., ...)` with the call shape the
+reference's eval/serve code uses (eval_mmvet.py:101-120, model_worker.py:169-180).
+
+The decoder stack (HF LlamaModel + the flash-attn monkey patch) runs per layer as
+  rmsnorm -> [fused QKV tcgen05 GEMM with RoPE epilogue] -> causal flash-attention (tcgen05/TMEM)
+  -> [o_proj GEMM + residual epilogue] -> rmsnorm -> [gate|up GEMM + SwiGLU epilogue]
+  -> [down GEMM + residual epilogue]
+through libmerlin_b200.so; there is no PyTorch fallback.  Weights are stored packed for the kernels
+(q|k|v fused, gate/up interleaved per 128 rows); state_dict()/load_state_dict() speak the reference's
+key names.
+"""
+from __future__ import annotations
+
+import json
+import os
+from collections import OrderedDict
+from dataclasses import dataclass
+from typing import List, Optional
+
+import torch
+import torch.nn as nn
+
+from .... import decode as _decode
+from .... import ops
+from ....lib import EPI_RESIDUAL, EPI_SWIGLU
+from ...utils.constants import IGNORE_INDEX
+from .base_mmgpt import MMGPTMetaForCausalLM
+
+try:  # keep the HF config class when transformers is importable (it is in this image)
+    from transformers import LlamaConfig
+    from transformers.modeling_outputs import CausalLMOutputWithPast
+
+    class MMGPTConfig(LlamaConfig):
+        model_type = "mmgpt"
+except Exception:  # pragma: no cover
+    LlamaConfig = None
+
+    @dataclass
+    class CausalLMOutputWithPast:  # type: ignore
+        loss: Optional[torch.Tensor] = None
+        logits: Optional[torch.Tensor] = None
+        past_key_values: Optional[object] = None
+        hidden_states: Optional[tuple] = None
+        attentions: Optional[tuple] = None
+
+    class MMGPTConfig:  # type: ignore
+        model_type = "mmgpt"
+
+        def __init__(self, **kw):
+            self.__dict__.update(dict(vocab_size=32000, hidden_size=4096, intermediate_size=11008,
+                                      num_hidden_layers=32, num_attention_heads=32, rms_norm_eps=1e-5,
+                                      rope_theta=10000.0, max_position_embeddings=4096))
+            self.__dict__.update(kw)
+
+
+def vicuna_7b_config(**kw) -> "MMGPTConfig":
+    """Vicuna-7B-v1.5 dims; vocab 32003 after the three image tokens."""
+    base = dict(vocab_size=32003, hidden_size=4096, intermediate_size=11008, num_hidden_layers=32,
+                num_attention_heads=32, num_key_value_heads=32, rms_norm_eps=1e-5, rope_theta=10000.0,
+                max_position_embeddings=4096, tie_word_embeddings=False)
+    base.update(kw)
+    return MMGPTConfig(**base)
+
+
+def vicuna_13b_config(**kw) -> "MMGPTConfig":
+    base = dict(vocab_size=32003, hidden_size=5120, intermediate_size=13824, num_hidden_layers=40,
+                num_attention_heads=40, num_key_value_heads=40, rms_norm_eps=1e-5, rope_theta=10000.0,
+                max_position_embeddings=4096, tie_word_embeddings=False)
+    base.update(kw)
+    return MMGPTConfig(**base)
+
+
+class MerlinKVCache:
+    """Per-layer key/value store for generate(): kv[l] is [B, capacity, 2*D] bf16 ([k | v] per token,
+    keys already rotated).  Stands in for the legacy tuple cache the reference indexes
+    (base_mmgpt.py:88) and for HF 5.x Cache objects (`get_seq_length`)."""
+
+    def __init__(self, num_layers: int, batch: int, capacity: int, hidden: int, device):
+        self.kv = [torch.empty((batch, capacity, 2 * hidden), dtype=torch.bfloat16, device=device)
+                   for _ in range(num_layers)]
+        self.capacity = capacity
+        self.seq_len = 0
+
+    def get_seq_length(self, layer_idx: int = 0) -> int:
+        return self.seq_len
+
+    def __len__(self):
+        return len(self.kv)
+
+    def __bool__(self):  # an allocated-but-empty cache must read as "no past" 
+        return self.seq_len > 0
+
+
+class _WeightHolder(nn.Module):
+    """Gives packed parameters the `.weight` attribute HF-style callers expect
+    (get_input_embeddings().weight, get_output_embeddings().weight)."""
+
+    def __init__(self, owner, name):
+        super().__init__()
+        object.__setattr__(self, "_owner", owner)
+        self._name = name
+
+    @property
+    def weight(self):
+        return getattr(self._owner, self._name)
+
+
+class MMGPTLlamaModel(nn.Module):
+    """Decoder stack (reference: MMGPTLlamaModel(LlamaModel), llama_mmgpt.py:31-35)."""
+
+    def __init__(self, config):
+        super().__init__()
+        self.config = config
+        D, FF, L, V = config.hidden_size, config.intermediate_size, config.num_hidden_layers, config.vocab_size
+        H = config.num_attention_heads
+        if D // H != 128 or getattr(config, "num_key_value_heads", H) != H:
+            raise ValueError("MMGPTLlamaModel: kernels need head_dim 128 and MHA (Vicuna-7B/13B)")
+        if FF % 128 != 0 or D % 8 != 0:
+            raise ValueError("MMGPTLlamaModel: intermediate_size must be a multiple of 128")
+        std = getattr(config, "initializer_range", 0.02)
+
+        def W(*shape):
+            return nn.Parameter(torch.empty(*shape).normal_(0.0, std))
+
+        self.embed_tokens = W(V, D)
+        self.qkv_w = nn.ParameterList([W(3 * D, D) for _ in range(L)])
+        self.o_w = nn.ParameterList([W(D, D) for _ in range(L)])
+        self.gate_up_w = nn.ParameterList([W(2 * FF, D) for _ in range(L)])   # interleaved per 128 rows
+        self.down_w = nn.ParameterList([W(D, FF) for _ in range(L)])
+        self.ln1_w = nn.ParameterList([nn.Parameter(torch.ones(D)) for _ in range(L)])
+        self.ln2_w = nn.ParameterList([nn.Parameter(torch.ones(D)) for _ in range(L)])
+        self.norm_w = nn.Parameter(torch.ones(D))
+        self._rope = None  # (cos, sin) fp32 tables, built lazily on the parameter device
+
+    def rope_tables(self, need: int):
+        if self._rope is None or self._rope[0].shape[0] < need or self._rope[0].device != self.embed_tokens.device:
+            size = max(need, getattr(self.config, "max_position_embeddings", 4096))
+            self._rope = ops.rope_tables(size, 128, float(getattr(self.config, "rope_theta", 10000.0)),
+                                         device=self.embed_tokens.device)
+        return self._rope
+
+    def forward_layers(self, x: torch.Tensor, batch: int, seq: int, seqlens: Optional[torch.Tensor],
+                       cache: Optional[MerlinKVCache] = None, collect_hidden: bool = False):
+        """x [batch*seq, D] bf16 (modified in place) -> final-normed hidden [batch*seq, D]."""
+        cfg = self.config
+        D, H = cfg.hidden_size, cfg.num_attention_heads
+        cos, sin = self.rope_tables(seq)
+        xn = torch.empty_like(x)
+        hidden = [x.clone()] if collect_hidden else None
+        for i in range(cfg.num_hidden_layers):
+            ops.rmsnorm(x, self.ln1_w[i], cfg.rms_norm_eps, out=xn)
+            qkv = ops.gemm_qkv_rope(xn, self.qkv_w[i], cos, sin, seq)
+            if cache is not None:
+                cache.kv[i][:, :seq].copy_(qkv.view(batch, seq, 3 * D)[:, :, D:])
+            att = ops.flash_attn(qkv, batch, seq, H, 128, causal=True, seqlens=seqlens)
+            ops.gemm(att, self.o_w[i], residual=x, out=x, epilogue=EPI_RESIDUAL)
+            ops.rmsnorm(x, self.ln2_w[i], cfg.rms_norm_eps, out=xn)
+            mid = ops.gemm(xn, self.gate_up_w[i], epilogue=EPI_SWIGLU)
+            ops.gemm(mid, self.down_w[i], residual=x, out=x, epilogue=EPI_RESIDUAL)
+            if collect_hidden:
+                hidden.append(x.clone())
+        if cache is not None:
+            cache.seq_len = seq
+        out = ops.rmsnorm(x, self.norm_w, cfg.rms_norm_eps, out=xn)
+        return out, hidden
+
+
+class MMGPTLlamaForCausalLM(nn.Module, MMGPTMetaForCausalLM):
+    config_class = MMGPTConfig
+
+    def __init__(self, config):
+        super().__init__()
+        self.config = config
+        self.model = MMGPTLlamaModel(config)
+        std = getattr(config, "initializer_range", 0.02)
+        self.lm_head_w = nn.Parameter(torch.empty(config.vocab_size, config.hidden_size).normal_(0.0, std))
+        self.use_im_start_end = True
+        self.use_beam_search = False
+        self.im_patch_token, self.im_start_token, self.im_end_token = 32000, 32001, 32002
+        self.num_new_tokens = 0
+        self._decoder = None
+
+    # ------------------------------------------------------------------ HF-style accessors
+    def get_model(self):
+        return self.model
+
+    def get_input_embeddings(self):
+        return _WeightHolder(self.model, "embed_tokens")
+
+    def get_output_embeddings(self):
+        return _WeightHolder(self, "lm_head_w")
+
+    @property
+    def device(self):
+        return self.lm_head_w.device
+
+    @property
+    def dtype(self):
+        return self.lm_head_w.dtype
+
+    def resize_token_embeddings(self, new_num_tokens: int):
+        old = self.config.vocab_size
+        if new_num_tokens == old:
+            return self.get_input_embeddings()
+        for owner, name in ((self.model, "embed_tokens"), (self, "lm_head_w")):
+            w = getattr(owner, name)
+            new = torch.empty(new_num_tokens, w.shape[1], dtype=w.dtype, device=w.device).normal_(
+                0.0, getattr(self.config, "initializer_range", 0.02))
+            n = min(old, new_num_tokens)
+            new[:n] = w.data[:n]
+            setattr(owner, name, nn.Parameter(new, requires_grad=w.requires_grad))
+        self.config.vocab_size = new_num_tokens
+        return self.get_input_embeddings()
+
+    # ------------------------------------------------------------------ reference-format state dict
+    def state_dict(self, *args, destination=None, prefix="", keep_vars=False):
+        cfg = self.config
+        D, FF = cfg.hidden_size, cfg.intermediate_size
+        out = destination if destination is not None else OrderedDict()
+
+        def put(k, v):
+            out[prefix + k] = v if keep_vars else v.detach()
+
+        m = self.model
+        put("model.embed_tokens.weight", m.embed_tokens)
+        for i in range(cfg.num_hidden_layers):
+            p = f"model.layers.{i}."
+            for n, blk in (("q", 0), ("k", 1), ("v", 2)):
+                put(p + f"self_attn.{n}_proj.weight", m.qkv_w[i][blk * D:(blk + 1) * D])
+            put(p + "self_attn.o_proj.weight", m.o_w[i])
+            gu = m.gate_up_w[i].view(FF // 128, 2, 128, D)
+            # strided views of the interleaved storage; reshape() materialises a copy for export and the
+            # load path below writes through the 4-D view
+            put(p + "mlp.gate_proj.weight", gu[:, 0].reshape(FF, D))
+            put(p + "mlp.up_proj.weight", gu[:, 1].reshape(FF, D))
+            put(p + "mlp.down_proj.weight", m.down_w[i])
+            put(p + "input_layernorm.weight", m.ln1_w[i])
+            put(p + "post_attention_layernorm.weight", m.ln2_w[i])
+        put("model.norm.weight", m.norm_w)
+        vt = getattr(m, "vision_tower", None)
+        if vt is not None:
+            vt.state_dict(destination=out, prefix=prefix + "model.vision_tower.", keep_vars=keep_vars)
+        pj = getattr(m, "projector", None)
+        if pj is not None:
+            pj.state_dict(destination=out, prefix=prefix + "model.projector.", keep_vars=keep_vars)
+        put("lm_head.weight", self.lm_head_w)
+        return out
+
+    def load_state_dict(self, state_dict, strict: bool = True, assign: bool = False):
+        cfg = self.config
+        D, FF = cfg.hidden_size, cfg.intermediate_size
+        own = self.state_dict(keep_vars=True)
+        skip = ("rotary_emb.inv_freq", "position_ids")
+        missing = [k for k in own if k not in state_dict]
+        unexpected = [k for k in state_dict if k not in own and not k.endswith(skip)]
+        if strict and (missing or unexpected):
+            raise RuntimeError(f"load_state_dict: missing {missing[:4]} ({len(missing)}), "
+                               f"unexpected {unexpected[:4]} ({len(unexpected)})")
+        m = self.model
+        with torch.no_grad():
+            for k, dst in own.items():
+                if k not in state_dict:
+                    continue
+                src = state_dict[k]
+                if tuple(src.shape) != tuple(dst.shape):
+                    raise RuntimeError(f"size mismatch for {k}: {tuple(src.shape)} vs {tuple(dst.shape)}")
+                if k.endswith("mlp.gate_proj.weight") or k.endswith("mlp.up_proj.weight"):
+                    i = int(k.split("layers.")[1].split(".")[0])
+                    which = 0 if "gate_proj" in k else 1
+                    m.gate_up_w[i].view(FF // 128, 2, 128, D)[:, which].copy_(src.view(FF // 128, 128, D))
+                else:
+                    dst.copy_(src)
+        return torch.nn.modules.module._IncompatibleKeys(missing, unexpected)
+
+    def save_pretrained(self, save_directory: str):
+        os.makedirs(save_directory, exist_ok=True)
+        sd = {k: v.detach().cpu().contiguous() for k, v in self.state_dict().items()}
+        torch.save(sd, os.path.join(save_directory, "pytorch_model.bin"))
+        cfg = self.config.to_dict() if hasattr(self.config, "to_dict") else dict(self.config.__dict__)
+        json.dump(cfg, open(os.path.join(save_directory, "config.json"), "w"), indent=2, default=str)
+
+    @classmethod
+    def from_pretrained(cls, path: str, config=None, **_):
+        if config is None:
+            raw = json.load(open(os.path.join(path, "config.json")))
+            raw = {k: v for k, v in raw.items() if k not in ("model_type", "architectures", "transformers_version")}
+            config = MMGPTConfig(**raw)
+        model = cls(config)
+        f = os.path.join(path, "pytorch_model.bin")
+        if os.path.exists(f):
+            sd = torch.load(f, map_location="cpu")
+            llm = {k: v for k, v in sd.items() if "vision_tower" not in k and "projector" not in k}
+            model.load_state_dict(llm, strict=False)
+        return model
+
+    # ------------------------------------------------------------------ forward (llama_mmgpt.py:53-112)
+    def forward(self, input_ids: torch.LongTensor = None, attention_mask: Optional[torch.Tensor] = None,
+                past_key_values=None, inputs_embeds: Optional[torch.FloatTensor] = None,
+                labels: Optional[torch.LongTensor] = None, use_cache: Optional[bool] = None,
+                output_attentions: Optional[bool] = None, output_hidden_states: Optional[bool] = None,
+                images: Optional[List[torch.Tensor]] = None, return_dict: Optional[bool] = None):
+        if output_attentions:
+            raise AssertionError("output_attentions is not supported")  # monkey_patch.py:61
+        if self.lm_head_w.dtype != torch.bfloat16 or not self.lm_head_w.is_cuda:
+            raise RuntimeError("MMGPTLlamaForCausalLM runs on CUDA in bfloat16: call "
+                               "model.to(dtype=torch.bfloat16, device='cuda') first (builder.py:163)")
+        return_dict = True if return_dict is None else return_dict
+        if past_key_values is not None and not isinstance(past_key_values, MerlinKVCache):
+            raise TypeError("past_key_values must be the MerlinKVCache returned by a previous forward")
+        if past_key_values is not None and not past_key_values:
+            past_key_values_in, past_for_mm = past_key_values, None
+        else:
+            past_key_values_in = past_for_mm = past_key_values
+
+        if inputs_embeds is None:
+            input_ids, attention_mask, _, inputs_embeds, labels = self.prepare_inputs_labels_for_multimodal(
+                input_ids, attention_mask, past_for_mm, labels, images)
+        device = self.device
+        if inputs_embeds is None:  # text-only or decode step: plain embedding gather
+            ids_dev = input_ids.to(device).contiguous()
+            flat, _ = ops.embed_splice(ids_dev, self.model.embed_tokens, None, -1)
+            inputs_embeds = flat.view(ids_dev.shape[0], ids_dev.shape[1], -1)
+        B, S, D = inputs_embeds.shape
+
+        if past_for_mm is not None:  # ---- decode step(s) against the cache (HF eager path, K12)
+            if S != 1:
+                raise NotImplementedError("cached forward supports one new token per step")
+            logits = self._get_decoder(past_for_mm).step_logits(inputs_embeds.reshape(B, D)).view(B, 1, -1)
+            out = CausalLMOutputWithPast(loss=None, logits=logits, past_key_values=past_for_mm)
+            return out if return_dict else (logits, past_for_mm)
+
+        seqlens = None
+        if attention_mask is not None:
+            am = attention_mask
+            lens = am.sum(dim=-1)
+            if bool((lens != S).any()):
+                seqlens = lens.to(device=device, dtype=torch.int32)
+        cache = None
+        if use_cache:
+            cache = past_key_values_in if past_key_values_in is not None else MerlinKVCache(
+                self.config.num_hidden_layers, B, max(S + 1024, getattr(self, "_cache_capacity", 0)), D, device)
+        x = inputs_embeds.reshape(B * S, D)
+        if x.dtype != torch.bfloat16:
+            x = x.to(torch.bfloat16)
+        x = x.contiguous()
+        hidden, all_hidden = self.model.forward_layers(x, B, S, seqlens, cache, bool(output_hidden_states))
+        logits2d = ops.gemm(hidden, self.lm_head_w)          # [B*S, V] on a 16-byte aligned pitch
+        logits = logits2d.view(B, S, -1) if logits2d.is_contiguous() else logits2d.unflatten(0, (B, S))
+
+        loss = None
+        if labels is not None:
+            lab = labels.to(device).contiguous()
+            loss, _ = ops.cross_entropy(logits2d, lab, B, S, IGNORE_INDEX)
+        hs = None
+        if output_hidden_states:
+            hs = tuple(h.view(B, S, D) for h in all_hidden[:-1]) + (hidden.view(B, S, D),)
+        if not return_dict:
+            out = (logits, cache)
+            return (loss,) + out if loss is not None else out
+        return CausalLMOutputWithPast(loss=loss, logits=logits, past_key_values=cache, hidden_states=hs,
+                                      attentions=None)
+
+    # ------------------------------------------------------------------ generation (llama_mmgpt.py:114-134)
+    def prepare_inputs_for_generation(self, input_ids, past_key_values=None, attention_mask=None,
+                                      inputs_embeds=None, **kwargs):
+        if past_key_values:
+            input_ids = input_ids[:, -1:]
+        if inputs_embeds is not None and not past_key_values:
+            model_inputs = {"inputs_embeds": inputs_embeds}
+        else:
+            model_inputs = {"input_ids": input_ids}
+        model_inputs.update({"past_key_values": past_key_values, "use_cache": kwargs.get("use_cache"),
+                             "attention_mask": attention_mask, "images": kwargs.get("images", None)})
+        return model_inputs
+
+    def _get_decoder(self, cache: MerlinKVCache):
+        if self._decoder is None or self._decoder.cache is not cache:
+            self._decoder = _decode.DecodeRunner(self, cache)
+        return self._decoder
+
+    @torch.no_grad()
+    def generate(self, input_ids: torch.LongTensor, images: Optional[List[torch.Tensor]] = None,
+                 max_new_tokens: int = 1024, do_sample: bool = False, temperature: float = 1.0,
+                 top_p: float = 1.0, num_beams: int = 1, eos_token_id: Optional[int] = 2,
+                 stopping_criteria=None, attention_mask=None, use_cache: bool = True, streamer=None,
+                 generator: Optional[torch.Generator] = None, **_):
+        """Greedy / temperature sampling with a KV cache.  Step 0 is the full multimodal prefill, later
+        steps feed one token and skip the vision path.  Returns [1, S + new] ids."""
+        if num_beams != 1:
+            raise NotImplementedError("beam search is a 'next' row (SURVEY.md §8f N4)")
+        if input_ids.shape[0] != 1:
+            raise NotImplementedError("generate() handles one sequence at a time (reference eval scripts)")
+        device = self.device
+        ids = input_ids.to(device)
+        self._cache_capacity = ids.shape[1] + max_new_tokens + 8
+        inputs = self.prepare_inputs_for_generation(ids, None, attention_mask, use_cache=True, images=images)
+        out = self.forward(**inputs)
+        cache = out.past_key_values
+        last = out.logits[:, -1, :]
+        if not do_sample and stopping_criteria is None and streamer is None and max_new_tokens > 0:
+            # device-resident greedy loop: one CUDA-graph replay per token, no host round trips
+            first = ops.argmax(last).view(1, 1)
+            ids = torch.cat([ids, first], dim=1)
+            if (eos_token_id is None or int(first) != eos_token_id) and max_new_tokens > 1:
+                more = self._get_decoder(cache).greedy(first, max_new_tokens - 1, eos_token_id)
+                ids = torch.cat([ids, more.view(1, -1)], dim=1)
+            return ids
+        new_tokens = []
+        for step in range(max_new_tokens):
+            if do_sample and temperature > 0:
+                probs = torch.softmax(last.float() / temperature, dim=-1)
+                nxt = torch.multinomial(probs, 1, generator=generator)
+            else:
+                nxt = ops.argmax(last).view(1, 1)
+            new_tokens.append(nxt)
+            ids = torch.cat([ids, nxt], dim=1)
+            if streamer is not None:
+                streamer.put(nxt.cpu())
+            if eos_token_id is not None and int(nxt) == eos_token_id:
+                break
+            if stopping_criteria is not None and any(c(ids, last) for c in stopping_criteria):
+                break
+            if step + 1 == max_new_tokens:
+                break
+            step_in = self.prepare_inputs_for_generation(ids, cache, torch.ones_like(ids), use_cache=True,
+                                                         images=images)
+            last = self.forward(**step_in).logits[:, -1, :]
+        if streamer is not None:
+            streamer.end()
+        return ids
+
+
+MerlinForCausalLM = MMGPTLlamaForCausalLM  # the name BASELINE.json's north_star uses

@@ -11,11 +11,52 @@ from typing import Optional
 import torch
 
 from . import lib as _lib
-from .lib import EPI_QUICKGELU, EPI_RESIDUAL, EPI_STORE, EPI_SWIGLU, check
+from .lib import EPI_QUICKGELU, EPI_RESIDUAL, EPI_STORE, EPI_SWIGLU
+from .lib import check as _check
 
 DEFAULT_CTA_GROUP = 2  # CTA-pair (cta_group::2) GEMM tiles unless overridden
 
 _BF16 = torch.bfloat16
+
+
+def check(status: int, what: str, launches: int = 0) -> None:
+    _check(status, what)
+    PROFILE.launches += launches
+
+
+class _Profile:
+    """Launch counter + optional CUDA-event timing of every GEMM launch (bench.py's roofline leg)."""
+
+    def __init__(self):
+        self.enabled = False
+        self.launches = 0
+        self.events = []
+
+    def reset(self, enabled: bool = False):
+        self.enabled = enabled
+        self.events = []
+
+    def gemm_summary(self):
+        """(algorithmic FLOPs, milliseconds, launches) of the GEMM launches recorded since reset()."""
+        torch.cuda.synchronize()
+        flops = sum(f for _, _, f in self.events)
+        ms = sum(a.elapsed_time(b) for a, b, _ in self.events)
+        return flops, ms, len(self.events)
+
+
+PROFILE = _Profile()
+
+
+def _gemm_call(fn, flops, *args):
+    PROFILE.launches += 1
+    if not PROFILE.enabled:
+        return fn(*args)
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    rc = fn(*args)
+    e1.record()
+    PROFILE.events.append((e0, e1, flops))
+    return rc
 
 
 def _stream() -> int:
@@ -62,9 +103,9 @@ def gemm(a: torch.Tensor, w: torch.Tensor, *, bias: Optional[torch.Tensor] = Non
     if M == 0:
         return out
     L = _lib.load()
-    check(L.merlin_gemm_bf16(_stream(), a.data_ptr(), lda, w.data_ptr(), ldb, out.data_ptr(), ldc,
-                             _ptr(residual), ldr, _ptr(bias), M, N, K, epilogue,
-                             cta_group or DEFAULT_CTA_GROUP), "merlin_gemm_bf16")
+    check(_gemm_call(L.merlin_gemm_bf16, 2 * M * N * K, _stream(), a.data_ptr(), lda, w.data_ptr(), ldb,
+                     out.data_ptr(), ldc, _ptr(residual), ldr, _ptr(bias), M, N, K, epilogue,
+                     cta_group or DEFAULT_CTA_GROUP), "merlin_gemm_bf16")
     return out
 
 
@@ -84,10 +125,9 @@ def gemm_qkv_rope(a: torch.Tensor, w_qkv: torch.Tensor, rope_cos: torch.Tensor, 
     if positions is not None and positions.dtype != torch.int32:
         raise ValueError("positions must be int32")
     L = _lib.load()
-    check(L.merlin_gemm_qkv_rope(_stream(), a.data_ptr(), lda, w_qkv.data_ptr(), ldb, out.data_ptr(), ldc,
-                                 rope_cos.data_ptr(), rope_sin.data_ptr(), _ptr(positions), M, N, K,
-                                 2 * N // 3, seq_len, cta_group or DEFAULT_CTA_GROUP),
-          "merlin_gemm_qkv_rope")
+    check(_gemm_call(L.merlin_gemm_qkv_rope, 2 * M * N * K, _stream(), a.data_ptr(), lda, w_qkv.data_ptr(), ldb,
+                     out.data_ptr(), ldc, rope_cos.data_ptr(), rope_sin.data_ptr(), _ptr(positions), M, N, K,
+                     2 * N // 3, seq_len, cta_group or DEFAULT_CTA_GROUP), "merlin_gemm_qkv_rope")
     return out
 
 
@@ -107,7 +147,7 @@ def flash_attn(qkv: torch.Tensor, batch: int, seq: int, heads: int, head_dim: in
     L = _lib.load()
     check(L.merlin_flash_attn_fwd(_stream(), qkv.data_ptr(), ld, out.data_ptr(), ldo, _ptr(lse),
                                   _ptr(seqlens), batch, seq, heads, head_dim, int(causal),
-                                  float(softmax_scale)), "merlin_flash_attn_fwd")
+                                  float(softmax_scale)), "merlin_flash_attn_fwd", 1)
     return (out, lse) if return_lse else out
 
 
@@ -117,7 +157,7 @@ def rmsnorm(x: torch.Tensor, weight: torch.Tensor, eps: float, out: Optional[tor
         out = torch.empty((M, D), dtype=_BF16, device=x.device)
     _, _, ldy = _rows2d(out, "out")
     check(_lib.load().merlin_rmsnorm(_stream(), x.data_ptr(), ldx, weight.data_ptr(), out.data_ptr(), ldy,
-                                     M, D, float(eps)), "merlin_rmsnorm")
+                                     M, D, float(eps)), "merlin_rmsnorm", 1)
     return out
 
 
@@ -128,7 +168,7 @@ def layernorm(x: torch.Tensor, weight: torch.Tensor, bias: torch.Tensor, eps: fl
         out = torch.empty((M, D), dtype=_BF16, device=x.device)
     _, _, ldy = _rows2d(out, "out")
     check(_lib.load().merlin_layernorm(_stream(), x.data_ptr(), ldx, weight.data_ptr(), bias.data_ptr(),
-                                       out.data_ptr(), ldy, M, D, float(eps)), "merlin_layernorm")
+                                       out.data_ptr(), ldy, M, D, float(eps)), "merlin_layernorm", 1)
     return out
 
 
@@ -142,7 +182,7 @@ def patch_im2col(pixels: torch.Tensor, patch: int, ld_col: int) -> torch.Tensor:
     g = hw // patch
     col = torch.empty((n * g * g, ld_col), dtype=_BF16, device=pixels.device)
     check(_lib.load().merlin_patch_im2col(_stream(), pixels.data_ptr(), col.data_ptr(), n, hw, patch, ld_col),
-          "merlin_patch_im2col")
+          "merlin_patch_im2col", 1)
     return col
 
 
@@ -153,7 +193,7 @@ def vit_embed_ln(patch_out: torch.Tensor, class_embedding: torch.Tensor, positio
     check(_lib.load().merlin_vit_embed_ln(_stream(), patch_out.data_ptr(), class_embedding.data_ptr(),
                                           position_embedding.data_ptr(), ln_w.data_ptr(), ln_b.data_ptr(),
                                           hidden.data_ptr(), n_img, tokens, D, float(eps)),
-          "merlin_vit_embed_ln")
+          "merlin_vit_embed_ln", 1)
     return hidden
 
 
@@ -162,26 +202,32 @@ def conv3x3_im2col(feat: torch.Tensor, n_img: int, grid: int, C: int, stride: in
     go = (grid + 2 - 3) // stride + 1
     col = torch.empty((n_img * go * go, 9 * C), dtype=_BF16, device=feat.device)
     check(_lib.load().merlin_conv3x3_im2col(_stream(), feat.data_ptr(), col.data_ptr(), n_img, grid, C,
-                                            stride, tok_stride, tok_off), "merlin_conv3x3_im2col")
+                                            stride, tok_stride, tok_off), "merlin_conv3x3_im2col", 1)
     return col
 
 
 def embed_splice(input_ids: torch.Tensor, embed_table: torch.Tensor, image_features: Optional[torch.Tensor],
-                 im_patch_token: int) -> tuple[torch.Tensor, torch.Tensor]:
-    """Returns (inputs_embeds [T, D], rank_ws) — rank_ws[T] holds the number of <im_patch> tokens."""
-    if input_ids.dtype != torch.int64 or not input_ids.is_contiguous():
-        raise ValueError("embed_splice: input_ids must be contiguous int64")
-    T = input_ids.numel()
+                 im_patch_token: int, feat_offset: Optional[torch.Tensor] = None,
+                 feat_limit: Optional[torch.Tensor] = None) -> tuple[torch.Tensor, torch.Tensor]:
+    """input_ids [B, S] int64 (CUDA) -> (inputs_embeds [B*S, D], counts [B] = #<im_patch> per sample)."""
+    if input_ids.dtype != torch.int64 or not input_ids.is_contiguous() or input_ids.dim() != 2:
+        raise ValueError("embed_splice: input_ids must be contiguous int64 [B, S]")
+    B, S = input_ids.shape
     V, D = embed_table.shape
-    out = torch.empty((T, D), dtype=_BF16, device=embed_table.device)
-    ws = torch.empty((T + 1,), dtype=torch.int32, device=embed_table.device)
+    out = torch.empty((B * S, D), dtype=_BF16, device=embed_table.device)
+    ws = torch.empty((B * S + B,), dtype=torch.int32, device=embed_table.device)
     nfeat = 0 if image_features is None else image_features.shape[0]
-    if image_features is not None and (not image_features.is_contiguous() or image_features.shape[1] != D):
-        raise ValueError("embed_splice: image_features must be contiguous [rows, D]")
+    if image_features is not None and (not image_features.is_contiguous() or image_features.shape[1] != D
+                                       or image_features.dtype != _BF16):
+        raise ValueError("embed_splice: image_features must be contiguous bf16 [rows, D]")
+    for t in (feat_offset, feat_limit):
+        if t is not None and (t.dtype != torch.int32 or t.numel() != B):
+            raise ValueError("embed_splice: feat_offset / feat_limit must be int32 [B]")
     check(_lib.load().merlin_embed_splice(_stream(), input_ids.data_ptr(), embed_table.data_ptr(),
-                                          _ptr(image_features), out.data_ptr(), ws.data_ptr(), T, D, nfeat,
-                                          V, im_patch_token), "merlin_embed_splice")
-    return out, ws
+                                          _ptr(image_features), out.data_ptr(), ws.data_ptr(), B, S, D, nfeat,
+                                          _ptr(feat_offset), _ptr(feat_limit), V, im_patch_token),
+          "merlin_embed_splice", 2)
+    return out, ws[B * S:]
 
 
 def rope_qk_inplace(qkv: torch.Tensor, rope_cos: torch.Tensor, rope_sin: torch.Tensor, heads: int,
@@ -189,7 +235,7 @@ def rope_qk_inplace(qkv: torch.Tensor, rope_cos: torch.Tensor, rope_sin: torch.T
     M, _, ld = _rows2d(qkv, "qkv")
     check(_lib.load().merlin_rope_qk_inplace(_stream(), qkv.data_ptr(), ld, rope_cos.data_ptr(),
                                              rope_sin.data_ptr(), _ptr(positions), M, heads, seq_len),
-          "merlin_rope_qk_inplace")
+          "merlin_rope_qk_inplace", 1)
     return qkv
 
 
@@ -203,14 +249,14 @@ def cross_entropy(logits: torch.Tensor, labels: torch.Tensor, batch: int, seq: i
     acc = torch.empty((2,), dtype=torch.float32, device=logits.device)
     check(_lib.load().merlin_cross_entropy_fwd(_stream(), logits.data_ptr(), ld, labels.data_ptr(), batch, seq,
                                                V, ignore_index, row.data_ptr(), acc.data_ptr()),
-          "merlin_cross_entropy_fwd")
+          "merlin_cross_entropy_fwd", 1)
     return acc[0] / acc[1], row
 
 
 def argmax(logits: torch.Tensor) -> torch.Tensor:
     M, V, ld = _rows2d(logits, "logits")
     out = torch.empty((M,), dtype=torch.int64, device=logits.device)
-    check(_lib.load().merlin_argmax(_stream(), logits.data_ptr(), ld, M, V, out.data_ptr()), "merlin_argmax")
+    check(_lib.load().merlin_argmax(_stream(), logits.data_ptr(), ld, M, V, out.data_ptr()), "merlin_argmax", 1)
     return out
 
 

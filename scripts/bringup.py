@@ -187,10 +187,11 @@ def elt_cases():
     ids[1, 300:444] = V - 3
     ids[1, 500:644] = V - 3
     feats = torch.randn(3 * 144, D, device=dev).to(torch.bfloat16)
-    out, ws = ops.embed_splice(ids.view(-1), table, feats, V - 3)
+    out, ws = ops.embed_splice(ids, table, feats, V - 3, torch.tensor([0, 144], dtype=torch.int32, device=dev),
+                               torch.tensor([144, 288], dtype=torch.int32, device=dev))
     ref = table[ids.view(-1)].clone()
     ref[ids.view(-1) == V - 3] = feats
-    print("[%s] embed_splice bit-exact, count=%d" % ("OK " if torch.equal(out, ref) else "BAD", ws[-1].item()))
+    print("[%s] embed_splice bit-exact, counts=%s" % ("OK " if torch.equal(out, ref) else "BAD", ws.tolist()))
     # CE + argmax
     B, S, Vv = 2, 50, 32003
     logits = torch.randn(B * S, 32008, device=dev).to(torch.bfloat16)[:, :Vv]

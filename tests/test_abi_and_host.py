@@ -1,0 +1,126 @@
+"""CPU: the C-ABI library loads and exports every symbol include/merlin_b200.h declares; host-side
+logic of the mmgpt mirror (state-dict contract, packing, grammar validation, error behaviour)."""
+import ctypes
+import os
+
+import pytest
+import torch
+
+from helpers import build_product_model, load_golden
+from merlin_b200 import lib as mlib
+from merlin_b200 import ops
+from oracle import merlin_oracle as O
+
+
+def test_library_exports_every_declared_symbol():
+    L = mlib.load()
+    names = mlib.declared_symbols()
+    assert len(names) >= 15
+    for n in names:
+        assert hasattr(L, n), f"{n} declared in include/merlin_b200.h but not exported"
+
+
+def test_prototypes_cover_the_header():
+    covered = set(mlib._PROTOTYPES) | {"merlin_last_error", "merlin_decode_workspace_bytes"}
+    assert set(mlib.declared_symbols()) <= covered
+
+
+def test_missing_library_fails_loudly(monkeypatch, tmp_path):
+    monkeypatch.setenv("MERLIN_B200_LIB", str(tmp_path / "nope.so"))
+    monkeypatch.setattr(mlib, "_lib", None)
+    with pytest.raises(mlib.MerlinError):
+        mlib.load()
+
+
+def test_invalid_arguments_return_error_codes_without_a_gpu():
+    L = mlib.load()
+    rc = L.merlin_gemm_bf16(None, None, 0, None, 0, None, 0, None, 0, None, 0, 0, 0, 0, 2)
+    assert rc == -1 and b"gemm" in L.merlin_last_error()
+    rc = L.merlin_flash_attn_fwd(None, 1, 0, 1, 0, None, None, 1, 1, 1, 96, 1, 0.0)
+    assert rc == -1 and b"head_dim" in L.merlin_last_error()
+    assert L.merlin_decode_workspace_bytes(4096, 11008, 32, 16) > 2 * (3 * 4096 + 11008)
+
+
+def test_ops_reject_cpu_tensors():
+    a = torch.zeros(4, 8, dtype=torch.bfloat16)
+    with pytest.raises(TypeError):
+        ops.gemm(a, a)
+
+
+def test_swiglu_interleave_layout():
+    g = torch.arange(256 * 4, dtype=torch.float32).view(256, 4)
+    u = -g
+    p = ops.swiglu_interleave(g, u)
+    assert p.shape == (512, 4)
+    assert torch.equal(p[:128], g[:128]) and torch.equal(p[128:256], u[:128])
+    assert torch.equal(p[256:384], g[128:]) and torch.equal(p[384:], u[128:])
+
+
+@pytest.mark.parametrize("name", ["tiny_conv", "tiny_mlp"])
+def test_state_dict_contract_round_trip(name):
+    """Reference key names / shapes in, packed storage inside, identical tensors out (Appendix A)."""
+    g, cfg = load_golden(name)
+    sd = O.init_state_dict(cfg, seed=0)
+    model = build_product_model(cfg, sd, device=None)
+    back = model.state_dict()
+    assert set(back) == set(sd)
+    for k in sd:
+        assert torch.equal(back[k], sd[k]), k
+    # packed layouts the kernels rely on
+    D, FF = cfg.hidden_size, cfg.intermediate_size
+    m = model.model
+    assert torch.equal(m.qkv_w[0][D:2 * D], sd["model.layers.0.self_attn.k_proj.weight"])
+    assert torch.equal(m.gate_up_w[1][128:256], sd["model.layers.1.mlp.up_proj.weight"][:128])
+    assert torch.equal(m.gate_up_w[1][256:384], sd["model.layers.1.mlp.gate_proj.weight"][128:256])
+    vt = m.vision_tower
+    assert vt.patch_weight.shape[1] % 8 == 0 and bool((vt.patch_weight[:, vt.k_patch:] == 0).all())
+    assert vt.num_patches == cfg.num_patches
+
+
+def test_strict_loading_reports_unknown_keys():
+    g, cfg = load_golden("tiny_conv")
+    sd = O.init_state_dict(cfg, seed=0)
+    sd["model.layers.0.bogus.weight"] = torch.zeros(1)
+    with pytest.raises(RuntimeError):
+        build_product_model(cfg, sd, device=None)
+
+
+def test_grammar_validation_matches_reference_errors():
+    g, cfg = load_golden("tiny_conv")
+    model = build_product_model(cfg, O.init_state_dict(cfg, seed=0), device=None)
+    ids = g["input_ids"].clone()
+    P = cfg.num_patches
+    model._validate_image_grammar(ids, g["images"], P)          # valid batch passes
+    bad = ids.clone()
+    bad[0, 1 + P + 1] = 7                                       # <im_end> overwritten
+    with pytest.raises(ValueError):
+        model._validate_image_grammar(bad, g["images"], P)
+    bad = ids.clone()
+    bad[0, -2] = cfg.im_start_token                             # unmatched <im_start>
+    with pytest.raises(ValueError):
+        model._validate_image_grammar(bad, g["images"], P)
+    model.use_im_start_end = False
+    with pytest.raises(NotImplementedError):
+        model._validate_image_grammar(ids, g["images"], P)
+
+
+def test_prepare_inputs_for_generation_contract():
+    from merlin_b200.mmgpt.model.mmgpt.llama_mmgpt import MerlinKVCache
+    g, cfg = load_golden("tiny_conv")
+    model = build_product_model(cfg, O.init_state_dict(cfg, seed=0), device=None)
+    ids = g["input_ids"][:1]
+    first = model.prepare_inputs_for_generation(ids, None, None, use_cache=True, images=g["images"][:1])
+    assert first["input_ids"].shape == ids.shape and first["past_key_values"] is None
+    empty = MerlinKVCache(cfg.num_layers, 1, 8, cfg.hidden_size, "cpu")
+    assert not empty                                            # empty cache == no past
+    assert model.prepare_inputs_for_generation(ids, empty)["input_ids"].shape == ids.shape
+    empty.seq_len = ids.shape[1]
+    step = model.prepare_inputs_for_generation(ids, empty, images=g["images"][:1])
+    assert step["input_ids"].shape == (1, 1) and step["images"] is not None
+
+
+def test_forward_without_cuda_fails_loudly():
+    g, cfg = load_golden("tiny_conv")
+    model = build_product_model(cfg, O.init_state_dict(cfg, seed=0), device=None)
+    with pytest.raises(RuntimeError):
+        model(input_ids=g["input_ids"], images=g["images"])

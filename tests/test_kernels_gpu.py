@@ -1,0 +1,225 @@
+"""GPU: every kernel behind the C ABI against a torch fp32 restatement of the same op.
+Integer / index work is bit-exact; floating work within the stated tolerance
+(max|Δ| <= 2^-7 · max|ref| per op)."""
+import pytest
+import torch
+
+from merlin_b200 import ops
+from merlin_b200.lib import EPI_QUICKGELU, EPI_RESIDUAL, EPI_SWIGLU
+
+pytestmark = pytest.mark.gpu
+DEV = "cuda"
+TOL = 2.0 ** -7
+
+
+def close(got, ref, tol=TOL):
+    got, ref = got.float(), ref.float()
+    assert not torch.isnan(got).any()
+    err = (got - ref).abs().max().item()
+    scale = ref.abs().max().item() + 1e-9
+    assert err <= tol * scale, f"max|Δ|={err:.4g} > {tol:.3g}·{scale:.4g}"
+
+
+def ints(shape):
+    return torch.randint(-2, 3, shape, device=DEV).to(torch.bfloat16)
+
+
+@pytest.mark.parametrize("cg", [1, 2])
+@pytest.mark.parametrize("mnk", [(256, 256, 64), (512, 512, 512), (577 * 5, 1024, 1024), (300, 1000, 592),
+                                 (1024, 32003, 256), (64, 256, 128), (1, 512, 256)])
+def test_gemm_integer_operands_exact(cg, mnk):
+    torch.manual_seed(0)
+    M, N, K = mnk
+    a, w = ints((M, K)), ints((N, K))
+    got = ops.gemm(a, w, cta_group=cg)
+    assert torch.equal(got.float(), a.float() @ w.float().t())   # |values| < 2^8: exact in bf16
+
+
+@pytest.mark.parametrize("cg", [1, 2])
+def test_gemm_large_and_linearity(cg):
+    torch.manual_seed(1)
+    a = torch.randn(4096, 4096, device=DEV).to(torch.bfloat16)
+    w = (torch.randn(4096, 4096, device=DEV) * 0.02).to(torch.bfloat16)
+    y = ops.gemm(a, w, cta_group=cg)
+    close(y, a.float() @ w.float().t())
+    # size-independent property: A·(2W)ᵀ == 2·(A·Wᵀ) exactly (power-of-two scaling commutes with rounding)
+    assert torch.equal(ops.gemm(a, (w * 2).contiguous(), cta_group=cg), y * 2)
+
+
+@pytest.mark.parametrize("cg", [1, 2])
+def test_gemm_epilogues(cg):
+    torch.manual_seed(2)
+    M, N, K = 1024 + 37, 1024, 512
+    a = torch.randn(M, K, device=DEV).to(torch.bfloat16)
+    w = (torch.randn(N, K, device=DEV) * 0.05).to(torch.bfloat16)
+    bias = torch.randn(N, device=DEV).to(torch.bfloat16)
+    res = torch.randn(M, N, device=DEV).to(torch.bfloat16)
+    base = a.float() @ w.float().t()
+    close(ops.gemm(a, w, bias=bias, cta_group=cg), base + bias.float())
+    close(ops.gemm(a, w, residual=res, epilogue=EPI_RESIDUAL, cta_group=cg), base + res.float())
+    close(ops.gemm(a, w, bias=bias, residual=res, epilogue=EPI_RESIDUAL, cta_group=cg), base + bias.float() + res.float())
+    x = res.clone()
+    ops.gemm(a, w, residual=x, out=x, epilogue=EPI_RESIDUAL, cta_group=cg)   # in place (residual stream)
+    close(x, base + res.float())
+    v = base + bias.float()
+    close(ops.gemm(a, w, bias=bias, epilogue=EPI_QUICKGELU, cta_group=cg), v * torch.sigmoid(1.702 * v))
+    FF = 1408
+    gw = (torch.randn(FF, K, device=DEV) * 0.05).to(torch.bfloat16)
+    uw = (torch.randn(FF, K, device=DEV) * 0.05).to(torch.bfloat16)
+    ref = torch.nn.functional.silu(a.float() @ gw.float().t()) * (a.float() @ uw.float().t())
+    close(ops.gemm(a, ops.swiglu_interleave(gw, uw), epilogue=EPI_SWIGLU, cta_group=cg), ref)
+
+
+def rope_ref(raw, cos, sin, S):
+    c = torch.cat([cos[:S], cos[:S]], -1)[None, :, None, :]
+    s = torch.cat([sin[:S], sin[:S]], -1)[None, :, None, :]
+
+    def rot(x):
+        x1, x2 = x[..., :64], x[..., 64:]
+        return x * c + torch.cat([-x2, x1], -1) * s
+
+    return torch.stack([rot(raw[:, :, 0]), rot(raw[:, :, 1]), raw[:, :, 2]], dim=2)
+
+
+@pytest.mark.parametrize("cg", [1, 2])
+def test_qkv_gemm_with_rope_epilogue(cg):
+    torch.manual_seed(3)
+    H, S, B = 4, 300, 2
+    D = H * 128
+    a = torch.randn(B * S, 256, device=DEV).to(torch.bfloat16)
+    wq = (torch.randn(3 * D, 256, device=DEV) * 0.05).to(torch.bfloat16)
+    cos, sin = ops.rope_tables(512)
+    raw = (a.float() @ wq.float().t()).view(B, S, 3, H, 128)
+    ref = rope_ref(raw, cos, sin, S).reshape(B * S, 3 * D)
+    close(ops.gemm_qkv_rope(a, wq, cos, sin, S, cta_group=cg), ref)
+    plain = ops.gemm(a, wq, cta_group=cg)
+    close(ops.rope_qk_inplace(plain, cos, sin, H, S), ref)
+
+
+def attn_ref(qkv, B, S, H, hd, causal, seqlens=None):
+    q, k, v = qkv.float().view(B, S, 3, H, hd).permute(2, 0, 3, 1, 4)
+    s = (q @ k.transpose(-1, -2)) / hd ** 0.5
+    idx = torch.arange(S, device=qkv.device)
+    mask = torch.zeros(B, 1, S, S, dtype=torch.bool, device=qkv.device)
+    if causal:
+        mask |= (idx[None, :] > idx[:, None])[None, None]
+    if seqlens is not None:
+        mask |= (idx[None, None, None, :] >= seqlens.view(B, 1, 1, 1))
+    s = s.masked_fill(mask, float("-inf"))
+    o = (torch.softmax(s, -1) @ v).permute(0, 2, 1, 3).reshape(B * S, H * hd)
+    if seqlens is not None:
+        o = o * (idx[None, :] < seqlens[:, None]).reshape(B * S, 1)
+    return o, torch.logsumexp(s, -1)
+
+
+@pytest.mark.parametrize("hd", [64, 128])
+@pytest.mark.parametrize("causal", [True, False])
+@pytest.mark.parametrize("bsh", [(1, 128, 1), (2, 384, 2), (1, 577, 3), (1, 1000, 2), (1, 2048, 4), (1, 1, 1), (1, 129, 1)])
+def test_flash_attention(hd, causal, bsh):
+    torch.manual_seed(4)
+    B, S, H = bsh
+    qkv = torch.randn(B * S, 3 * H * hd, device=DEV).to(torch.bfloat16)
+    out, lse = ops.flash_attn(qkv, B, S, H, hd, causal=causal, return_lse=True)
+    ref, ref_lse = attn_ref(qkv, B, S, H, hd, causal)
+    close(out, ref)
+    close(lse, ref_lse, tol=1e-4)
+
+
+@pytest.mark.parametrize("hd", [64, 128])
+def test_flash_attention_rescale_and_padding(hd):
+    torch.manual_seed(5)
+    B, S, H = 1, 512, 2
+    qkv = (torch.randn(B * S, 3 * H * hd, device=DEV) * 4).to(torch.bfloat16)    # forces max refresh / O rescale
+    close(ops.flash_attn(qkv, B, S, H, hd, causal=True), attn_ref(qkv, B, S, H, hd, True)[0])
+    B, S = 3, 300
+    qkv = torch.randn(B * S, 3 * H * hd, device=DEV).to(torch.bfloat16)
+    sl = torch.tensor([300, 129, 7], dtype=torch.int32, device=DEV)
+    out = ops.flash_attn(qkv, B, S, H, hd, causal=True, seqlens=sl)
+    close(out, attn_ref(qkv, B, S, H, hd, True, sl)[0])
+    assert bool((out.view(B, S, -1)[2, 7:] == 0).all())                           # pad rows are zeros (pad_input)
+
+
+def test_norms():
+    torch.manual_seed(6)
+    x = torch.randn(300, 4096, device=DEV).to(torch.bfloat16)
+    w = torch.randn(4096, device=DEV).to(torch.bfloat16)
+    b = torch.randn(4096, device=DEV).to(torch.bfloat16)
+    xf = x.float()
+    close(ops.rmsnorm(x, w, 1e-5), w.float() * (xf * torch.rsqrt(xf.pow(2).mean(-1, keepdim=True) + 1e-5)))
+    x5 = torch.randn(7, 5120, device=DEV).to(torch.bfloat16)
+    w5 = torch.randn(5120, device=DEV).to(torch.bfloat16)
+    close(ops.rmsnorm(x5, w5, 1e-5), w5.float() * (x5.float() * torch.rsqrt(x5.float().pow(2).mean(-1, keepdim=True) + 1e-5)))
+    x1, w1, b1 = x[:, :1024].contiguous(), w[:1024].contiguous(), b[:1024].contiguous()
+    close(ops.layernorm(x1, w1, b1, 1e-5), torch.nn.functional.layer_norm(x1.float(), (1024,), w1.float(), b1.float(), 1e-5))
+
+
+def test_im2col_gathers_are_bit_exact():
+    torch.manual_seed(7)
+    px = torch.randn(2, 3, 336, 336, device=DEV).to(torch.bfloat16)
+    col = ops.patch_im2col(px, 14, 592)
+    ref = torch.nn.functional.unfold(px.float(), 14, stride=14).transpose(1, 2).reshape(2 * 576, 588)
+    assert torch.equal(col[:, :588].float(), ref) and bool((col[:, 588:] == 0).all())
+    hid = torch.randn(2 * 577, 1024, device=DEV).to(torch.bfloat16)
+    for stride in (1, 2):
+        col = ops.conv3x3_im2col(hid, 2, 24, 1024, stride, 577, 1)
+        feat = hid.view(2, 577, 1024)[:, 1:].permute(0, 2, 1).reshape(2, 1024, 24, 24).float()
+        un = torch.nn.functional.unfold(feat, 3, padding=1, stride=stride)
+        P = un.shape[-1]
+        assert torch.equal(col.float(), un.view(2, 1024, 9, P).permute(0, 3, 2, 1).reshape(2 * P, 9 * 1024))
+
+
+def test_vit_embed_ln():
+    torch.manual_seed(8)
+    po = torch.randn(2 * 576, 1024, device=DEV).to(torch.bfloat16)
+    cls = torch.randn(1024, device=DEV).to(torch.bfloat16)
+    pos = torch.randn(577, 1024, device=DEV).to(torch.bfloat16)
+    lw = torch.randn(1024, device=DEV).to(torch.bfloat16)
+    lb = torch.randn(1024, device=DEV).to(torch.bfloat16)
+    emb = torch.cat([cls.expand(2, 1, 1024), po.view(2, 576, 1024)], 1) + pos
+    close(ops.vit_embed_ln(po, cls, pos, lw, lb, 2, 1e-5),
+          torch.nn.functional.layer_norm(emb.float(), (1024,), lw.float(), lb.float(), 1e-5).reshape(-1, 1024))
+
+
+def test_embed_splice_bit_exact_with_ragged_samples():
+    torch.manual_seed(9)
+    V, D, P = 1000, 512, 144
+    pid = V - 3
+    table = torch.randn(V, D, device=DEV).to(torch.bfloat16)
+    ids = torch.randint(0, pid, (3, 700), device=DEV)
+    ids[0, 10:10 + P] = pid                       # sample 0: 1 image
+    ids[1, 300:300 + P] = pid                     # sample 1: 2 images
+    ids[1, 500:500 + P] = pid
+    #                                               sample 2: text only, but owns one (unused) zero image
+    feats = torch.randn(4 * P, D, device=DEV).to(torch.bfloat16)
+    off = torch.tensor([0, P, 3 * P], dtype=torch.int32, device=DEV)
+    lim = torch.tensor([P, 2 * P, P], dtype=torch.int32, device=DEV)
+    out, counts = ops.embed_splice(ids, table, feats, pid, off, lim)
+    ref = table[ids.view(-1)].clone().view(3, 700, D)
+    ref[0][ids[0] == pid] = feats[:P]
+    ref[1][ids[1] == pid] = feats[P:3 * P]
+    assert torch.equal(out.view(3, 700, D), ref)
+    assert counts.tolist() == [P, 2 * P, 0]
+    # more placeholders than feature rows: the surplus keeps its token embedding (zip truncation, base_mmgpt.py:121)
+    lim2 = torch.tensor([P, P, P], dtype=torch.int32, device=DEV)
+    out2, _ = ops.embed_splice(ids, table, feats, pid, off, lim2)
+    ref[1, 500:500 + P] = table[pid]
+    assert torch.equal(out2.view(3, 700, D), ref)
+    # empty batch
+    e, _ = ops.embed_splice(torch.zeros((0, 5), dtype=torch.int64, device=DEV), table, None, pid)
+    assert e.shape == (0, D)
+
+
+def test_cross_entropy_and_argmax():
+    torch.manual_seed(10)
+    B, S, V = 2, 50, 32003
+    logits = torch.randn(B * S, 32008, device=DEV).to(torch.bfloat16)[:, :V]
+    labels = torch.randint(0, V, (B, S), device=DEV)
+    labels[:, :20] = -100
+    loss, row = ops.cross_entropy(logits, labels, B, S)
+    ref = torch.nn.functional.cross_entropy(logits.float().view(B, S, V)[:, :-1].reshape(-1, V), labels[:, 1:].reshape(-1))
+    assert abs(loss.item() - ref.item()) < 1e-4
+    assert bool((row.view(B, S)[:, :19] == 0).all()) and bool((row.view(B, S)[:, -1] == 0).all())
+    assert torch.equal(ops.argmax(logits), logits.float().argmax(-1))
+    tie = torch.zeros(1, 64, device=DEV, dtype=torch.bfloat16)
+    tie[0, 5] = tie[0, 40] = 3.0
+    assert ops.argmax(tie).item() == 5                                           # lowest index on ties

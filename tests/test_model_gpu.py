@@ -1,0 +1,146 @@
+"""GPU parity proper: the product path (mmgpt mirror -> C ABI -> sm_100a kernels) against the CPU
+oracle and the golden vectors recorded from the real reference, on identical seeded inputs.
+
+Tolerances (bf16 weights/activations vs the fp32 oracle): logits max|Δ| <= 1e-2 (north_star),
+loss |Δ| <= 2e-3, image features / hidden states max|Δ| <= 2^-6·max|ref|; splice bit-exact;
+greedy token ids identical."""
+import pytest
+import torch
+
+from helpers import build_product_model, load_golden
+from oracle import merlin_oracle as O
+
+pytestmark = pytest.mark.gpu
+DEV = "cuda"
+
+
+def to_dev(images):
+    return [im.to(DEV) for im in images]
+
+
+@pytest.mark.parametrize("name", ["tiny_conv", "tiny_mlp", "tiny_pad"])
+def test_forward_matches_reference_golden(name):
+    g, cfg = load_golden(name)
+    sd = O.init_state_dict(cfg, seed=0)
+    model = build_product_model(cfg, sd)
+    out = model(input_ids=g["input_ids"].to(DEV), attention_mask=g["attention_mask"].to(DEV),
+                labels=g["labels"].to(DEV), images=to_dev(g["images"]))
+    valid = g["attention_mask"].bool()
+    logits = out.logits.float().cpu()
+    assert logits.shape == g["ref_logits"].shape
+    err = (logits[valid] - g["ref_logits"][valid]).abs().max().item()
+    assert err <= 1e-2, f"logits max|Δ| = {err}"
+    assert abs(out.loss.item() - g["ref_loss"].item()) <= 2e-3
+    # the oracle itself agrees with the golden on the same inputs (ties the three together)
+    mine = O.forward(sd, cfg, g["input_ids"], g["attention_mask"], g["labels"], g["images"])
+    assert (mine["logits"][valid] - g["ref_logits"][valid]).abs().max().item() < 1e-4
+
+
+def test_vision_tower_and_projector_api_match_oracle():
+    g, cfg = load_golden("tiny_conv")
+    sd = O.init_state_dict(cfg, seed=0)
+    model = build_product_model(cfg, sd)
+    tower, proj = model.get_model().vision_tower, model.get_model().projector
+    feats = tower(to_dev(g["images"]))                       # tuple of [n_i, P, C]  (clip_encoder.py:74-82)
+    ref = O.vision_tower_forward(sd, cfg, g["images"])
+    assert [tuple(f.shape) for f in feats] == [tuple(r.shape) for r in ref]
+    for f, r in zip(feats, ref):
+        assert (f.float().cpu() - r).abs().max().item() <= 2.0 ** -6 * r.abs().max().item()
+    pf = proj(feats)                                          # list of [n_i, P', D]  (conv_projector.py:23-39)
+    for f, r in zip(pf, g["ref_image_features"]):
+        assert tuple(f.shape) == tuple(r.shape)
+        assert (f.float().cpu() - r).abs().max().item() <= 2.0 ** -6 * r.abs().max().item()
+    assert tower.num_patches == cfg.num_patches and tower.hidden_size == cfg.vit_hidden
+    assert tower.dummy_feature.shape == (1, cfg.vit_hidden)
+
+
+def test_splice_bit_exact_against_oracle():
+    """inputs_embeds: gather rows are bit-exact copies of bf16 table rows / projected features."""
+    g, cfg = load_golden("tiny_conv")
+    sd = O.init_state_dict(cfg, seed=0)
+    model = build_product_model(cfg, sd)
+    ids = g["input_ids"].to(DEV)
+    _, _, _, embeds, _ = model.prepare_inputs_labels_for_multimodal(ids, None, None, None, to_dev(g["images"]))
+    feats = model.encode_images(to_dev(g["images"]))
+    ref = model.get_model().embed_tokens[ids].clone()
+    for b in range(ids.shape[0]):
+        ref[b][ids[b] == cfg.im_patch_token] = feats[b].reshape(-1, ref.shape[-1])
+    assert torch.equal(embeds, ref)
+    # text rows equal the oracle's embedding rows exactly (weights are bf16-representable)
+    text = (g["input_ids"] != cfg.im_patch_token)
+    assert torch.equal(embeds.float().cpu()[text], g["ref_inputs_embeds"][text])
+
+
+def test_hidden_states_per_layer():
+    g, cfg = load_golden("tiny_conv")
+    sd = O.init_state_dict(cfg, seed=0)
+    model = build_product_model(cfg, sd)
+    out = model(input_ids=g["input_ids"].to(DEV), images=to_dev(g["images"]), output_hidden_states=True)
+    feats = O.encode_images(sd, cfg, g["images"])
+    emb = O.prepare_inputs_embeds(sd, cfg, g["input_ids"], feats)
+    final, layers = O.decoder_forward(sd, cfg, emb, None, return_layers=True)
+    refs = [emb] + layers[:-1] + [final]
+    assert len(out.hidden_states) == len(refs)
+    for h, r in zip(out.hidden_states, refs):
+        assert (h.float().cpu() - r).abs().max().item() <= 2.0 ** -6 * r.abs().max().item()
+
+
+def test_error_behaviour_on_device():
+    g, cfg = load_golden("tiny_conv")
+    model = build_product_model(cfg, O.init_state_dict(cfg, seed=0))
+    bad = g["input_ids"].clone()
+    bad[0, 1 + cfg.num_patches + 1] = 7
+    with pytest.raises(ValueError):
+        model(input_ids=bad.to(DEV), images=to_dev(g["images"]))
+    with pytest.raises(ValueError):
+        model(input_ids=g["input_ids"].to(DEV), images=to_dev(g["images"][:1]))
+    with pytest.raises(AssertionError):
+        model(input_ids=g["input_ids"].to(DEV), images=to_dev(g["images"]), output_attentions=True)
+
+
+def test_greedy_generate_matches_reference_tokens():
+    g, cfg = load_golden("tiny_conv")
+    model = build_product_model(cfg, O.init_state_dict(cfg, seed=0))
+    ids = g["input_ids"][:1]
+    n_new = g["ref_generate"].shape[1] - ids.shape[1]
+    out = model.generate(ids.to(DEV), images=to_dev(g["images"][:1]), max_new_tokens=n_new, eos_token_id=None)
+    assert torch.equal(out.cpu(), g["ref_generate"])
+    # the step-by-step forward(past_key_values=...) path gives the same tokens as the graph-replayed loop
+    out2 = model.generate(ids.to(DEV), images=to_dev(g["images"][:1]), max_new_tokens=n_new, eos_token_id=None,
+                          stopping_criteria=[lambda i, s: False])
+    assert torch.equal(out2, out)
+
+
+def test_decode_step_logits_match_full_forward():
+    """Decode property: logits of token t from the cached single-token path == row t of a full forward."""
+    g, cfg = load_golden("tiny_conv")
+    model = build_product_model(cfg, O.init_state_dict(cfg, seed=0))
+    ids = g["input_ids"][:1].to(DEV)
+    imgs = to_dev(g["images"][:1])
+    full = model(input_ids=ids, images=imgs).logits
+    pre = model(input_ids=ids[:, :-1], images=imgs, use_cache=True)
+    step = model(input_ids=ids[:, -1:], images=imgs, past_key_values=pre.past_key_values,
+                 attention_mask=torch.ones_like(ids), use_cache=True)
+    assert (step.logits[0, 0].float() - full[0, -1].float()).abs().max().item() <= 1e-2
+
+
+def test_full_width_single_layer_properties():
+    """At Vicuna-7B width (D=4096, FF=11008, S=2048) the oracle is too slow for every test run, so use
+    size-independent properties: causality (prefix logits unchanged by the suffix) and determinism."""
+    from merlin_b200.mmgpt.model.mmgpt.llama_mmgpt import MMGPTLlamaForCausalLM, vicuna_7b_config
+    torch.manual_seed(0)
+    model = MMGPTLlamaForCausalLM(vicuna_7b_config(num_hidden_layers=1, vocab_size=2048)).to(device=DEV, dtype=torch.bfloat16)
+    ids = torch.randint(3, 2000, (1, 2048), device=DEV)
+    a = model(input_ids=ids).logits
+    b = model(input_ids=ids).logits
+    assert torch.equal(a, b)
+    c = model(input_ids=ids[:, :1024]).logits
+    assert (a[:, :1024].float() - c.float()).abs().max().item() <= 1e-2
+    # against torch fp32 math of the same layer on the GPU
+    sd = {k: v.float() for k, v in model.state_dict().items()}
+    ocfg = O.OracleConfig(vocab_size=2048, num_layers=1)
+    emb = torch.nn.functional.embedding(ids[:, :256], sd["model.embed_tokens.weight"])
+    ref = torch.nn.functional.linear(O.decoder_forward(sd, ocfg, emb, None, positions=torch.arange(256, device=DEV)),
+                                     sd["lm_head.weight"])
+    got = model(input_ids=ids[:, :256]).logits.float()
+    assert (got - ref).abs().max().item() <= 1e-2
