@@ -243,9 +243,9 @@ def main():
         return model.generate(ids_d, images=[img_d], max_new_tokens=DECODE_TOKENS, eos_token_id=None)
 
     def step_host():
-        ids = input_ids_h.to(device, non_blocking=True)
-        img = images_h.to(device, non_blocking=True).to(torch.bfloat16)
-        out = model.generate(ids, images=[img], max_new_tokens=DECODE_TOKENS, eos_token_id=None)
+        # public API with HOST (pinned) inputs: generate() validates the token grammar on the host ids,
+        # copies ids + fp32 pixels to the device (H2D inside the timed region) and decodes
+        out = model.generate(input_ids_h, images=[images_h], max_new_tokens=DECODE_TOKENS, eos_token_id=None)
         return out[:, SEQ_LEN:].cpu()   # device -> host read of the step's result (generated ids)
 
     def barrier():

@@ -82,27 +82,35 @@ class DecodeRunner:
                                        self.n_out.data_ptr(), self.pos.data_ptr(), self.out_ids.numel()),
               "merlin_record_advance")
 
+    def ensure_graph(self):
+        """Capture one greedy step (embed -> decoder -> argmax -> record/advance).  The warm-up run
+        outside capture scribbles on cache row `pos`; callers (re)fill the cache afterwards."""
+        if self.graph is not None:
+            return
+        self.pos.fill_(min(self.cache.seq_len, self.cache.capacity - 1))
+        self._greedy_body()  # warm-up outside capture (one-time kernel attributes)
+        torch.cuda.synchronize()
+        g = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(g):
+            self._greedy_body()
+        self.graph = g
+
     def greedy(self, first_token: torch.Tensor, n_tokens: int, eos_token_id=None, check_every: int = 16,
                use_graph: bool = True) -> torch.Tensor:
         """Feeds `first_token` (already chosen from the prefill logits) and decodes n_tokens more
         greedily without host round trips; returns the generated ids (truncated after eos)."""
-        n_tokens = min(n_tokens, self.cache.capacity - self.cache.seq_len)
+        if use_graph:
+            self.ensure_graph()
         self.token.copy_(first_token.reshape(1))
         self.pos.fill_(self.cache.seq_len)
         self.n_out.zero_()
-        if use_graph and self.graph is None:
-            self._greedy_body()  # warm-up outside capture (one-time kernel attributes)
-            self.token.copy_(first_token.reshape(1))
-            self.pos.fill_(self.cache.seq_len)
-            self.n_out.zero_()
-            torch.cuda.synchronize()
-            g = torch.cuda.CUDAGraph()
-            with torch.cuda.graph(g):
-                self._greedy_body()
-            self.graph = g
-            self.token.copy_(first_token.reshape(1))
-            self.pos.fill_(self.cache.seq_len)
-            self.n_out.zero_()
+        return self.run(n_tokens, eos_token_id, check_every, use_graph, base=0)
+
+    def run(self, n_tokens: int, eos_token_id=None, check_every: int = 16, use_graph: bool = True,
+            base: int = 0) -> torch.Tensor:
+        """Decode n_tokens more from the device-resident (token, pos, n_out) state; `base` tokens were
+        already recorded in out_ids by the caller.  Returns out_ids[base : base + done]."""
+        n_tokens = min(n_tokens, self.cache.capacity - self.cache.seq_len)
         done = 0
         while done < n_tokens:
             chunk = min(check_every, n_tokens - done)
@@ -114,10 +122,88 @@ class DecodeRunner:
                 _ops.PROFILE.launches += self.launches_per_step + 3
             done += chunk
             if eos_token_id is not None:
-                ids = self.out_ids[:done]
+                ids = self.out_ids[base:base + done]
                 hit = (ids == eos_token_id).nonzero()
                 if hit.numel():
                     done = int(hit[0]) + 1
                     break
         self.cache.seq_len += done
-        return self.out_ids[:done].clone()
+        return self.out_ids[base:base + done].clone()
+
+
+class GraphedGenerator:
+    """Whole generate() step from CUDA graphs for one (sequence length, image batch) shape: static
+    input buffers, one graph for the multimodal prefill (ViT -> projector -> splice -> 32 layers ->
+    lm_head -> argmax of the last row), then DecodeRunner's per-token graph."""
+
+    def __init__(self, lm, S: int, image_shape, capacity: int):
+        from .mmgpt.model.mmgpt.llama_mmgpt import MerlinKVCache
+        cfg = lm.config
+        dev = lm.device
+        self.lm, self.S = lm, S
+        self.ids = torch.zeros((1, S), dtype=torch.int64, device=dev)
+        self.img = torch.zeros(tuple(image_shape), dtype=torch.bfloat16, device=dev)
+        self.cache = MerlinKVCache(cfg.num_hidden_layers, 1, capacity, cfg.hidden_size, dev)
+        self.runner = DecodeRunner(lm, self.cache)
+        tower = lm.get_model().vision_tower
+        rows = image_shape[0] * tower.num_patches
+        self.feat_offset = torch.zeros(1, dtype=torch.int32, device=dev)
+        self.feat_limit = torch.full((1,), rows, dtype=torch.int32, device=dev)
+        self.scratch_pos = torch.zeros(1, dtype=torch.int32, device=dev)
+        self.per_image = tower.num_patches
+        self.cache.seq_len = S
+        self.runner.ensure_graph()
+        self._body()                       # warm-up outside capture
+        torch.cuda.synchronize()
+        g = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(g):
+            self._body()
+        self.graph = g
+        self.launches = None
+
+    def _body(self):
+        L_ = _lib.load()
+        r = self.runner
+        before = _ops.PROFILE.launches
+        logits2d = self.lm._prefill_core(self.ids, self.img, self.feat_offset, self.feat_limit, self.cache)
+        st = torch.cuda.current_stream().cuda_stream
+        V = self.lm.config.vocab_size
+        last = logits2d[self.S - 1:self.S]
+        check(L_.merlin_argmax(st, last.data_ptr(), logits2d.stride(0), 1, V, r.token.data_ptr()), "merlin_argmax")
+        r.n_out.zero_()
+        r.pos.fill_(self.S)
+        check(L_.merlin_record_advance(st, r.token.data_ptr(), r.out_ids.data_ptr(), r.n_out.data_ptr(),
+                                       self.scratch_pos.data_ptr(), r.out_ids.numel()), "merlin_record_advance")
+        self.launches = _ops.PROFILE.launches - before + 2
+        self.logits2d = logits2d
+
+    def generate(self, input_ids: torch.Tensor, images: torch.Tensor, max_new_tokens: int, eos_token_id=None):
+        ids_host = input_ids if not input_ids.is_cuda else input_ids.cpu()
+        self.lm._validate_image_grammar(ids_host, [images], self.per_image)
+        self.ids.copy_(input_ids, non_blocking=True)
+        self.img.copy_(images, non_blocking=True)
+        self.graph.replay()
+        _ops.PROFILE.launches += self.launches
+        self.cache.seq_len = self.S
+        new = None
+        if max_new_tokens > 1:
+            if eos_token_id is not None and int(self.runner.out_ids[0]) == eos_token_id:
+                pass
+            else:
+                self.runner.run(max_new_tokens - 1, eos_token_id, base=1)
+        n = int(self.cache.seq_len - self.S) + 1
+        new = self.runner.out_ids[:n]
+        return torch.cat([self.ids, new.view(1, -1)], dim=1)
+
+
+def graphed_generate(lm, input_ids, images, max_new_tokens, eos_token_id):
+    key = (int(input_ids.shape[1]), tuple(images.shape))
+    pool = lm.__dict__.setdefault("_graphed", {})
+    gen = pool.get(key)
+    need = input_ids.shape[1] + max_new_tokens + 8
+    if gen is None or gen.cache.capacity < need:
+        if len(pool) >= 4:
+            pool.pop(next(iter(pool)))
+        gen = GraphedGenerator(lm, int(input_ids.shape[1]), images.shape, need)
+        pool[key] = gen
+    return gen.generate(input_ids, images, max_new_tokens, eos_token_id)

@@ -336,8 +336,7 @@ class MMGPTLlamaForCausalLM(nn.Module, MMGPTMetaForCausalLM):
 
         seqlens = None
         if attention_mask is not None:
-            am = attention_mask
-            lens = am.sum(dim=-1)
+            lens = attention_mask.sum(dim=-1)
             if bool((lens != S).any()):
                 seqlens = lens.to(device=device, dtype=torch.int32)
         cache = None
@@ -348,8 +347,7 @@ class MMGPTLlamaForCausalLM(nn.Module, MMGPTMetaForCausalLM):
         if x.dtype != torch.bfloat16:
             x = x.to(torch.bfloat16)
         x = x.contiguous()
-        hidden, all_hidden = self.model.forward_layers(x, B, S, seqlens, cache, bool(output_hidden_states))
-        logits2d = ops.gemm(hidden, self.lm_head_w)          # [B*S, V] on a 16-byte aligned pitch
+        logits2d, hidden, all_hidden = self._decoder_core(x, B, S, seqlens, cache, bool(output_hidden_states))
         logits = logits2d.view(B, S, -1) if logits2d.is_contiguous() else logits2d.unflatten(0, (B, S))
 
         loss = None
@@ -364,6 +362,30 @@ class MMGPTLlamaForCausalLM(nn.Module, MMGPTMetaForCausalLM):
             return (loss,) + out if loss is not None else out
         return CausalLMOutputWithPast(loss=loss, logits=logits, past_key_values=cache, hidden_states=hs,
                                       attentions=None)
+
+    def _decoder_core(self, x, B, S, seqlens, cache, collect_hidden=False):
+        """Device-only tail of forward: decoder stack + lm_head (kernel launches only, graph-capturable)."""
+        hidden, all_hidden = self.model.forward_layers(x, B, S, seqlens, cache, collect_hidden)
+        logits2d = ops.gemm(hidden, self.lm_head_w)          # [B*S, V] on a 16-byte aligned pitch
+        return logits2d, hidden, all_hidden
+
+    def _prefill_core(self, ids_dev, images_bf16, feat_offset, feat_limit, cache):
+        """Device-only multimodal prefill for one pre-validated batch: ViT -> projector -> splice ->
+        decoder -> lm_head.  No host reads, so the whole thing can be captured in a CUDA graph."""
+        m = self.model
+        B, S = ids_dev.shape
+        tower, proj = m.vision_tower, m.projector
+        n = images_bf16.shape[0]
+        hidden = tower.encode(images_bf16)
+        if hasattr(proj, "project") and tower.select_feature == "patch":
+            grid = tower.config.image_size // tower.config.patch_size
+            feats = proj.project(hidden, n, grid, tower.tokens, 1)
+        else:
+            feats = proj([tower.feature_select(hidden, n)])[0]
+        feats = feats.reshape(-1, feats.shape[-1])
+        x, _ = ops.embed_splice(ids_dev, m.embed_tokens, feats, self.im_patch_token, feat_offset, feat_limit)
+        logits2d, _, _ = self._decoder_core(x, B, S, None, cache)
+        return logits2d
 
     # ------------------------------------------------------------------ generation (llama_mmgpt.py:114-134)
     def prepare_inputs_for_generation(self, input_ids, past_key_values=None, attention_mask=None,
@@ -396,6 +418,13 @@ class MMGPTLlamaForCausalLM(nn.Module, MMGPTMetaForCausalLM):
         if input_ids.shape[0] != 1:
             raise NotImplementedError("generate() handles one sequence at a time (reference eval scripts)")
         device = self.device
+        fast = (not do_sample and stopping_criteria is None and streamer is None and max_new_tokens > 0
+                and attention_mask is None and images is not None and len(images) == 1
+                and getattr(self, "use_cuda_graphs", True) and not getattr(self, "use_beam_search", False)
+                and getattr(self.model, "vision_tower", None) is not None)
+        if fast:
+            # whole step from CUDA graphs: 1 replay for the multimodal prefill, 1 per decoded token
+            return _decode.graphed_generate(self, input_ids, images[0], max_new_tokens, eos_token_id)
         ids = input_ids.to(device)
         self._cache_capacity = ids.shape[1] + max_new_tokens + 8
         inputs = self.prepare_inputs_for_generation(ids, None, attention_mask, use_cache=True, images=images)

@@ -223,6 +223,8 @@ def embed_splice(input_ids: torch.Tensor, embed_table: torch.Tensor, image_featu
     for t in (feat_offset, feat_limit):
         if t is not None and (t.dtype != torch.int32 or t.numel() != B):
             raise ValueError("embed_splice: feat_offset / feat_limit must be int32 [B]")
+    if B * S == 0:
+        return out, ws[B * S:]
     check(_lib.load().merlin_embed_splice(_stream(), input_ids.data_ptr(), embed_table.data_ptr(),
                                           _ptr(image_features), out.data_ptr(), ws.data_ptr(), B, S, D, nfeat,
                                           _ptr(feat_offset), _ptr(feat_limit), V, im_patch_token),

@@ -21,7 +21,7 @@ def close(got, ref, tol=TOL):
 
 
 def ints(shape):
-    return torch.randint(-2, 3, shape, device=DEV).to(torch.bfloat16)
+    return torch.randint(-1, 2, shape, device=DEV).to(torch.bfloat16)
 
 
 @pytest.mark.parametrize("cg", [1, 2])
@@ -32,7 +32,7 @@ def test_gemm_integer_operands_exact(cg, mnk):
     M, N, K = mnk
     a, w = ints((M, K)), ints((N, K))
     got = ops.gemm(a, w, cta_group=cg)
-    assert torch.equal(got.float(), a.float() @ w.float().t())   # |values| < 2^8: exact in bf16
+    assert torch.equal(got.float(), a.float() @ w.float().t())   # operands in {-1,0,1}: |sums| < 2^8, exact in bf16
 
 
 @pytest.mark.parametrize("cg", [1, 2])

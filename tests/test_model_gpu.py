@@ -135,7 +135,7 @@ def test_full_width_single_layer_properties():
     b = model(input_ids=ids).logits
     assert torch.equal(a, b)
     c = model(input_ids=ids[:, :1024]).logits
-    assert (a[:, :1024].float() - c.float()).abs().max().item() <= 1e-2
+    assert (a[:, :1024].float() - c.float()).abs().max().item() <= 2.0 ** -6 * a.float().abs().max().item()
     # against torch fp32 math of the same layer on the GPU
     sd = {k: v.float() for k, v in model.state_dict().items()}
     ocfg = O.OracleConfig(vocab_size=2048, num_layers=1)
@@ -143,4 +143,5 @@ def test_full_width_single_layer_properties():
     ref = torch.nn.functional.linear(O.decoder_forward(sd, ocfg, emb, None, positions=torch.arange(256, device=DEV)),
                                      sd["lm_head.weight"])
     got = model(input_ids=ids[:, :256]).logits.float()
-    assert (got - ref).abs().max().item() <= 1e-2
+    # |logits| reach ~5 here, where one bf16 ulp of the OUTPUT is already 3e-2: use the per-op bound
+    assert (got - ref).abs().max().item() <= 2.0 ** -6 * ref.abs().max().item()
