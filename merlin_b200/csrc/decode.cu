@@ -9,6 +9,8 @@
 #include "host.cuh"
 #include "ptx.cuh"
 
+#include <cstdlib>
+
 namespace mb {
 
 enum GemvMode : int {
@@ -61,6 +63,47 @@ gemv_pair_kernel(const GemvParams p) {
   const int nvec = p.K >> 3;
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
 
+  // ---- which two weight rows does this warp own?  (independent of any activation)
+  const int task = blockIdx.x * kGemvWarps + warp;
+  int row_a, row_b;
+  if (kMode == GEMV_QKV_ROPE) {
+    const int qk_tasks = p.D;  // 2*D rows of q,k -> D pairs (j, j+64)
+    if (task < qk_tasks) {
+      const int head = task >> 6, j = task & 63;  // head index over q heads then k heads
+      row_a = head * 128 + j;
+      row_b = row_a + 64;
+    } else {
+      row_a = 2 * p.D + 2 * (task - qk_tasks);
+      row_b = row_a + 1;
+    }
+  } else if (kMode == GEMV_SWIGLU) {
+    const int blk = task >> 7, j = task & 127;
+    row_a = blk * 256 + j;
+    row_b = row_a + 128;
+  } else {
+    row_a = 2 * task;
+    row_b = row_a + 1;
+  }
+  const bool active = row_a < p.N;
+  const bool has_b = row_b < p.N;
+  const uint4* wa = reinterpret_cast<const uint4*>(p.W + static_cast<size_t>(active ? row_a : 0) * p.K);
+  const uint4* wb = reinterpret_cast<const uint4*>(p.W + static_cast<size_t>(has_b ? row_b : (active ? row_a : 0)) * p.K);
+
+  // ---- prefetch the first weight batch (8 x 16 B per lane) BEFORE waiting on the producer kernel:
+  // with programmatic dependent launch this overlaps the previous kernel's tail and our own prologue.
+  uint4 a[4], b[4];
+#pragma unroll
+  for (int u = 0; u < 4; ++u) {
+    const int idx = lane + 32 * u;
+    a[u] = b[u] = make_uint4(0, 0, 0, 0);
+    if (active && idx < nvec) {
+      a[u] = ld_stream(wa + idx);
+      b[u] = ld_stream(wb + idx);
+    }
+  }
+  asm volatile("griddepcontrol.wait;" ::: "memory");          // producer's writes (x, residual) are visible
+  asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+
   // ---- prologue: stage x (optionally RMS-normalised, rounded to bf16 like the prefill path)
   const uint4* xg = reinterpret_cast<const uint4*>(p.x);
   if (p.norm_w != nullptr) {
@@ -91,46 +134,35 @@ gemv_pair_kernel(const GemvParams p) {
     for (int i = threadIdx.x; i < nvec; i += kGemvThreads) xs[i] = xg[i];
   }
   __syncthreads();
+  if (!active) return;
 
-  // ---- which two weight rows does this warp own?
-  const int task = blockIdx.x * kGemvWarps + warp;
-  int row_a, row_b;
-  if (kMode == GEMV_QKV_ROPE) {
-    const int qk_tasks = p.D;  // 2*D rows of q,k -> D pairs (j, j+64)
-    if (task < qk_tasks) {
-      const int head = task >> 6, j = task & 63;  // head index over q heads then k heads
-      row_a = head * 128 + j;
-      row_b = row_a + 64;
-    } else {
-      row_a = 2 * p.D + 2 * (task - qk_tasks);
-      row_b = row_a + 1;
-    }
-  } else if (kMode == GEMV_SWIGLU) {
-    const int blk = task >> 7, j = task & 127;
-    row_a = blk * 256 + j;
-    row_b = row_a + 128;
-  } else {
-    row_a = 2 * task;
-    row_b = row_a + 1;
-  }
-  if (row_a >= p.N) return;
-  const bool has_b = row_b < p.N;
-  const uint4* wa = reinterpret_cast<const uint4*>(p.W + static_cast<size_t>(row_a) * p.K);
-  const uint4* wb = reinterpret_cast<const uint4*>(p.W + static_cast<size_t>(has_b ? row_b : row_a) * p.K);
-
+  // ---- software-pipelined main loop: issue batch n+1, then consume batch n
   float sa = 0.f, sb = 0.f;
-  int i = lane;
-  for (; i + 96 < nvec; i += 128) {  // 8 independent 16-byte loads in flight per lane
-    const uint4 a0 = ld_stream(wa + i), a1 = ld_stream(wa + i + 32), a2 = ld_stream(wa + i + 64),
-                a3 = ld_stream(wa + i + 96);
-    const uint4 b0 = ld_stream(wb + i), b1 = ld_stream(wb + i + 32), b2 = ld_stream(wb + i + 64),
-                b3 = ld_stream(wb + i + 96);
-    sa += dot8(a0, xs[i]) + dot8(a1, xs[i + 32]) + dot8(a2, xs[i + 64]) + dot8(a3, xs[i + 96]);
-    sb += dot8(b0, xs[i]) + dot8(b1, xs[i + 32]) + dot8(b2, xs[i + 64]) + dot8(b3, xs[i + 96]);
-  }
-  for (; i < nvec; i += 32) {
-    sa += dot8(ld_stream(wa + i), xs[i]);
-    sb += dot8(ld_stream(wb + i), xs[i]);
+  for (int i = lane; i < nvec; i += 128) {
+    uint4 na[4], nb[4];
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      const int idx = i + 128 + 32 * u;
+      na[u] = nb[u] = make_uint4(0, 0, 0, 0);
+      if (idx < nvec) {
+        na[u] = ld_stream(wa + idx);
+        nb[u] = ld_stream(wb + idx);
+      }
+    }
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      const int idx = i + 32 * u;
+      if (idx < nvec) {
+        const uint4 xv = xs[idx];
+        sa += dot8(a[u], xv);
+        sb += dot8(b[u], xv);
+      }
+    }
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      a[u] = na[u];
+      b[u] = nb[u];
+    }
   }
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) {
@@ -182,6 +214,8 @@ flash_decode_partial_kernel(const __nv_bfloat16* __restrict__ q, const __nv_bflo
   __shared__ float s_o[16][128];
   __shared__ float s_m[16], s_l[16];
   const int h = blockIdx.x, split = blockIdx.y;
+  asm volatile("griddepcontrol.wait;" ::: "memory");
+  asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
   const int T = *pos_ptr + 1;
   const int chunk = (T + n_splits - 1) / n_splits;
   const int k0 = split * chunk;
@@ -206,15 +240,22 @@ flash_decode_partial_kernel(const __nv_bfloat16* __restrict__ q, const __nv_bflo
 #pragma unroll
   for (int e = 0; e < 16; ++e) o[e] = 0.f;
 
+  // software-pipelined over keys: the loads of key n+1 are in flight while key n is reduced
+  auto load_key = [&](int key, uint4 (&r)[4]) {
+    const bool live = key < k1;
+    const __nv_bfloat16* row = kv + static_cast<size_t>(live ? key : k0) * 2 * D + h * 128 + sub * 16;
+    r[0] = ld_stream(reinterpret_cast<const uint4*>(row));
+    r[1] = ld_stream(reinterpret_cast<const uint4*>(row) + 1);
+    r[2] = ld_stream(reinterpret_cast<const uint4*>(row + D));
+    r[3] = ld_stream(reinterpret_cast<const uint4*>(row + D) + 1);
+  };
+  uint4 cur[4], nxt[4];
+  if (k0 < k1) load_key(k0 + slot, cur);
   for (int base = k0; base < k1; base += 16) {
     const int key = base + slot;
     const bool live = key < k1;
-    const __nv_bfloat16* row = kv + static_cast<size_t>(live ? key : k0) * 2 * D + h * 128 + sub * 16;
-    const uint4 ka = ld_stream(reinterpret_cast<const uint4*>(row));
-    const uint4 kb = ld_stream(reinterpret_cast<const uint4*>(row) + 1);
-    const uint4 va = ld_stream(reinterpret_cast<const uint4*>(row + D));
-    const uint4 vb = ld_stream(reinterpret_cast<const uint4*>(row + D) + 1);
-    const uint32_t kw[8] = {ka.x, ka.y, ka.z, ka.w, kb.x, kb.y, kb.z, kb.w};
+    if (base + 16 < k1) load_key(key + 16, nxt);
+    const uint32_t kw[8] = {cur[0].x, cur[0].y, cur[0].z, cur[0].w, cur[1].x, cur[1].y, cur[1].z, cur[1].w};
     float s = 0.f;
 #pragma unroll
     for (int e = 0; e < 8; ++e) {
@@ -229,7 +270,7 @@ flash_decode_partial_kernel(const __nv_bfloat16* __restrict__ q, const __nv_bflo
       const float alpha = fast_exp2(m - m_new);
       const float pr = fast_exp2(s - m_new);
       l = l * alpha + pr;
-      const uint32_t vw[8] = {va.x, va.y, va.z, va.w, vb.x, vb.y, vb.z, vb.w};
+      const uint32_t vw[8] = {cur[2].x, cur[2].y, cur[2].z, cur[2].w, cur[3].x, cur[3].y, cur[3].z, cur[3].w};
 #pragma unroll
       for (int e = 0; e < 8; ++e) {
         o[2 * e] = fmaf(pr, bf16_lo(vw[e]), o[2 * e] * alpha);
@@ -237,6 +278,8 @@ flash_decode_partial_kernel(const __nv_bfloat16* __restrict__ q, const __nv_bflo
       }
       m = m_new;
     }
+#pragma unroll
+    for (int e = 0; e < 4; ++e) cur[e] = nxt[e];
   }
   // merge the 16 key slots of the block
 #pragma unroll
@@ -269,6 +312,8 @@ __global__ void __launch_bounds__(128)
 flash_decode_combine_kernel(const float* __restrict__ part_o, const float* __restrict__ part_ml,
                             int n_splits, __nv_bfloat16* __restrict__ out) {
   const int h = blockIdx.x, d = threadIdx.x;
+  asm volatile("griddepcontrol.wait;" ::: "memory");
+  asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
   float M = -INFINITY;
   for (int s = 0; s < n_splits; ++s) M = fmaxf(M, part_ml[(static_cast<size_t>(h) * n_splits + s) * 2]);
   float acc = 0.f, L = 0.f;
@@ -302,6 +347,23 @@ __global__ void record_advance_kernel(const int64_t* token, int64_t* out_ids, in
   }
 }
 
+// Launch config with programmatic dependent launch: the kernel may start while its predecessor in the
+// stream drains; it calls griddepcontrol.wait before touching anything the predecessor wrote.
+static bool g_use_pdl = true;
+static cudaLaunchAttribute g_pdl_attr;
+static cudaLaunchConfig_t pdl_config(dim3 grid, dim3 block, size_t smem, cudaStream_t st) {
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = grid;
+  cfg.blockDim = block;
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = st;
+  g_pdl_attr.id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  g_pdl_attr.val.programmaticStreamSerializationAllowed = g_use_pdl ? 1 : 0;
+  cfg.attrs = &g_pdl_attr;
+  cfg.numAttrs = 1;
+  return cfg;
+}
+
 template <int kMode>
 static int launch_gemv(cudaStream_t st, const GemvParams& p, int tasks) {
   const size_t smem = static_cast<size_t>(p.K) * 2;
@@ -313,8 +375,8 @@ static int launch_gemv(cudaStream_t st, const GemvParams& p, int tasks) {
   }
   MB_CHECK_ARG(smem <= 96 * 1024 && p.K % 8 == 0, "gemv: K=%d unsupported", p.K);
   const int blocks = (tasks + kGemvWarps - 1) / kGemvWarps;
-  gemv_pair_kernel<kMode><<<blocks, kGemvThreads, smem, st>>>(p);
-  MB_CHECK_CUDA(cudaGetLastError());
+  cudaLaunchConfig_t cfg = pdl_config(dim3(blocks), dim3(kGemvThreads), smem, st);
+  MB_CHECK_CUDA(cudaLaunchKernelEx(&cfg, gemv_pair_kernel<kMode>, p));
   return MERLIN_OK;
 }
 
@@ -338,6 +400,10 @@ int merlin_decode_step(void* stream, const merlin_decoder_weights* w, void* x, c
   MB_CHECK_ARG(w->hidden == w->heads * 128, "decode_step: head_dim must be 128");
   MB_CHECK_ARG(w->intermediate % 128 == 0 && n_splits >= 1 && n_splits <= 64, "decode_step: bad config");
   cudaStream_t st = static_cast<cudaStream_t>(stream);
+  {
+    const char* e = getenv("MERLIN_PDL");
+    g_use_pdl = !(e && e[0] == '0');
+  }
   const int D = w->hidden, FF = w->intermediate, H = w->heads;
   uint8_t* ws = static_cast<uint8_t*>(workspace);
   __nv_bfloat16* qbuf = reinterpret_cast<__nv_bfloat16*>(ws);
@@ -366,10 +432,15 @@ int merlin_decode_step(void* stream, const merlin_decoder_weights* w, void* x, c
     p.eps = w->rms_eps;
     if ((rc = launch_gemv<GEMV_QKV_ROPE>(st, p, 3 * D / 2)) != MERLIN_OK) return rc;
     // split-K attention over the cache (keys 0..pos)
-    flash_decode_partial_kernel<<<dim3(H, n_splits), kFdThreads, 0, st>>>(
-        qbuf, static_cast<const __nv_bfloat16*>(w->kv_cache[i]), pos_dev, D, n_splits, scale_log2e, part_o,
-        part_ml);
-    flash_decode_combine_kernel<<<H, 128, 0, st>>>(part_o, part_ml, n_splits, att);
+    {
+      cudaLaunchConfig_t cfg = pdl_config(dim3(H, n_splits), dim3(kFdThreads), 0, st);
+      MB_CHECK_CUDA(cudaLaunchKernelEx(&cfg, flash_decode_partial_kernel, static_cast<const __nv_bfloat16*>(qbuf),
+                                       static_cast<const __nv_bfloat16*>(w->kv_cache[i]), pos_dev, D, n_splits,
+                                       scale_log2e, part_o, part_ml));
+      cudaLaunchConfig_t cfg2 = pdl_config(dim3(H), dim3(128), 0, st);
+      MB_CHECK_CUDA(cudaLaunchKernelEx(&cfg2, flash_decode_combine_kernel, static_cast<const float*>(part_o),
+                                       static_cast<const float*>(part_ml), n_splits, att));
+    }
     // x += o_proj(att)
     GemvParams po = {};
     po.W = static_cast<const __nv_bfloat16*>(w->o_w[i]);
