@@ -1,8 +1,10 @@
 // merlin_b200 — host launcher for the flash-attention forward kernel (attn.cuh).
 #include "attn.cuh"
+#include "attn2.cuh"
 #include "host.cuh"
 
 #include <cmath>
+#include <cstdlib>
 
 namespace mb {
 
@@ -21,6 +23,33 @@ static int launch_attn(cudaStream_t stream, const CUtensorMap& tq, const CUtenso
   attn_fwd_kernel<HD, kCausal><<<grid, kAttnThreads, Cfg::kSmemBytes, stream>>>(tq, to, p);
   MB_CHECK_CUDA(cudaGetLastError());
   return MERLIN_OK;
+}
+
+template <int HD, bool kCausal>
+static int launch_attn2(cudaStream_t stream, const CUtensorMap& tq, const CUtensorMap& to,
+                        const AttnParams& p) {
+  using Cfg = Attn2Cfg<HD>;
+  static bool configured = false;
+  if (!configured) {
+    MB_CHECK_CUDA(cudaFuncSetAttribute(attn_fwd2_kernel<HD, kCausal>,
+                                       cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::kSmemBytes));
+    configured = true;
+  }
+  const int nq = (p.S + kAttnBlock - 1) / kAttnBlock;
+  dim3 grid(static_cast<unsigned>((nq + 1) / 2), static_cast<unsigned>(p.H), static_cast<unsigned>(p.B));
+  attn_fwd2_kernel<HD, kCausal><<<grid, kAttn2Threads, Cfg::kSmemBytes, stream>>>(tq, to, p);
+  MB_CHECK_CUDA(cudaGetLastError());
+  return MERLIN_OK;
+}
+
+// 1 = one query tile per CTA (attn.cuh), 2 = two query tiles, ping-pong softmax, P in TMEM (attn2.cuh)
+static int attn_version() {
+  static int v = -1;
+  if (v < 0) {
+    const char* e = getenv("MERLIN_ATTN_V");
+    v = (e && e[0] == '2') ? 2 : 1;
+  }
+  return v;
 }
 
 }  // namespace mb
@@ -64,6 +93,11 @@ extern "C" int merlin_flash_attn_fwd(void* stream, const void* qkv, int64_t ld_q
     if ((rc = make_tmap_bf16(&to, out, 3, dims, str, box)) != MERLIN_OK) return rc;
   }
   cudaStream_t st = static_cast<cudaStream_t>(stream);
+  if (attn_version() == 2) {
+    if (head_dim == 128)
+      return causal ? launch_attn2<128, true>(st, tq, to, p) : launch_attn2<128, false>(st, tq, to, p);
+    return causal ? launch_attn2<64, true>(st, tq, to, p) : launch_attn2<64, false>(st, tq, to, p);
+  }
   if (head_dim == 128)
     return causal ? launch_attn<128, true>(st, tq, to, p) : launch_attn<128, false>(st, tq, to, p);
   return causal ? launch_attn<64, true>(st, tq, to, p) : launch_attn<64, false>(st, tq, to, p);

@@ -151,6 +151,7 @@ class GraphedGenerator:
         self.feat_limit = torch.full((1,), rows, dtype=torch.int32, device=dev)
         self.scratch_pos = torch.zeros(1, dtype=torch.int32, device=dev)
         self.per_image = tower.num_patches
+        self.launches = 0
         self.cache.seq_len = S
         self.runner.ensure_graph()
         self._body()                       # warm-up outside capture
@@ -159,7 +160,6 @@ class GraphedGenerator:
         with torch.cuda.graph(g):
             self._body()
         self.graph = g
-        self.launches = None
 
     def _body(self):
         L_ = _lib.load()
