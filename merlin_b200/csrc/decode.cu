@@ -31,6 +31,7 @@ struct GemvParams {
   const int* pos;                 // device scalar: position of the token being decoded
   int N, K, D;
   float eps;
+  int ksplit;                     // 1, 2 or 4 warps per row pair
 };
 
 constexpr int kGemvWarps = 4;
@@ -60,11 +61,16 @@ __global__ void __launch_bounds__(kGemvThreads)
 gemv_pair_kernel(const GemvParams p) {
   extern __shared__ uint4 xs[];  // K bf16 (normalised) activation
   __shared__ float red[kGemvWarps];
+  __shared__ float part[kGemvWarps][2];
   const int nvec = p.K >> 3;
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
 
   // ---- which two weight rows does this warp own?  (independent of any activation)
-  const int task = blockIdx.x * kGemvWarps + warp;
+  // ksplit adjacent warps share one row pair and split K between them (more CTAs for small N).
+  const int ksplit = p.ksplit;
+  const int kpart = warp % ksplit;
+  const int v0 = (nvec * kpart) / ksplit, v1 = (nvec * (kpart + 1)) / ksplit;
+  const int task = (blockIdx.x * kGemvWarps + warp) / ksplit;
   int row_a, row_b;
   if (kMode == GEMV_QKV_ROPE) {
     const int qk_tasks = p.D;  // 2*D rows of q,k -> D pairs (j, j+64)
@@ -94,9 +100,9 @@ gemv_pair_kernel(const GemvParams p) {
   uint4 a[4], b[4];
 #pragma unroll
   for (int u = 0; u < 4; ++u) {
-    const int idx = lane + 32 * u;
+    const int idx = v0 + lane + 32 * u;
     a[u] = b[u] = make_uint4(0, 0, 0, 0);
-    if (active && idx < nvec) {
+    if (active && idx < v1) {
       a[u] = ld_stream(wa + idx);
       b[u] = ld_stream(wb + idx);
     }
@@ -134,17 +140,16 @@ gemv_pair_kernel(const GemvParams p) {
     for (int i = threadIdx.x; i < nvec; i += kGemvThreads) xs[i] = xg[i];
   }
   __syncthreads();
-  if (!active) return;
 
   // ---- software-pipelined main loop: issue batch n+1, then consume batch n
   float sa = 0.f, sb = 0.f;
-  for (int i = lane; i < nvec; i += 128) {
+  for (int i = v0 + lane; active && i < v1; i += 128) {
     uint4 na[4], nb[4];
 #pragma unroll
     for (int u = 0; u < 4; ++u) {
       const int idx = i + 128 + 32 * u;
       na[u] = nb[u] = make_uint4(0, 0, 0, 0);
-      if (idx < nvec) {
+      if (idx < v1) {
         na[u] = ld_stream(wa + idx);
         nb[u] = ld_stream(wb + idx);
       }
@@ -152,7 +157,7 @@ gemv_pair_kernel(const GemvParams p) {
 #pragma unroll
     for (int u = 0; u < 4; ++u) {
       const int idx = i + 32 * u;
-      if (idx < nvec) {
+      if (idx < v1) {
         const uint4 xv = xs[idx];
         sa += dot8(a[u], xv);
         sb += dot8(b[u], xv);
@@ -169,7 +174,20 @@ gemv_pair_kernel(const GemvParams p) {
     sa += __shfl_xor_sync(0xffffffffu, sa, o);
     sb += __shfl_xor_sync(0xffffffffu, sb, o);
   }
-  if (lane != 0) return;
+  if (ksplit > 1) {  // combine the K partitions of this row pair (adjacent warps) through shared memory
+    if (lane == 0) {
+      part[warp][0] = sa;
+      part[warp][1] = sb;
+    }
+    __syncthreads();
+    if (kpart == 0) {
+      for (int s2 = 1; s2 < ksplit; ++s2) {
+        sa += part[warp + s2][0];
+        sb += part[warp + s2][1];
+      }
+    }
+  }
+  if (lane != 0 || kpart != 0 || !active) return;
 
   if (kMode == GEMV_QKV_ROPE) {
     const int pos = *p.pos;
@@ -364,8 +382,14 @@ static cudaLaunchConfig_t pdl_config(dim3 grid, dim3 block, size_t smem, cudaStr
   return cfg;
 }
 
+static int env_int(const char* name, int dflt) {
+  const char* e = getenv(name);
+  return e ? atoi(e) : dflt;
+}
+
 template <int kMode>
-static int launch_gemv(cudaStream_t st, const GemvParams& p, int tasks) {
+static int launch_gemv(cudaStream_t st, GemvParams p, int tasks, int ksplit) {
+  p.ksplit = ksplit;
   const size_t smem = static_cast<size_t>(p.K) * 2;
   static bool configured = false;
   if (!configured) {
@@ -374,7 +398,7 @@ static int launch_gemv(cudaStream_t st, const GemvParams& p, int tasks) {
     configured = true;
   }
   MB_CHECK_ARG(smem <= 96 * 1024 && p.K % 8 == 0, "gemv: K=%d unsupported", p.K);
-  const int blocks = (tasks + kGemvWarps - 1) / kGemvWarps;
+  const int blocks = (tasks * p.ksplit + kGemvWarps - 1) / kGemvWarps;
   cudaLaunchConfig_t cfg = pdl_config(dim3(blocks), dim3(kGemvThreads), smem, st);
   MB_CHECK_CUDA(cudaLaunchKernelEx(&cfg, gemv_pair_kernel<kMode>, p));
   return MERLIN_OK;
@@ -405,6 +429,9 @@ int merlin_decode_step(void* stream, const merlin_decoder_weights* w, void* x, c
     g_use_pdl = !(e && e[0] == '0');
   }
   const int D = w->hidden, FF = w->intermediate, H = w->heads;
+  // warps per row pair: more CTAs in flight for the small-N projections (tunable for experiments)
+  static const int ks_qkv = env_int("MERLIN_KS_QKV", 1), ks_o = env_int("MERLIN_KS_O", 2),
+                   ks_gu = env_int("MERLIN_KS_GU", 1), ks_down = env_int("MERLIN_KS_DOWN", 4);
   uint8_t* ws = static_cast<uint8_t*>(workspace);
   __nv_bfloat16* qbuf = reinterpret_cast<__nv_bfloat16*>(ws);
   __nv_bfloat16* att = qbuf + D;
@@ -430,7 +457,7 @@ int merlin_decode_step(void* stream, const merlin_decoder_weights* w, void* x, c
     p.K = D;
     p.D = D;
     p.eps = w->rms_eps;
-    if ((rc = launch_gemv<GEMV_QKV_ROPE>(st, p, 3 * D / 2)) != MERLIN_OK) return rc;
+    if ((rc = launch_gemv<GEMV_QKV_ROPE>(st, p, 3 * D / 2, ks_qkv)) != MERLIN_OK) return rc;
     // split-K attention over the cache (keys 0..pos)
     {
       cudaLaunchConfig_t cfg = pdl_config(dim3(H, n_splits), dim3(kFdThreads), 0, st);
@@ -450,7 +477,7 @@ int merlin_decode_step(void* stream, const merlin_decoder_weights* w, void* x, c
     po.N = D;
     po.K = D;
     po.D = D;
-    if ((rc = launch_gemv<GEMV_PLAIN>(st, po, D / 2)) != MERLIN_OK) return rc;
+    if ((rc = launch_gemv<GEMV_PLAIN>(st, po, D / 2, ks_o)) != MERLIN_OK) return rc;
     // RMSNorm -> gate/up GEMV -> SwiGLU
     GemvParams pg = {};
     pg.W = static_cast<const __nv_bfloat16*>(w->gate_up_w[i]);
@@ -461,7 +488,7 @@ int merlin_decode_step(void* stream, const merlin_decoder_weights* w, void* x, c
     pg.K = D;
     pg.D = D;
     pg.eps = w->rms_eps;
-    if ((rc = launch_gemv<GEMV_SWIGLU>(st, pg, FF)) != MERLIN_OK) return rc;
+    if ((rc = launch_gemv<GEMV_SWIGLU>(st, pg, FF, ks_gu)) != MERLIN_OK) return rc;
     // x += down(mid)
     GemvParams pd = {};
     pd.W = static_cast<const __nv_bfloat16*>(w->down_w[i]);
@@ -471,7 +498,7 @@ int merlin_decode_step(void* stream, const merlin_decoder_weights* w, void* x, c
     pd.N = D;
     pd.K = FF;
     pd.D = D;
-    if ((rc = launch_gemv<GEMV_PLAIN>(st, pd, D / 2)) != MERLIN_OK) return rc;
+    if ((rc = launch_gemv<GEMV_PLAIN>(st, pd, D / 2, ks_down)) != MERLIN_OK) return rc;
   }
   // final RMSNorm -> lm_head
   GemvParams pl = {};
@@ -483,7 +510,7 @@ int merlin_decode_step(void* stream, const merlin_decoder_weights* w, void* x, c
   pl.K = D;
   pl.D = D;
   pl.eps = w->rms_eps;
-  if ((rc = launch_gemv<GEMV_PLAIN>(st, pl, (w->vocab + 1) / 2)) != MERLIN_OK) return rc;
+  if ((rc = launch_gemv<GEMV_PLAIN>(st, pl, (w->vocab + 1) / 2, 1)) != MERLIN_OK) return rc;
   MB_CHECK_CUDA(cudaGetLastError());
   return MERLIN_OK;
 }

@@ -145,3 +145,24 @@ def test_full_width_single_layer_properties():
     got = model(input_ids=ids[:, :256]).logits.float()
     # |logits| reach ~5 here, where one bf16 ulp of the OUTPUT is already 3e-2: use the per-op bound
     assert (got - ref).abs().max().item() <= 2.0 ** -6 * ref.abs().max().item()
+
+
+def test_operator_seam_in_hf_llama_matches_eager():
+    """replace_llama_attn_with_flash_attn(): HF LlamaModel dispatching to merlin_flash_attn_fwd through
+    the attention registry equals HF eager attention (valid rows), incl. a right-padded sample."""
+    from transformers import LlamaConfig, LlamaModel
+    from merlin_b200.mmgpt.utils.llama_flash_attn_monkey_patch import replace_llama_attn_with_flash_attn
+    name = replace_llama_attn_with_flash_attn()
+    cfg = LlamaConfig(vocab_size=300, hidden_size=256, intermediate_size=384, num_hidden_layers=2,
+                      num_attention_heads=2, num_key_value_heads=2, attn_implementation="eager")
+    torch.manual_seed(0)
+    m = LlamaModel(cfg).to(DEV, torch.bfloat16).eval()
+    ids = torch.randint(0, 300, (2, 200), device=DEV)
+    mask = torch.ones(2, 200, dtype=torch.long, device=DEV)
+    mask[1, 150:] = 0
+    with torch.no_grad():
+        ref = m(input_ids=ids, attention_mask=mask).last_hidden_state.float()
+        m.config._attn_implementation = name
+        got = m(input_ids=ids, attention_mask=mask).last_hidden_state.float()
+    valid = mask.bool()
+    assert (got[valid] - ref[valid]).abs().max().item() <= 2.0 ** -5 * ref[valid].abs().max().item()
