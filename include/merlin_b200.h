@@ -44,6 +44,15 @@ int merlin_gemm_bf16(void* stream, const void* A, int64_t lda, const void* B, in
                      int64_t ldc, const void* R, int64_t ldr, const void* bias, int M, int N, int K,
                      int epilogue, int cta_group);
 
+/* Same contraction with explicit operand layouts, for the backward GEMMs.  a_mn_major != 0: A is given as
+ * the row-major [K, M] matrix Aᵀ (lda = its row pitch); b_mn_major != 0: B is given as the row-major
+ * [K, N] matrix Bᵀ.  dgrad  dX[M,Kin] = dY[M,N]·W[N,Kin]   -> (A=dY, B=W with b_mn_major=1, "N"=Kin, "K"=N);
+ * wgrad  dW[N,Kin] = dYᵀ·X -> (A=dY with a_mn_major=1, B=X with b_mn_major=1, "M"=N, "N"=Kin, "K"=tokens);
+ * EPI_RESIDUAL with R == C accumulates into an existing gradient.  (autograd of the nn.Linear calls above) */
+int merlin_gemm_bf16_ex(void* stream, const void* A, int64_t lda, int a_mn_major, const void* B, int64_t ldb,
+                        int b_mn_major, void* C, int64_t ldc, const void* R, int64_t ldr, const void* bias,
+                        int M, int N, int K, int epilogue, int cta_group);
+
 /* qkv[M, N] = A[M,K] · Wqkv[N,K]ᵀ with half-split rotary embedding (head_dim 128, fp32 cos/sin
  * tables [max_pos,64]) applied in the epilogue to columns [0, rope_cols) — the q and k blocks.
  * Row r uses position positions[r] (or r % seq_len when positions == NULL).
@@ -111,6 +120,10 @@ int merlin_embed_splice(void* stream, const int64_t* input_ids, const void* embe
  * Stand-alone form of the merlin_gemm_qkv_rope epilogue (HF:llama/modeling_llama.py:138-168). */
 int merlin_rope_qk_inplace(void* stream, void* qkv, int64_t ld, const float* rope_cos,
                            const float* rope_sin, const int* positions, int M, int H, int seq_len);
+/* Same with an explicit direction: inverse != 0 rotates by −θ (the backward of the rotation). */
+int merlin_rope_qk_inplace_ex(void* stream, void* qkv, int64_t ld, const float* rope_cos,
+                              const float* rope_sin, const int* positions, int M, int H, int seq_len,
+                              int inverse);
 
 /* Shifted causal-LM cross-entropy: row (b,t) scores labels[b,t+1]; rows whose label is ignore_index
  * (or t == S-1) are skipped.  loss_sum_count[0] = Σ nll, [1] = #scored rows (mean = sum/count);
@@ -159,6 +172,63 @@ int merlin_embed_token(void* stream, const void* embed_table, const int64_t* tok
 /* out_ids[*n_out_dev] = *token_dev; ++*n_out_dev; ++*pos_dev  — closes one greedy step on the device. */
 int merlin_record_advance(void* stream, const int64_t* token_dev, int64_t* out_ids, int* n_out_dev,
                           int* pos_dev, int capacity);
+
+/* ---- backward / optimizer (training path; autograd of the ops above + the step loop of
+ * mmgpt/engine/train/trainer.py:45-74 with mmgpt/utils/llrd_utils.py param groups) ---- */
+
+/* RMSNorm backward: dx = rstd·(w⊙dy − x̂·mean(w⊙dy⊙x̂)) (+ dres, the gradient arriving through the residual
+ * connection; NULL = none); dweight[D] (fp32, NULL = skip) accumulates Σ_rows dy⊙x̂. */
+int merlin_rmsnorm_bwd(void* stream, const void* x, const void* weight, const void* dy, const void* dres,
+                       void* dx, float* dweight, int M, int D, float eps);
+
+/* Training form of LlamaMLP's activation: gate_up[M, 2FF] is the plain output of the packed gate/up GEMM
+ * (kept for backward); mid[M, FF] = silu(gate)·up.  Backward: dgate_up (may alias gate_up) from dmid. */
+int merlin_swiglu_fwd(void* stream, const void* gate_up, void* mid, int M, int FF);
+int merlin_swiglu_bwd(void* stream, const void* gate_up, const void* dmid, void* dgate_up, int M, int FF);
+
+/* dlogits = (softmax(logits) − onehot(labels shifted)) · grad_scale / count for scored rows, 0 elsewhere;
+ * may run in place (dlogits == logits).  loss_sum_count from merlin_cross_entropy_fwd. */
+int merlin_cross_entropy_bwd(void* stream, const void* logits, int64_t ld, const int64_t* labels, int B, int S,
+                             int V, int64_t ignore_index, const float* loss_sum_count, float grad_scale,
+                             void* dlogits, int64_t ldd);
+
+/* Backward of merlin_embed_splice: rows of <im_patch> tokens (rank >= 0) are copied to
+ * dimage_features[rank], all other rows are added into dembed_table[input_ids[t]] (either may be NULL). */
+int merlin_embed_splice_bwd(void* stream, const int64_t* input_ids, const int* rank, const void* dx,
+                            void* dembed_table, void* dimage_features, int T, int D, int n_feature_rows,
+                            int64_t vocab);
+
+/* out[N] (fp32) += column sums of x[M,N] (bias gradients). */
+int merlin_colsum(void* stream, const void* x, int64_t ld, float* out, int M, int N);
+
+/* delta[B,H,S] = rowsum(dO ∘ O): pre-pass of the flash-attention backward. */
+int merlin_attn_delta(void* stream, const void* out, const void* dout, float* delta, int B, int S, int H,
+                      int head_dim, int64_t ld);
+
+/* Flash-attention backward (head_dim 128): dqkv[B*S, ld_dqkv] packed [dq|dk|dv] from the forward's packed
+ * qkv, its output `out`, the incoming gradient `dout`, and the saved log-sum-exp.  dq/dk are gradients
+ * w.r.t. the ROTATED q/k (apply merlin_rope_qk_inplace(..., inverse) afterwards).  workspace:
+ * merlin_flash_attn_bwd_workspace_bytes() bytes (delta + fp32 dq accumulator).
+ * Replaces the backward of flash_attn_varlen_qkvpacked_func (monkey_patch.py:82-95). */
+size_t merlin_flash_attn_bwd_workspace_bytes(int B, int S, int H, int head_dim);
+int merlin_flash_attn_bwd(void* stream, const void* qkv, int64_t ld_qkv, const void* out, const void* dout,
+                          int64_t ld_out, const float* lse, const int* seqlens, void* dqkv, int64_t ld_dqkv,
+                          void* workspace, int B, int S, int H, int head_dim, int causal, float softmax_scale);
+
+/* out[0] = Σ g² over a flat bf16 gradient arena of n elements (n % 8 == 0): global grad norm. */
+int merlin_grad_sumsq(void* stream, const void* grads, int64_t n, float* out);
+
+/* Fused AdamW over flat bf16 arenas (params, grads, exp_avg, exp_avg_sq; n elements).  Elements
+ * [c·chunk, (c+1)·chunk) use lr·lr_mult[c] and weight_decay[c] (LLRD / no-decay groups; lr_mult 0 freezes).
+ * Gradients are scaled by grad_scale and clipped to max_grad_norm (<= 0: off) using grad_sumsq[0].
+ * torch.optim.AdamW update rule, fp32 math, bf16 state (the reference keeps bf16 weights and state). */
+int merlin_adamw_step(void* stream, void* params, const void* grads, void* exp_avg, void* exp_avg_sq,
+                      const float* lr_mult, const float* weight_decay, int chunk, int64_t n, float lr, float beta1,
+                      float beta2, float eps, int step, float grad_scale, float max_grad_norm,
+                      const float* grad_sumsq);
+
+/* y[n] (bf16) = x[n] (fp32): folds fp32 accumulators (norm-weight / bias gradients) into the arena. */
+int merlin_f32_to_bf16(void* stream, const float* x, void* y, int64_t n);
 
 #ifdef __cplusplus
 }

@@ -1,8 +1,10 @@
 // merlin_b200 — host launcher for the flash-attention forward kernel (attn.cuh).
 #include "attn.cuh"
 #include "attn2.cuh"
+#include "attn_bwd.cuh"
 #include "host.cuh"
 
+#include <algorithm>
 #include <cmath>
 #include <cstdlib>
 
@@ -101,4 +103,76 @@ extern "C" int merlin_flash_attn_fwd(void* stream, const void* qkv, int64_t ld_q
   if (head_dim == 128)
     return causal ? launch_attn<128, true>(st, tq, to, p) : launch_attn<128, false>(st, tq, to, p);
   return causal ? launch_attn<64, true>(st, tq, to, p) : launch_attn<64, false>(st, tq, to, p);
+}
+
+extern "C" int merlin_attn_delta(void* stream, const void* out, const void* dout, float* delta, int B, int S,
+                                 int H, int head_dim, int64_t ld);
+
+extern "C" size_t merlin_flash_attn_bwd_workspace_bytes(int B, int S, int H, int head_dim) {
+  return (static_cast<size_t>(B) * H * S + static_cast<size_t>(B) * S * H * head_dim) * sizeof(float);
+}
+
+extern "C" int merlin_flash_attn_bwd(void* stream, const void* qkv, int64_t ld_qkv, const void* out,
+                                     const void* dout, int64_t ld_out, const float* lse, const int* seqlens,
+                                     void* dqkv, int64_t ld_dqkv, void* workspace, int B, int S, int H,
+                                     int head_dim, int causal, float softmax_scale) {
+  using namespace mb;
+  MB_CHECK_ARG(qkv && out && dout && lse && dqkv && workspace, "flash_attn_bwd: null tensor");
+  MB_CHECK_ARG(head_dim == 128, "flash_attn_bwd: only head_dim 128 (the Vicuna decoder) is built");
+  MB_CHECK_ARG(B > 0 && S > 0 && H > 0, "flash_attn_bwd: empty problem");
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  float* delta = static_cast<float*>(workspace);
+  float* dq_acc = delta + static_cast<size_t>(B) * H * S;
+  int rc = merlin_attn_delta(stream, out, dout, delta, B, S, H, head_dim, ld_out);
+  if (rc != MERLIN_OK) return rc;
+  MB_CHECK_CUDA(cudaMemsetAsync(dq_acc, 0, static_cast<size_t>(B) * S * H * head_dim * sizeof(float), st));
+
+  AttnBwdParams p = {};
+  p.B = B;
+  p.S = S;
+  p.H = H;
+  p.q_col0 = 0;
+  p.k_col0 = H * head_dim;
+  p.v_col0 = 2 * H * head_dim;
+  p.scale = softmax_scale > 0.f ? softmax_scale : 1.0f / std::sqrt(static_cast<float>(head_dim));
+  p.scale_log2e = p.scale * 1.4426950408889634f;
+  p.seqlens = seqlens;
+  p.lse = lse;
+  p.delta = delta;
+  p.dq_accum = dq_acc;
+  p.dqkv = static_cast<__nv_bfloat16*>(dqkv);
+  p.ld_dqkv = ld_dqkv;
+
+  CUtensorMap tq, tdo;
+  {
+    uint64_t dims[3] = {static_cast<uint64_t>(3) * H * head_dim, static_cast<uint64_t>(S), static_cast<uint64_t>(B)};
+    uint64_t str[2] = {static_cast<uint64_t>(ld_qkv) * 2, static_cast<uint64_t>(ld_qkv) * 2 * S};
+    uint32_t box[3] = {64, kBwdBlock, 1};
+    if ((rc = make_tmap_bf16(&tq, qkv, 3, dims, str, box)) != MERLIN_OK) return rc;
+  }
+  {
+    uint64_t dims[3] = {static_cast<uint64_t>(H) * head_dim, static_cast<uint64_t>(S), static_cast<uint64_t>(B)};
+    uint64_t str[2] = {static_cast<uint64_t>(ld_out) * 2, static_cast<uint64_t>(ld_out) * 2 * S};
+    uint32_t box[3] = {64, kBwdBlock, 1};
+    if ((rc = make_tmap_bf16(&tdo, dout, 3, dims, str, box)) != MERLIN_OK) return rc;
+  }
+  static bool configured = false;
+  if (!configured) {
+    MB_CHECK_CUDA(cudaFuncSetAttribute(attn_bwd_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                       AttnBwdCfg::kSmemBytes));
+    MB_CHECK_CUDA(cudaFuncSetAttribute(attn_bwd_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                       AttnBwdCfg::kSmemBytes));
+    configured = true;
+  }
+  dim3 grid(static_cast<unsigned>((S + kBwdBlock - 1) / kBwdBlock), static_cast<unsigned>(H),
+            static_cast<unsigned>(B));
+  if (causal) attn_bwd_kernel<true><<<grid, kBwdThreads, AttnBwdCfg::kSmemBytes, st>>>(tq, tdo, p);
+  else attn_bwd_kernel<false><<<grid, kBwdThreads, AttnBwdCfg::kSmemBytes, st>>>(tq, tdo, p);
+  MB_CHECK_CUDA(cudaGetLastError());
+  const int64_t rows = static_cast<int64_t>(B) * S;
+  const int width = H * head_dim;
+  dq_to_bf16_kernel<<<static_cast<unsigned>(std::min<int64_t>((rows * (width / 8) + 255) / 256, 148 * 16)), 256, 0, st>>>(
+      dq_acc, static_cast<__nv_bfloat16*>(dqkv), ld_dqkv, 0, width, rows);
+  MB_CHECK_CUDA(cudaGetLastError());
+  return MERLIN_OK;
 }

@@ -1,0 +1,296 @@
+// merlin_b200 — flash-attention backward for sm_100a (tcgen05 + TMEM + TMA), head_dim 128.
+//
+// One CTA owns a 128-key tile j of one head and walks the query tiles i that attend to it
+// (i >= j when causal).  Per (i, j):
+//     S  = Q_i K_jᵀ            dP = dO_i V_jᵀ                      (tcgen05 -> TMEM, fp32)
+//     P  = exp2(S·c − lse_i)    dS = P ∘ (dP − δ_i) · scale         (128 threads, one query row each)
+//     dV += Pᵀ dO_i            dK += dSᵀ Q_i            dQ_i = dS K_j
+// dK / dV accumulate in TMEM across the whole walk and are written once; dQ_i is reduced into an fp32
+// global buffer with red.global.add (the cross-CTA reduction over key tiles).  P and dS are written
+// once to 128B-swizzled shared tiles and consumed both K-major (dQ) and MN-major (dV, dK: the same
+// bytes, described with the M and K roles swapped), as are the Q / dO / K / V row-major TMA tiles.
+// TMEM: S|dQ [0,128)  dP [128,256)  dV [256,384)  dK [384,512).
+#pragma once
+#include "ptx.cuh"
+
+namespace mb {
+
+constexpr int kBwdThreads = 256;
+constexpr int kBwdBlock = 128;
+
+struct AttnBwdParams {
+  int B, S, H;
+  int q_col0, k_col0, v_col0;   // column offsets inside packed qkv / dqkv rows
+  float scale;                  // softmax scale
+  float scale_log2e;
+  const int* seqlens;           // [B] or nullptr
+  const float* lse;             // [B, H, S] natural log-sum-exp from the forward
+  const float* delta;           // [B, H, S] rowsum(dO ∘ O)
+  float* dq_accum;              // [B*S, H*128] fp32, zero-initialised
+  __nv_bfloat16* dqkv;          // [B*S, ld_dqkv] packed gradient (k and v blocks written here)
+  int64_t ld_dqkv;
+};
+
+struct AttnBwdCfg {
+  static constexpr int kTileBytes = kBwdBlock * 128 * 2;        // 32 KB: [128 rows x 128] bf16
+  static constexpr int kSmemTiles = kTileBytes * 6;             // K, V, Q, dO, P, dS
+  static constexpr int kNumBars = 8;
+  static constexpr int kSmemBytes = kSmemTiles + kNumBars * 8 + 16 + 1024;
+};
+
+__device__ __forceinline__ void red_add_f32(float* addr, float v) {
+  asm volatile("red.global.add.f32 [%0], %1;" ::"l"(addr), "f"(v) : "memory");
+}
+
+template <bool kCausal>
+__global__ void __launch_bounds__(kBwdThreads, 1)
+attn_bwd_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid_constant__ CUtensorMap tm_do,
+                const AttnBwdParams p) {
+  using Cfg = AttnBwdCfg;
+  constexpr int HD = 128;
+  constexpr int kAtomBytes = kBwdBlock * 128;   // 16 KB: [128 rows x 64 bf16]
+
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) &
+                                             ~static_cast<uintptr_t>(1023));
+  uint8_t* sk = smem;
+  uint8_t* sv = sk + Cfg::kTileBytes;
+  uint8_t* sq = sv + Cfg::kTileBytes;
+  uint8_t* sdo = sq + Cfg::kTileBytes;
+  uint8_t* sp = sdo + Cfg::kTileBytes;
+  uint8_t* sds = sp + Cfg::kTileBytes;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + Cfg::kSmemTiles);
+  uint64_t* kv_full = bars;        // K_j, V_j landed (once)
+  uint64_t* qdo_full = bars + 1;   // Q_i, dO_i landed
+  uint64_t* qdo_empty = bars + 2;  // MMAs of step i no longer read Q_i / dO_i / P / dS
+  uint64_t* sdp_full = bars + 3;   // S and dP in TMEM
+  uint64_t* pds_full = bars + 4;   // P and dS in shared memory (128 arrivals)
+  uint64_t* dq_full = bars + 5;    // dV, dK, dQ MMAs of step i complete
+  uint64_t* dq_read = bars + 6;    // dQ drained from TMEM (128 arrivals): S region reusable
+  uint32_t* tmem_ptr_smem = reinterpret_cast<uint32_t*>(bars + Cfg::kNumBars);
+
+  const int warp = threadIdx.x >> 5;
+  const int j = blockIdx.x;   // key tile
+  const int head = blockIdx.y;
+  const int batch = blockIdx.z;
+  const int len = p.seqlens ? p.seqlens[batch] : p.S;
+  const int nq = (min(len, p.S) + kBwdBlock - 1) / kBwdBlock;   // query tiles that contain valid rows
+  const int kv0 = j * kBwdBlock;
+  const int i_begin = kCausal ? j : 0;
+  const bool has_work = kv0 < len && i_begin < nq;
+  const int n_steps = has_work ? (nq - i_begin) : 0;
+
+  if (warp == 0 && elect_one()) {
+    tma_prefetch_desc(&tm_qkv);
+    tma_prefetch_desc(&tm_do);
+  }
+  if (warp == 1 && elect_one()) {
+    mbar_init(kv_full, 1);
+    mbar_init(qdo_full, 1);
+    mbar_init(qdo_empty, 1);
+    mbar_init(sdp_full, 1);
+    mbar_init(pds_full, 128);
+    mbar_init(dq_full, 1);
+    mbar_init(dq_read, 128);
+    fence_barrier_init();
+  }
+  if (warp == 2) tmem_alloc<512>(tmem_ptr_smem);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_ptr_smem;
+  const uint32_t t_s = tmem_base, t_dp = tmem_base + 128, t_dv = tmem_base + 256, t_dk = tmem_base + 384;
+
+  if (warp == 0) {
+    // ===================================================== TMA producer
+    if (elect_one() && n_steps > 0) {
+      mbar_expect_tx(kv_full, 2 * Cfg::kTileBytes);
+#pragma unroll
+      for (int a = 0; a < 2; ++a) {
+        tma_load_3d(&tm_qkv, kv_full, sk + a * kAtomBytes, p.k_col0 + head * HD + a * 64, kv0, batch, kEvictFirst);
+        tma_load_3d(&tm_qkv, kv_full, sv + a * kAtomBytes, p.v_col0 + head * HD + a * 64, kv0, batch, kEvictFirst);
+      }
+      for (int s = 0; s < n_steps; ++s) {
+        const int q0 = (i_begin + s) * kBwdBlock;
+        mbar_wait(qdo_empty, (s & 1) ^ 1);
+        mbar_expect_tx(qdo_full, 2 * Cfg::kTileBytes);
+#pragma unroll
+        for (int a = 0; a < 2; ++a) {
+          tma_load_3d(&tm_qkv, qdo_full, sq + a * kAtomBytes, p.q_col0 + head * HD + a * 64, q0, batch, kEvictLast);
+          tma_load_3d(&tm_do, qdo_full, sdo + a * kAtomBytes, head * HD + a * 64, q0, batch, kEvictLast);
+        }
+      }
+    }
+    __syncwarp();
+  } else if (warp == 1) {
+    // ======================================================= MMA issuer
+    if (elect_one() && n_steps > 0) {
+      constexpr uint32_t idesc_kk = umma_idesc_bf16(128, 128, 0, 0);   // S, dP : A, B K-major
+      constexpr uint32_t idesc_mm = umma_idesc_bf16(128, 128, 1, 1);   // dV, dK: A, B MN-major
+      constexpr uint32_t idesc_km = umma_idesc_bf16(128, 128, 0, 1);   // dQ    : A K-major, B MN-major
+      const uint32_t a_k = smem_u32(sk), a_v = smem_u32(sv), a_q = smem_u32(sq), a_do = smem_u32(sdo),
+                     a_p = smem_u32(sp), a_ds = smem_u32(sds);
+      mbar_wait(kv_full, 0);
+      for (int s = 0; s < n_steps; ++s) {
+        mbar_wait(qdo_full, s & 1);
+        mbar_wait(dq_read, (s & 1) ^ 1);   // dQ of the previous step has left the S region
+        tc_fence_after();
+#pragma unroll
+        for (int kk = 0; kk < HD / 16; ++kk) {
+          const uint32_t off = (kk >> 2) * kAtomBytes + (kk & 3) * 32;
+          umma_ss(t_s, umma_desc_k_sw128(a_q + off), umma_desc_k_sw128(a_k + off), idesc_kk, kk != 0);
+        }
+#pragma unroll
+        for (int kk = 0; kk < HD / 16; ++kk) {
+          const uint32_t off = (kk >> 2) * kAtomBytes + (kk & 3) * 32;
+          umma_ss(t_dp, umma_desc_k_sw128(a_do + off), umma_desc_k_sw128(a_v + off), idesc_kk, kk != 0);
+        }
+        umma_commit(sdp_full);
+
+        mbar_wait(pds_full, s & 1);
+        tc_fence_after();
+#pragma unroll
+        for (int kk = 0; kk < kBwdBlock / 16; ++kk) {
+          // reduction over 16 query rows per instruction: every operand advances 16 rows = 2 KB
+          const uint32_t roff = kk * 2048;
+          umma_ss(t_dv, umma_desc_mn_sw128(a_p + roff, kAtomBytes), umma_desc_mn_sw128(a_do + roff, kAtomBytes),
+                  idesc_mm, (s | kk) != 0);
+        }
+#pragma unroll
+        for (int kk = 0; kk < kBwdBlock / 16; ++kk) {
+          const uint32_t roff = kk * 2048;
+          umma_ss(t_dk, umma_desc_mn_sw128(a_ds + roff, kAtomBytes), umma_desc_mn_sw128(a_q + roff, kAtomBytes),
+                  idesc_mm, (s | kk) != 0);
+        }
+#pragma unroll
+        for (int kk = 0; kk < kBwdBlock / 16; ++kk) {
+          // dQ = dS K: reduction over 16 keys: A advances inside the key-major rows, B by 16 key rows
+          const uint32_t aoff = (kk >> 2) * kAtomBytes + (kk & 3) * 32;
+          umma_ss(t_s, umma_desc_k_sw128(a_ds + aoff), umma_desc_mn_sw128(a_k + kk * 2048, kAtomBytes), idesc_km,
+                  kk != 0);
+        }
+        umma_commit(qdo_empty);
+        umma_commit(dq_full);
+      }
+    }
+    __syncwarp();
+  } else if (warp >= 4) {
+    // ===================================================== P / dS / dQ threads
+    const int ewarp = warp - 4;
+    const int row = ewarp * 32 + static_cast<int>(lane_id());
+    const uint32_t lane_sel = static_cast<uint32_t>(ewarp * 32) << 16;
+    const float log2e = 1.4426950408889634f;
+    for (int s = 0; s < n_steps; ++s) {
+      const int i = i_begin + s;
+      const int q_idx = i * kBwdBlock + row;
+      const bool q_valid = q_idx < len;
+      const size_t stat = (static_cast<size_t>(batch) * p.H + head) * p.S + (q_valid ? q_idx : 0);
+      const float lse2 = q_valid ? p.lse[stat] * log2e : 0.f;
+      const float dlt = q_valid ? p.delta[stat] : 0.f;
+      mbar_wait(sdp_full, s & 1);
+      tc_fence_after();
+#pragma unroll
+      for (int ch = 0; ch < 4; ++ch) {
+        uint32_t sv_[32], dpv[32];
+        tmem_ld32(t_s + lane_sel + ch * 32, sv_);
+        tmem_ld32(t_dp + lane_sel + ch * 32, dpv);
+        tmem_ld_wait();
+        uint32_t pw[16], dw[16];
+#pragma unroll
+        for (int c = 0; c < 32; c += 2) {
+          float pv[2], dv[2];
+#pragma unroll
+          for (int e = 0; e < 2; ++e) {
+            const int kv = kv0 + ch * 32 + c + e;
+            const bool dead = !q_valid || kv >= len || (kCausal && kv > q_idx);
+            const float pe = dead ? 0.f : fast_exp2(fmaf(__uint_as_float(sv_[c + e]), p.scale_log2e, -lse2));
+            pv[e] = pe;
+            dv[e] = pe * (__uint_as_float(dpv[c + e]) - dlt) * p.scale;
+          }
+          pw[c >> 1] = pack_bf16(pv[0], pv[1]);
+          dw[c >> 1] = pack_bf16(dv[0], dv[1]);
+        }
+        // 32 keys = 64 bytes = four 16-byte chunks of this row inside atom (ch >> 1)
+#pragma unroll
+        for (int q4 = 0; q4 < 4; ++q4) {
+          const int chunk = (ch & 1) * 4 + q4;
+          const uint32_t off = (ch >> 1) * kAtomBytes + sw128_offset(row, chunk);
+          *reinterpret_cast<uint4*>(sp + off) = make_uint4(pw[q4 * 4], pw[q4 * 4 + 1], pw[q4 * 4 + 2], pw[q4 * 4 + 3]);
+          *reinterpret_cast<uint4*>(sds + off) = make_uint4(dw[q4 * 4], dw[q4 * 4 + 1], dw[q4 * 4 + 2], dw[q4 * 4 + 3]);
+        }
+      }
+      fence_proxy_async_smem();
+      tc_fence_before();
+      mbar_arrive(pds_full);
+
+      // dQ_i tile -> fp32 global reduction
+      mbar_wait(dq_full, s & 1);
+      tc_fence_after();
+      float* dq_row = p.dq_accum + (static_cast<size_t>(batch) * p.S + (q_idx < p.S ? q_idx : 0)) * (p.H * HD) + head * HD;
+#pragma unroll
+      for (int ch = 0; ch < 4; ++ch) {
+        uint32_t v[32];
+        tmem_ld32(t_s + lane_sel + ch * 32, v);
+        tmem_ld_wait();
+        if (q_valid) {
+#pragma unroll
+          for (int e = 0; e < 32; ++e) red_add_f32(dq_row + ch * 32 + e, __uint_as_float(v[e]));
+        }
+      }
+      tc_fence_before();
+      mbar_arrive(dq_read);
+    }
+
+    // ---- dK, dV of this key tile (thread = key row)
+    const int kv_idx = kv0 + row;
+    if (kv_idx < p.S) {
+      __nv_bfloat16* out_row = p.dqkv + (static_cast<size_t>(batch) * p.S + kv_idx) * p.ld_dqkv;
+      const bool live = n_steps > 0 && kv_idx < len;
+#pragma unroll
+      for (int which = 0; which < 2; ++which) {
+        const uint32_t t_acc = which == 0 ? t_dk : t_dv;
+        __nv_bfloat16* dst = out_row + (which == 0 ? p.k_col0 : p.v_col0) + head * HD;
+#pragma unroll
+        for (int ch = 0; ch < 4; ++ch) {
+          uint32_t v[32];
+          if (n_steps > 0) {
+            tmem_ld32(t_acc + lane_sel + ch * 32, v);
+            tmem_ld_wait();
+          }
+#pragma unroll
+          for (int q4 = 0; q4 < 4; ++q4) {
+            uint4 w = make_uint4(0, 0, 0, 0);
+            if (live) {
+              w.x = pack_bf16(__uint_as_float(v[q4 * 8 + 0]), __uint_as_float(v[q4 * 8 + 1]));
+              w.y = pack_bf16(__uint_as_float(v[q4 * 8 + 2]), __uint_as_float(v[q4 * 8 + 3]));
+              w.z = pack_bf16(__uint_as_float(v[q4 * 8 + 4]), __uint_as_float(v[q4 * 8 + 5]));
+              w.w = pack_bf16(__uint_as_float(v[q4 * 8 + 6]), __uint_as_float(v[q4 * 8 + 7]));
+            }
+            *reinterpret_cast<uint4*>(dst + ch * 32 + q4 * 8) = w;
+          }
+        }
+      }
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 2) tmem_dealloc<512>(tmem_base);
+}
+
+// dq (fp32 accumulator, [M, H*128]) -> bf16 q block of the packed gradient rows
+__global__ void dq_to_bf16_kernel(const float* __restrict__ acc, __nv_bfloat16* __restrict__ dqkv, int64_t ld,
+                                  int q_col0, int width, int64_t rows) {
+  const int vec_per_row = width >> 3;
+  for (int64_t i = blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x; i < rows * vec_per_row;
+       i += static_cast<int64_t>(gridDim.x) * blockDim.x) {
+    const int64_t r = i / vec_per_row;
+    const int c = static_cast<int>(i % vec_per_row) * 8;
+    const float4 a = *reinterpret_cast<const float4*>(acc + r * width + c);
+    const float4 b = *reinterpret_cast<const float4*>(acc + r * width + c + 4);
+    *reinterpret_cast<uint4*>(dqkv + r * ld + q_col0 + c) =
+        make_uint4(pack_bf16(a.x, a.y), pack_bf16(a.z, a.w), pack_bf16(b.x, b.y), pack_bf16(b.z, b.w));
+  }
+}
+
+}  // namespace mb

@@ -1,0 +1,458 @@
+// merlin_b200 — HBM-bound backward / optimizer kernels of the training path:
+// RMSNorm backward (+ residual-gradient add), SwiGLU forward-with-save / backward, inverse RoPE,
+// cross-entropy backward (in place over the logits), embedding / splice backward, column sums for bias
+// gradients, attention delta = rowsum(dO ∘ O), gradient-norm partials and a fused AdamW over a flat
+// parameter arena with per-chunk learning-rate / weight-decay tables (LLRD param groups).
+#include "host.cuh"
+#include "ptx.cuh"
+
+namespace mb {
+
+__device__ __forceinline__ float warp_sum_b(float v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+__device__ __forceinline__ float block_sum_b(float v, float* red) {
+  v = warp_sum_b(v);
+  const int w = threadIdx.x >> 5, nw = (blockDim.x + 31) >> 5;
+  __syncthreads();
+  if ((threadIdx.x & 31) == 0) red[w] = v;
+  __syncthreads();
+  float t = (threadIdx.x < nw) ? red[threadIdx.x] : 0.f;
+  if (w == 0) {
+    t = warp_sum_b(t);
+    if (threadIdx.x == 0) red[0] = t;
+  }
+  __syncthreads();
+  return red[0];
+}
+__device__ __forceinline__ void unpack8b(const uint4& q, float (&f)[8]) {
+  f[0] = bf16_lo(q.x); f[1] = bf16_hi(q.x); f[2] = bf16_lo(q.y); f[3] = bf16_hi(q.y);
+  f[4] = bf16_lo(q.z); f[5] = bf16_hi(q.z); f[6] = bf16_lo(q.w); f[7] = bf16_hi(q.w);
+}
+__device__ __forceinline__ uint4 pack8b(const float (&f)[8]) {
+  return make_uint4(pack_bf16(f[0], f[1]), pack_bf16(f[2], f[3]), pack_bf16(f[4], f[5]),
+                    pack_bf16(f[6], f[7]));
+}
+
+// ------------------------------------------------------------------ RMSNorm backward
+// y = w ⊙ x̂, x̂ = x·r, r = rsqrt(mean(x²)+eps).  g = w ⊙ dy;  dx = r·(g − x̂·mean(g ⊙ x̂)) (+ dres);
+// dw[j] += Σ_rows dy[row,j]·x̂[row,j]   (fp32 atomics, one per column per block of kRows rows).
+constexpr int kRnbThreads = 256;
+constexpr int kRnbVec = 4;    // D <= 8192
+constexpr int kRnbRows = 16;  // rows per block (amortises the dw atomics)
+
+__global__ void __launch_bounds__(kRnbThreads)
+rmsnorm_bwd_kernel(const __nv_bfloat16* __restrict__ x, const __nv_bfloat16* __restrict__ w,
+                   const __nv_bfloat16* __restrict__ dy, const __nv_bfloat16* __restrict__ dres,
+                   __nv_bfloat16* __restrict__ dx, float* __restrict__ dw, int M, int D, float eps) {
+  __shared__ float red[32];
+  const int nvec = D >> 3;
+  float wv[kRnbVec][8], dwacc[kRnbVec][8];
+#pragma unroll
+  for (int i = 0; i < kRnbVec; ++i) {
+    const int idx = threadIdx.x + i * kRnbThreads;
+    if (idx < nvec) unpack8b(reinterpret_cast<const uint4*>(w)[idx], wv[i]);
+#pragma unroll
+    for (int e = 0; e < 8; ++e) dwacc[i][e] = 0.f;
+  }
+  const int row0 = blockIdx.x * kRnbRows;
+  for (int r = 0; r < kRnbRows && row0 + r < M; ++r) {
+    const size_t off = static_cast<size_t>(row0 + r) * D;
+    float xv[kRnbVec][8], gv[kRnbVec][8];
+    float ss = 0.f;
+#pragma unroll
+    for (int i = 0; i < kRnbVec; ++i) {
+      const int idx = threadIdx.x + i * kRnbThreads;
+      if (idx < nvec) {
+        unpack8b(reinterpret_cast<const uint4*>(x + off)[idx], xv[i]);
+        unpack8b(reinterpret_cast<const uint4*>(dy + off)[idx], gv[i]);
+#pragma unroll
+        for (int e = 0; e < 8; ++e) ss += xv[i][e] * xv[i][e];
+      }
+    }
+    const float rstd = rsqrtf(block_sum_b(ss, red) / static_cast<float>(D) + eps);
+    float dot = 0.f;
+#pragma unroll
+    for (int i = 0; i < kRnbVec; ++i) {
+      const int idx = threadIdx.x + i * kRnbThreads;
+      if (idx < nvec) {
+#pragma unroll
+        for (int e = 0; e < 8; ++e) {
+          const float xh = xv[i][e] * rstd;
+          dwacc[i][e] += gv[i][e] * xh;        // dy·x̂
+          gv[i][e] *= wv[i][e];                // g = w ⊙ dy
+          dot += gv[i][e] * xh;
+          xv[i][e] = xh;
+        }
+      }
+    }
+    const float mean_gx = block_sum_b(dot, red) / static_cast<float>(D);
+#pragma unroll
+    for (int i = 0; i < kRnbVec; ++i) {
+      const int idx = threadIdx.x + i * kRnbThreads;
+      if (idx < nvec) {
+        float o[8];
+        if (dres) unpack8b(reinterpret_cast<const uint4*>(dres + off)[idx], o);
+#pragma unroll
+        for (int e = 0; e < 8; ++e) {
+          const float v = rstd * (gv[i][e] - xv[i][e] * mean_gx);
+          o[e] = dres ? o[e] + v : v;
+        }
+        reinterpret_cast<uint4*>(dx + off)[idx] = pack8b(o);
+      }
+    }
+  }
+  if (dw) {
+#pragma unroll
+    for (int i = 0; i < kRnbVec; ++i) {
+      const int idx = threadIdx.x + i * kRnbThreads;
+      if (idx < nvec)
+#pragma unroll
+        for (int e = 0; e < 8; ++e) atomicAdd(&dw[idx * 8 + e], dwacc[i][e]);
+    }
+  }
+}
+
+// ------------------------------------------------------------------ SwiGLU (training form)
+// gu [M, 2FF]: per 256 columns, 128 gate then 128 up (the packed gate/up weight layout).
+__global__ void swiglu_fwd_kernel(const __nv_bfloat16* __restrict__ gu, __nv_bfloat16* __restrict__ mid,
+                                  int64_t total_vec /* M*FF/8 */, int FF) {
+  const int vec_per_row = FF >> 3;
+  for (int64_t i = blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x; i < total_vec;
+       i += static_cast<int64_t>(gridDim.x) * blockDim.x) {
+    const int64_t row = i / vec_per_row;
+    const int c = static_cast<int>(i % vec_per_row) * 8;     // output column
+    const int blk = c >> 7, j = c & 127;
+    const __nv_bfloat16* base = gu + row * 2 * FF + blk * 256 + j;
+    float g[8], u[8], o[8];
+    unpack8b(*reinterpret_cast<const uint4*>(base), g);
+    unpack8b(*reinterpret_cast<const uint4*>(base + 128), u);
+#pragma unroll
+    for (int e = 0; e < 8; ++e) o[e] = g[e] / (1.f + __expf(-g[e])) * u[e];
+    *reinterpret_cast<uint4*>(mid + row * FF + c) = pack8b(o);
+  }
+}
+// dgu (same interleaved layout, may alias gu): dg = dmid·u·σ(g)(1 + g(1−σ(g))), du = dmid·g·σ(g)
+__global__ void swiglu_bwd_kernel(const __nv_bfloat16* __restrict__ gu, const __nv_bfloat16* __restrict__ dmid,
+                                  __nv_bfloat16* __restrict__ dgu, int64_t total_vec, int FF) {
+  const int vec_per_row = FF >> 3;
+  for (int64_t i = blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x; i < total_vec;
+       i += static_cast<int64_t>(gridDim.x) * blockDim.x) {
+    const int64_t row = i / vec_per_row;
+    const int c = static_cast<int>(i % vec_per_row) * 8;
+    const int blk = c >> 7, j = c & 127;
+    const int64_t off = row * 2 * FF + blk * 256 + j;
+    float g[8], u[8], d[8], dg[8], du[8];
+    unpack8b(*reinterpret_cast<const uint4*>(gu + off), g);
+    unpack8b(*reinterpret_cast<const uint4*>(gu + off + 128), u);
+    unpack8b(*reinterpret_cast<const uint4*>(dmid + row * FF + c), d);
+#pragma unroll
+    for (int e = 0; e < 8; ++e) {
+      const float s = 1.f / (1.f + __expf(-g[e]));
+      dg[e] = d[e] * u[e] * s * (1.f + g[e] * (1.f - s));
+      du[e] = d[e] * g[e] * s;
+    }
+    *reinterpret_cast<uint4*>(dgu + off) = pack8b(dg);
+    *reinterpret_cast<uint4*>(dgu + off + 128) = pack8b(du);
+  }
+}
+
+// ------------------------------------------------------------------ cross-entropy backward
+// logits row (b,t) -> dlogits = (softmax − onehot(label[b,t+1])) · grad_scale / count, or 0 when the
+// row is not scored.  In place (dlogits may alias logits).  count = loss_sum_count[1] of the forward.
+__global__ void __launch_bounds__(1024)
+cross_entropy_bwd_kernel(const __nv_bfloat16* __restrict__ logits, int64_t ld, const int64_t* __restrict__ labels,
+                         int S, int V, int64_t ignore_index, const float* __restrict__ sum_count,
+                         float grad_scale, __nv_bfloat16* __restrict__ dlogits, int64_t ldd) {
+  __shared__ float red[32];
+  const int row = blockIdx.x;
+  const int t = row % S;
+  int64_t label = ignore_index;
+  if (t + 1 < S) label = labels[row + 1];
+  const __nv_bfloat16* lr = logits + static_cast<size_t>(row) * ld;
+  __nv_bfloat16* dr = dlogits + static_cast<size_t>(row) * ldd;
+  if (label == ignore_index || label < 0 || label >= V) {
+    for (int i = threadIdx.x; i < V; i += blockDim.x) dr[i] = __float2bfloat16(0.f);
+    return;
+  }
+  float mx = -INFINITY;
+  for (int i = threadIdx.x; i < V; i += blockDim.x) mx = fmaxf(mx, __bfloat162float(lr[i]));
+  // block max via the sum helper's scratch
+  mx = warp_sum_b(0.f) * 0.f + mx;
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, o));
+  __syncthreads();
+  if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = mx;
+  __syncthreads();
+  float m2 = (threadIdx.x < (blockDim.x >> 5)) ? red[threadIdx.x] : -INFINITY;
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) m2 = fmaxf(m2, __shfl_xor_sync(0xffffffffu, m2, o));
+  __syncthreads();
+  if (threadIdx.x == 0) red[0] = m2;
+  __syncthreads();
+  mx = red[0];
+  float se = 0.f;
+  for (int i = threadIdx.x; i < V; i += blockDim.x) se += __expf(__bfloat162float(lr[i]) - mx);
+  se = block_sum_b(se, red);
+  const float scale = grad_scale / sum_count[1];
+  const float inv = 1.f / se;
+  for (int i = threadIdx.x; i < V; i += blockDim.x) {
+    float p = __expf(__bfloat162float(lr[i]) - mx) * inv;
+    if (i == label) p -= 1.f;
+    dr[i] = __float2bfloat16_rn(p * scale);
+  }
+}
+
+// ------------------------------------------------------------------ embedding / splice backward
+// dx [T, D]: rows of <im_patch> tokens go to dfeats[rank] (unique destination), the others are
+// accumulated into dtable[ids[t]] (bf16x2 atomics; duplicates are rare).
+__global__ void embed_splice_bwd_kernel(const int64_t* __restrict__ ids, const int* __restrict__ rank,
+                                        const __nv_bfloat16* __restrict__ dx, __nv_bfloat16* __restrict__ dtable,
+                                        __nv_bfloat16* __restrict__ dfeats, int D, int n_feat_rows, int64_t vocab) {
+  const int t = blockIdx.x;
+  const int r = rank ? rank[t] : -1;
+  const __nv_bfloat16* src = dx + static_cast<size_t>(t) * D;
+  if (r >= 0 && r < n_feat_rows) {
+    if (dfeats == nullptr) return;
+    uint4* dst = reinterpret_cast<uint4*>(dfeats + static_cast<size_t>(r) * D);
+    for (int i = threadIdx.x; i < (D >> 3); i += blockDim.x) dst[i] = reinterpret_cast<const uint4*>(src)[i];
+    return;
+  }
+  if (dtable == nullptr) return;
+  int64_t id = ids[t];
+  if (id < 0 || id >= vocab) return;
+  __nv_bfloat162* dst = reinterpret_cast<__nv_bfloat162*>(dtable + static_cast<size_t>(id) * D);
+  const __nv_bfloat162* s2 = reinterpret_cast<const __nv_bfloat162*>(src);
+  for (int i = threadIdx.x; i < (D >> 1); i += blockDim.x) atomicAdd(&dst[i], s2[i]);
+}
+
+// out[j] += Σ_rows x[row, j]   (bias gradients); fp32 accumulation buffer
+__global__ void colsum_kernel(const __nv_bfloat16* __restrict__ x, int64_t ld, float* __restrict__ out, int M,
+                              int N, int rows_per_block) {
+  const int col = blockIdx.x * blockDim.x + threadIdx.x;
+  if (col >= N) return;
+  const int r0 = blockIdx.y * rows_per_block;
+  float acc = 0.f;
+  for (int r = r0; r < min(M, r0 + rows_per_block); ++r) acc += __bfloat162float(x[static_cast<size_t>(r) * ld + col]);
+  atomicAdd(&out[col], acc);
+}
+
+// delta[b,h,s] = Σ_d dO[b,s,h,d]·O[b,s,h,d]     (flash-attention backward pre-pass)
+__global__ void attn_delta_kernel(const __nv_bfloat16* __restrict__ o, const __nv_bfloat16* __restrict__ d_o,
+                                  float* __restrict__ delta, int S, int H, int hd, int64_t ld) {
+  // one warp per (row, head)
+  const int gw = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const int lane = threadIdx.x & 31;
+  const int row = gw / H, h = gw % H;  // row = b*S + s
+  const int64_t off = static_cast<int64_t>(row) * ld + h * hd;
+  float acc = 0.f;
+  for (int d = lane * 2; d < hd; d += 64) {
+    const __nv_bfloat162 a = *reinterpret_cast<const __nv_bfloat162*>(o + off + d);
+    const __nv_bfloat162 b = *reinterpret_cast<const __nv_bfloat162*>(d_o + off + d);
+    acc += __low2float(a) * __low2float(b) + __high2float(a) * __high2float(b);
+  }
+  acc = warp_sum_b(acc);
+  if (lane == 0) {
+    const int b = row / S, s = row % S;
+    delta[(static_cast<size_t>(b) * H + h) * S + s] = acc;
+  }
+}
+
+// ------------------------------------------------------------------ optimizer
+// Σ g² over the flat gradient arena (fp32 atomics into out[0]).
+__global__ void sumsq_kernel(const __nv_bfloat16* __restrict__ g, int64_t n_vec, float* __restrict__ out) {
+  __shared__ float red[32];
+  float acc = 0.f;
+  for (int64_t i = blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x; i < n_vec;
+       i += static_cast<int64_t>(gridDim.x) * blockDim.x) {
+    float f[8];
+    unpack8b(reinterpret_cast<const uint4*>(g)[i], f);
+#pragma unroll
+    for (int e = 0; e < 8; ++e) acc += f[e] * f[e];
+  }
+  acc = block_sum_b(acc, red);
+  if (threadIdx.x == 0) atomicAdd(out, acc);
+}
+
+// Fused AdamW over a flat arena: p, g, m, v are bf16 (the reference keeps bf16 weights AND optimizer
+// state, mmgpt/model/builder.py:110-114,163); math in fp32.  chunk c = elements [c*chunk, (c+1)*chunk)
+// carries its own lr multiplier and weight decay (LLRD groups, llrd_utils.py:25-79).
+// torch.optim.AdamW semantics: p *= 1 − lr·wd; m = β1 m + (1−β1) g; v = β2 v + (1−β2) g²;
+// p −= lr/bc1 · m / (sqrt(v)/sqrt(bc2) + eps).  g is first scaled by grad_scale·clip where
+// clip = min(1, max_norm / (sqrt(sumsq[0])·grad_scale + 1e-6)) (torch clip_grad_norm_).
+__global__ void adamw_kernel(__nv_bfloat16* __restrict__ p, const __nv_bfloat16* __restrict__ g,
+                             __nv_bfloat16* __restrict__ m, __nv_bfloat16* __restrict__ v,
+                             const float* __restrict__ lr_mult, const float* __restrict__ wd, int chunk_vec,
+                             int64_t n_vec, float lr, float beta1, float beta2, float eps, float bc1, float bc2,
+                             float grad_scale, float max_norm, const float* __restrict__ sumsq) {
+  float clip = grad_scale;
+  if (max_norm > 0.f && sumsq != nullptr) {
+    const float norm = sqrtf(sumsq[0]) * grad_scale;
+    clip = grad_scale * fminf(1.f, max_norm / (norm + 1e-6f));
+  }
+  const float inv_sqrt_bc2 = rsqrtf(bc2);
+  for (int64_t i = blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x; i < n_vec;
+       i += static_cast<int64_t>(gridDim.x) * blockDim.x) {
+    const int64_t c = i / chunk_vec;
+    const float lr_c = lr * lr_mult[c];
+    if (lr_c == 0.f) continue;  // frozen segment
+    const float wd_c = wd[c];
+    float pf[8], gf[8], mf[8], vf[8];
+    unpack8b(reinterpret_cast<const uint4*>(p)[i], pf);
+    unpack8b(reinterpret_cast<const uint4*>(g)[i], gf);
+    unpack8b(reinterpret_cast<const uint4*>(m)[i], mf);
+    unpack8b(reinterpret_cast<const uint4*>(v)[i], vf);
+#pragma unroll
+    for (int e = 0; e < 8; ++e) {
+      const float gg = gf[e] * clip;
+      mf[e] = beta1 * mf[e] + (1.f - beta1) * gg;
+      vf[e] = beta2 * vf[e] + (1.f - beta2) * gg * gg;
+      const float denom = sqrtf(vf[e]) * inv_sqrt_bc2 + eps;
+      pf[e] = pf[e] * (1.f - lr_c * wd_c) - (lr_c / bc1) * (mf[e] / denom);
+    }
+    reinterpret_cast<uint4*>(p)[i] = pack8b(pf);
+    reinterpret_cast<uint4*>(m)[i] = pack8b(mf);
+    reinterpret_cast<uint4*>(v)[i] = pack8b(vf);
+  }
+}
+
+// y = bf16(x_fp32)  (fp32 gradient accumulators -> bf16 gradient arena)
+__global__ void f32_to_bf16_kernel(const float* __restrict__ x, __nv_bfloat16* __restrict__ y, int64_t n) {
+  for (int64_t i = blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x; i < n;
+       i += static_cast<int64_t>(gridDim.x) * blockDim.x)
+    y[i] = __float2bfloat16_rn(x[i]);
+}
+
+static int grid_for(int64_t work_items, int threads) {
+  int64_t blocks = (work_items + threads - 1) / threads;
+  const int64_t cap = static_cast<int64_t>(sm_count()) * 16;
+  return static_cast<int>(blocks < 1 ? 1 : (blocks > cap ? cap : blocks));
+}
+
+}  // namespace mb
+
+using namespace mb;
+
+extern "C" {
+
+int merlin_rmsnorm_bwd(void* stream, const void* x, const void* weight, const void* dy, const void* dres,
+                       void* dx, float* dweight, int M, int D, float eps) {
+  MB_CHECK_ARG(x && weight && dy && dx, "rmsnorm_bwd: null tensor");
+  MB_CHECK_ARG(D % 8 == 0 && D <= 8 * kRnbThreads * kRnbVec, "rmsnorm_bwd: D=%d unsupported", D);
+  if (M == 0) return MERLIN_OK;
+  rmsnorm_bwd_kernel<<<(M + kRnbRows - 1) / kRnbRows, kRnbThreads, 0, static_cast<cudaStream_t>(stream)>>>(
+      static_cast<const __nv_bfloat16*>(x), static_cast<const __nv_bfloat16*>(weight),
+      static_cast<const __nv_bfloat16*>(dy), static_cast<const __nv_bfloat16*>(dres),
+      static_cast<__nv_bfloat16*>(dx), dweight, M, D, eps);
+  MB_CHECK_CUDA(cudaGetLastError());
+  return MERLIN_OK;
+}
+
+int merlin_swiglu_fwd(void* stream, const void* gate_up, void* mid, int M, int FF) {
+  MB_CHECK_ARG(gate_up && mid && FF % 128 == 0, "swiglu_fwd: bad argument");
+  const int64_t nvec = static_cast<int64_t>(M) * FF / 8;
+  if (nvec == 0) return MERLIN_OK;
+  swiglu_fwd_kernel<<<grid_for(nvec, 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(
+      static_cast<const __nv_bfloat16*>(gate_up), static_cast<__nv_bfloat16*>(mid), nvec, FF);
+  MB_CHECK_CUDA(cudaGetLastError());
+  return MERLIN_OK;
+}
+
+int merlin_swiglu_bwd(void* stream, const void* gate_up, const void* dmid, void* dgate_up, int M, int FF) {
+  MB_CHECK_ARG(gate_up && dmid && dgate_up && FF % 128 == 0, "swiglu_bwd: bad argument");
+  const int64_t nvec = static_cast<int64_t>(M) * FF / 8;
+  if (nvec == 0) return MERLIN_OK;
+  swiglu_bwd_kernel<<<grid_for(nvec, 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(
+      static_cast<const __nv_bfloat16*>(gate_up), static_cast<const __nv_bfloat16*>(dmid),
+      static_cast<__nv_bfloat16*>(dgate_up), nvec, FF);
+  MB_CHECK_CUDA(cudaGetLastError());
+  return MERLIN_OK;
+}
+
+int merlin_cross_entropy_bwd(void* stream, const void* logits, int64_t ld, const int64_t* labels, int B, int S,
+                             int V, int64_t ignore_index, const float* loss_sum_count, float grad_scale,
+                             void* dlogits, int64_t ldd) {
+  MB_CHECK_ARG(logits && labels && loss_sum_count && dlogits, "cross_entropy_bwd: null tensor");
+  cross_entropy_bwd_kernel<<<B * S, 1024, 0, static_cast<cudaStream_t>(stream)>>>(
+      static_cast<const __nv_bfloat16*>(logits), ld, labels, S, V, ignore_index, loss_sum_count, grad_scale,
+      static_cast<__nv_bfloat16*>(dlogits), ldd);
+  MB_CHECK_CUDA(cudaGetLastError());
+  return MERLIN_OK;
+}
+
+int merlin_embed_splice_bwd(void* stream, const int64_t* input_ids, const int* rank, const void* dx,
+                            void* dembed_table, void* dimage_features, int T, int D, int n_feature_rows,
+                            int64_t vocab) {
+  MB_CHECK_ARG(input_ids && dx && D % 8 == 0, "embed_splice_bwd: bad argument");
+  if (T == 0) return MERLIN_OK;
+  embed_splice_bwd_kernel<<<T, 256, 0, static_cast<cudaStream_t>(stream)>>>(
+      input_ids, rank, static_cast<const __nv_bfloat16*>(dx), static_cast<__nv_bfloat16*>(dembed_table),
+      static_cast<__nv_bfloat16*>(dimage_features), D, n_feature_rows, vocab);
+  MB_CHECK_CUDA(cudaGetLastError());
+  return MERLIN_OK;
+}
+
+int merlin_colsum(void* stream, const void* x, int64_t ld, float* out, int M, int N) {
+  MB_CHECK_ARG(x && out, "colsum: null tensor");
+  if (M == 0 || N == 0) return MERLIN_OK;
+  const int rows_per_block = 64;
+  dim3 grid((N + 255) / 256, (M + rows_per_block - 1) / rows_per_block);
+  colsum_kernel<<<grid, 256, 0, static_cast<cudaStream_t>(stream)>>>(static_cast<const __nv_bfloat16*>(x), ld,
+                                                                     out, M, N, rows_per_block);
+  MB_CHECK_CUDA(cudaGetLastError());
+  return MERLIN_OK;
+}
+
+int merlin_attn_delta(void* stream, const void* out, const void* dout, float* delta, int B, int S, int H,
+                      int head_dim, int64_t ld) {
+  MB_CHECK_ARG(out && dout && delta, "attn_delta: null tensor");
+  const int64_t warps = static_cast<int64_t>(B) * S * H;
+  if (warps == 0) return MERLIN_OK;
+  const int threads = 256;
+  attn_delta_kernel<<<static_cast<unsigned>((warps * 32 + threads - 1) / threads), threads, 0,
+                      static_cast<cudaStream_t>(stream)>>>(static_cast<const __nv_bfloat16*>(out),
+                                                           static_cast<const __nv_bfloat16*>(dout), delta, S, H,
+                                                           head_dim, ld);
+  MB_CHECK_CUDA(cudaGetLastError());
+  return MERLIN_OK;
+}
+
+int merlin_grad_sumsq(void* stream, const void* grads, int64_t n, float* out) {
+  MB_CHECK_ARG(grads && out && n % 8 == 0, "grad_sumsq: bad argument");
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  MB_CHECK_CUDA(cudaMemsetAsync(out, 0, sizeof(float), st));
+  if (n == 0) return MERLIN_OK;
+  sumsq_kernel<<<grid_for(n / 8, 256), 256, 0, st>>>(static_cast<const __nv_bfloat16*>(grads), n / 8, out);
+  MB_CHECK_CUDA(cudaGetLastError());
+  return MERLIN_OK;
+}
+
+int merlin_adamw_step(void* stream, void* params, const void* grads, void* exp_avg, void* exp_avg_sq,
+                      const float* lr_mult, const float* weight_decay, int chunk, int64_t n, float lr, float beta1,
+                      float beta2, float eps, int step, float grad_scale, float max_grad_norm,
+                      const float* grad_sumsq) {
+  MB_CHECK_ARG(params && grads && exp_avg && exp_avg_sq && lr_mult && weight_decay, "adamw: null tensor");
+  MB_CHECK_ARG(chunk % 8 == 0 && chunk > 0 && n % 8 == 0 && step >= 1, "adamw: bad chunking");
+  if (n == 0) return MERLIN_OK;
+  const float bc1 = 1.f - powf(beta1, static_cast<float>(step));
+  const float bc2 = 1.f - powf(beta2, static_cast<float>(step));
+  adamw_kernel<<<grid_for(n / 8, 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(
+      static_cast<__nv_bfloat16*>(params), static_cast<const __nv_bfloat16*>(grads),
+      static_cast<__nv_bfloat16*>(exp_avg), static_cast<__nv_bfloat16*>(exp_avg_sq), lr_mult, weight_decay,
+      chunk / 8, n / 8, lr, beta1, beta2, eps, bc1, bc2, grad_scale, max_grad_norm, grad_sumsq);
+  MB_CHECK_CUDA(cudaGetLastError());
+  return MERLIN_OK;
+}
+
+int merlin_f32_to_bf16(void* stream, const float* x, void* y, int64_t n) {
+  MB_CHECK_ARG(x && y, "f32_to_bf16: null tensor");
+  if (n == 0) return MERLIN_OK;
+  f32_to_bf16_kernel<<<grid_for(n, 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(
+      x, static_cast<__nv_bfloat16*>(y), n);
+  MB_CHECK_CUDA(cudaGetLastError());
+  return MERLIN_OK;
+}
+
+}  // extern "C"

@@ -430,8 +430,8 @@ int merlin_decode_step(void* stream, const merlin_decoder_weights* w, void* x, c
   }
   const int D = w->hidden, FF = w->intermediate, H = w->heads;
   // warps per row pair: more CTAs in flight for the small-N projections (tunable for experiments)
-  static const int ks_qkv = env_int("MERLIN_KS_QKV", 1), ks_o = env_int("MERLIN_KS_O", 2),
-                   ks_gu = env_int("MERLIN_KS_GU", 1), ks_down = env_int("MERLIN_KS_DOWN", 4);
+  static const int ks_qkv = env_int("MERLIN_KS_QKV", 1), ks_o = env_int("MERLIN_KS_O", 1),
+                   ks_gu = env_int("MERLIN_KS_GU", 1), ks_down = env_int("MERLIN_KS_DOWN", 1);
   uint8_t* ws = static_cast<uint8_t*>(workspace);
   __nv_bfloat16* qbuf = reinterpret_cast<__nv_bfloat16*>(ws);
   __nv_bfloat16* att = qbuf + D;

@@ -312,7 +312,7 @@ __global__ void embed_splice_kernel(const int64_t* __restrict__ ids, const int* 
 // Half-split rotary embedding in place on the q and k blocks of packed qkv rows (head_dim 128).
 __global__ void rope_qk_kernel(__nv_bfloat16* __restrict__ qkv, int64_t ld, const float* __restrict__ cosT,
                                const float* __restrict__ sinT, const int* __restrict__ positions,
-                               int H, int seq_len) {
+                               int H, int seq_len, float sin_sign) {
   const int row = blockIdx.x;
   const int pos = positions ? positions[row] : row % seq_len;
   const float* cp = cosT + static_cast<size_t>(pos) * 64;
@@ -323,7 +323,7 @@ __global__ void rope_qk_kernel(__nv_bfloat16* __restrict__ qkv, int64_t ld, cons
     const int head = i >> 6, j = i & 63;
     __nv_bfloat16* h = base + head * 128;
     const float a = __bfloat162float(h[j]), b = __bfloat162float(h[j + 64]);
-    const float c = cp[j], s = sp[j];
+    const float c = cp[j], s = sp[j] * sin_sign;
     h[j] = __float2bfloat16_rn(a * c - b * s);
     h[j + 64] = __float2bfloat16_rn(b * c + a * s);
   }
@@ -497,14 +497,20 @@ int merlin_embed_splice(void* stream, const int64_t* input_ids, const void* embe
   return MERLIN_OK;
 }
 
-int merlin_rope_qk_inplace(void* stream, void* qkv, int64_t ld, const float* rope_cos,
-                           const float* rope_sin, const int* positions, int M, int H, int seq_len) {
+int merlin_rope_qk_inplace_ex(void* stream, void* qkv, int64_t ld, const float* rope_cos,
+                              const float* rope_sin, const int* positions, int M, int H, int seq_len,
+                              int inverse) {
   MB_CHECK_ARG(qkv && rope_cos && rope_sin && M >= 0 && H > 0 && seq_len > 0, "rope: bad argument");
   if (M == 0) return MERLIN_OK;
   rope_qk_kernel<<<M, 256, 0, static_cast<cudaStream_t>(stream)>>>(
-      static_cast<__nv_bfloat16*>(qkv), ld, rope_cos, rope_sin, positions, H, seq_len);
+      static_cast<__nv_bfloat16*>(qkv), ld, rope_cos, rope_sin, positions, H, seq_len, inverse ? -1.f : 1.f);
   MB_CHECK_CUDA(cudaGetLastError());
   return MERLIN_OK;
+}
+
+int merlin_rope_qk_inplace(void* stream, void* qkv, int64_t ld, const float* rope_cos,
+                           const float* rope_sin, const int* positions, int M, int H, int seq_len) {
+  return merlin_rope_qk_inplace_ex(stream, qkv, ld, rope_cos, rope_sin, positions, M, H, seq_len, 0);
 }
 
 int merlin_cross_entropy_fwd(void* stream, const void* logits, int64_t ld, const int64_t* labels,

@@ -84,13 +84,13 @@ int sm_count() {
   return n;
 }
 
-template <int kCtaGroup>
+template <int kCtaGroup, bool kAMN, bool kBMN>
 static int launch_gemm(cudaStream_t stream, const CUtensorMap& ta, const CUtensorMap& tb,
                        const CUtensorMap& tc, const CUtensorMap& tr, const GemmParams& p) {
   using Cfg = GemmCfg<kCtaGroup>;
   static bool configured = false;
   if (!configured) {
-    MB_CHECK_CUDA(cudaFuncSetAttribute(gemm_bf16_kernel<kCtaGroup>,
+    MB_CHECK_CUDA(cudaFuncSetAttribute(gemm_bf16_kernel<kCtaGroup, kAMN, kBMN>,
                                        cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::kSmemBytes));
     configured = true;
   }
@@ -110,12 +110,13 @@ static int launch_gemm(cudaStream_t stream, const CUtensorMap& ta, const CUtenso
   attr[0].val.clusterDim.z = 1;
   cfg.attrs = attr;
   cfg.numAttrs = 1;
-  MB_CHECK_CUDA(cudaLaunchKernelEx(&cfg, gemm_bf16_kernel<kCtaGroup>, ta, tb, tc, tr, p));
+  MB_CHECK_CUDA(cudaLaunchKernelEx(&cfg, gemm_bf16_kernel<kCtaGroup, kAMN, kBMN>, ta, tb, tc, tr, p));
   return MERLIN_OK;
 }
 
 int gemm_dispatch(cudaStream_t stream, const void* A, int64_t lda, const void* B, int64_t ldb, void* C,
-                  int64_t ldc, const void* R, int64_t ldr, const GemmParams& p, int cta_group) {
+                  int64_t ldc, const void* R, int64_t ldr, const GemmParams& p, int cta_group,
+                  bool a_mn = false, bool b_mn = false) {
   MB_CHECK_ARG(p.M > 0 && p.N > 0 && p.K > 0, "gemm: empty problem M=%d N=%d K=%d", p.M, p.N, p.K);
   MB_CHECK_ARG(cta_group == 1 || cta_group == 2, "gemm: cta_group must be 1 or 2, got %d", cta_group);
   MB_CHECK_ARG(A && B && C, "gemm: null operand");
@@ -130,15 +131,16 @@ int gemm_dispatch(cudaStream_t stream, const void* A, int64_t lda, const void* B
   CUtensorMap ta, tb, tc, tr;
   int rc;
   {
-    uint64_t dims[2] = {static_cast<uint64_t>(p.K), static_cast<uint64_t>(p.M)};
+    // K-major: rows of A are M, inner dim K.  MN-major: stored [K, M], inner dim M, 64x64 boxes.
+    uint64_t dims[2] = {static_cast<uint64_t>(a_mn ? p.M : p.K), static_cast<uint64_t>(a_mn ? p.K : p.M)};
     uint64_t str[1] = {static_cast<uint64_t>(lda) * 2};
-    uint32_t box[2] = {kBlockK, kBlockM};
+    uint32_t box[2] = {kBlockK, a_mn ? 64u : static_cast<uint32_t>(kBlockM)};
     if ((rc = make_tmap_bf16(&ta, A, 2, dims, str, box)) != MERLIN_OK) return rc;
   }
   {
-    uint64_t dims[2] = {static_cast<uint64_t>(p.K), static_cast<uint64_t>(p.N)};
+    uint64_t dims[2] = {static_cast<uint64_t>(b_mn ? p.N : p.K), static_cast<uint64_t>(b_mn ? p.K : p.N)};
     uint64_t str[1] = {static_cast<uint64_t>(ldb) * 2};
-    uint32_t box[2] = {kBlockK, static_cast<uint32_t>(kBlockN / cta_group)};
+    uint32_t box[2] = {kBlockK, b_mn ? 64u : static_cast<uint32_t>(kBlockN / cta_group)};
     if ((rc = make_tmap_bf16(&tb, B, 2, dims, str, box)) != MERLIN_OK) return rc;
   }
   {
@@ -155,8 +157,15 @@ int gemm_dispatch(cudaStream_t stream, const void* A, int64_t lda, const void* B
   } else {
     tr = tc;
   }
-  return cta_group == 2 ? launch_gemm<2>(stream, ta, tb, tc, tr, p)
-                        : launch_gemm<1>(stream, ta, tb, tc, tr, p);
+  MB_CHECK_ARG(!(a_mn && !b_mn), "gemm: A MN-major with B K-major is not instantiated");
+  if (cta_group == 2) {
+    if (a_mn) return launch_gemm<2, true, true>(stream, ta, tb, tc, tr, p);
+    if (b_mn) return launch_gemm<2, false, true>(stream, ta, tb, tc, tr, p);
+    return launch_gemm<2, false, false>(stream, ta, tb, tc, tr, p);
+  }
+  if (a_mn) return launch_gemm<1, true, true>(stream, ta, tb, tc, tr, p);
+  if (b_mn) return launch_gemm<1, false, true>(stream, ta, tb, tc, tr, p);
+  return launch_gemm<1, false, false>(stream, ta, tb, tc, tr, p);
 }
 
 }  // namespace mb
@@ -178,6 +187,21 @@ int merlin_gemm_bf16(void* stream, const void* A, int64_t lda, const void* B, in
   p.bias = static_cast<const __nv_bfloat16*>(bias);
   return mb::gemm_dispatch(static_cast<cudaStream_t>(stream), A, lda, B, ldb, C, ldc, R, ldr, p,
                            cta_group);
+}
+
+int merlin_gemm_bf16_ex(void* stream, const void* A, int64_t lda, int a_mn_major, const void* B, int64_t ldb,
+                        int b_mn_major, void* C, int64_t ldc, const void* R, int64_t ldr, const void* bias,
+                        int M, int N, int K, int epilogue, int cta_group) {
+  MB_CHECK_ARG(epilogue >= MERLIN_EPI_STORE && epilogue <= MERLIN_EPI_SWIGLU,
+               "merlin_gemm_bf16_ex: unknown epilogue %d", epilogue);
+  mb::GemmParams p = {};
+  p.M = M;
+  p.N = N;
+  p.K = K;
+  p.epilogue = epilogue;
+  p.bias = static_cast<const __nv_bfloat16*>(bias);
+  return mb::gemm_dispatch(static_cast<cudaStream_t>(stream), A, lda, B, ldb, C, ldc, R, ldr, p, cta_group,
+                           a_mn_major != 0, b_mn_major != 0);
 }
 
 int merlin_gemm_qkv_rope(void* stream, const void* A, int64_t lda, const void* Wqkv, int64_t ldb,

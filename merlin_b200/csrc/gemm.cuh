@@ -117,7 +117,11 @@ __device__ __forceinline__ TileCoord tile_coord(int t, int tiles_m) {
   return TileCoord{t % tiles_m, t / tiles_m};
 }
 
-template <int kCtaGroup>
+// kAMN / kBMN: the operand is stored "MN-major", i.e. as a row-major [K, M] (resp. [K, N]) matrix whose
+// contiguous dimension is M (N) — what backward needs: dX = dY·W reads W[N_red, K_out] as B, and
+// dW = dYᵀ·X reads dY[M_red, N] as A and X[M_red, K] as B.  Such tiles are staged as 64-element x 64-row
+// 128B-swizzled boxes and described to tcgen05.mma with MN-major descriptors.
+template <int kCtaGroup, bool kAMN = false, bool kBMN = false>
 __global__ void __launch_bounds__(kGemmThreads, 1)
 gemm_bf16_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant__ CUtensorMap tm_b,
                  const __grid_constant__ CUtensorMap tm_c, const __grid_constant__ CUtensorMap tm_r,
@@ -199,14 +203,28 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant
           mbar_wait(&empty_bar[stage], phase ^ 1);
           uint8_t* sa = smem_ab + stage * Cfg::kStageBytes;
           uint8_t* sb = sa + Cfg::kABytes;
+          auto load = [&](const CUtensorMap* tm, void* dst, int c0, int c1, uint64_t hint) {
+            if constexpr (kCtaGroup == 2) tma_load_2d_pair(tm, &full_bar[stage], dst, c0, c1, hint);
+            else tma_load_2d(tm, &full_bar[stage], dst, c0, c1, hint);
+          };
           if constexpr (kCtaGroup == 2) {
             if (is_leader) mbar_expect_tx(&full_bar[stage], 2 * Cfg::kStageBytes);
-            tma_load_2d_pair(&tm_a, &full_bar[stage], sa, kb * kBlockK, m0, kEvictNormal);
-            tma_load_2d_pair(&tm_b, &full_bar[stage], sb, kb * kBlockK, n0, kEvictLast);
           } else {
             mbar_expect_tx(&full_bar[stage], Cfg::kStageBytes);
-            tma_load_2d(&tm_a, &full_bar[stage], sa, kb * kBlockK, m0, kEvictNormal);
-            tma_load_2d(&tm_b, &full_bar[stage], sb, kb * kBlockK, n0, kEvictLast);
+          }
+          if constexpr (kAMN) {
+#pragma unroll
+            for (int i = 0; i < kBlockM / 64; ++i)
+              load(&tm_a, sa + i * 8192, m0 + i * 64, kb * kBlockK, kEvictNormal);
+          } else {
+            load(&tm_a, sa, kb * kBlockK, m0, kEvictNormal);
+          }
+          if constexpr (kBMN) {
+#pragma unroll
+            for (int i = 0; i < Cfg::kLoadN / 64; ++i)
+              load(&tm_b, sb + i * 8192, n0 + i * 64, kb * kBlockK, kEvictLast);
+          } else {
+            load(&tm_b, sb, kb * kBlockK, n0, kEvictLast);
           }
           if (++stage == kStages) {
             stage = 0;
@@ -219,7 +237,7 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant
   } else if (warp == 1) {
     // ======================================================= MMA issuer
     if (is_leader && elect_one()) {
-      constexpr uint32_t idesc = umma_idesc_bf16(kBlockM * kCtaGroup, kBlockN, 0, 0);
+      constexpr uint32_t idesc = umma_idesc_bf16(kBlockM * kCtaGroup, kBlockN, kAMN ? 1 : 0, kBMN ? 1 : 0);
       int stage = 0;
       uint32_t phase = 0;
       int acc = 0;
@@ -233,15 +251,14 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant
           tc_fence_after();
           const uint32_t sa = smem_u32(smem_ab + stage * Cfg::kStageBytes);
           const uint32_t sb = sa + Cfg::kABytes;
-          const uint64_t da = umma_desc_k_sw128(sa);
-          const uint64_t db = umma_desc_k_sw128(sb);
 #pragma unroll
           for (int k = 0; k < kBlockK / 16; ++k) {
-            // advance 16 bf16 = 32 bytes along K inside the swizzle atom: +2 in (addr >> 4) units
-            if constexpr (kCtaGroup == 2)
-              umma_ss_pair(tmem_d, da + 2 * k, db + 2 * k, idesc, (kb | k) != 0);
-            else
-              umma_ss(tmem_d, da + 2 * k, db + 2 * k, idesc, (kb | k) != 0);
+            // K-major: advance 16 bf16 = 32 bytes inside the swizzle atom.  MN-major: 16 k-rows of
+            // 128 bytes = 2048 bytes; 64-element MN groups are 8 KB apart (LBO).
+            const uint64_t da = kAMN ? umma_desc_mn_sw128(sa + k * 2048, 8192) : umma_desc_k_sw128(sa + k * 32);
+            const uint64_t db = kBMN ? umma_desc_mn_sw128(sb + k * 2048, 8192) : umma_desc_k_sw128(sb + k * 32);
+            if constexpr (kCtaGroup == 2) umma_ss_pair(tmem_d, da, db, idesc, (kb | k) != 0);
+            else umma_ss(tmem_d, da, db, idesc, (kb | k) != 0);
           }
           if constexpr (kCtaGroup == 2) umma_commit_pair(&empty_bar[stage]);
           else umma_commit(&empty_bar[stage]);

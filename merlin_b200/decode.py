@@ -13,7 +13,7 @@ from . import lib as _lib
 from . import ops as _ops
 from .lib import DecoderWeights, check
 
-N_SPLITS = int(__import__("os").environ.get("MERLIN_FD_SPLITS", "16"))  # flash-decode key splits (x 32 heads CTAs per layer)
+N_SPLITS = int(__import__("os").environ.get("MERLIN_FD_SPLITS", "32"))  # flash-decode key splits (x 32 heads CTAs per layer)
 
 
 def _ptr_array(tensors):

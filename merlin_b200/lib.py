@@ -25,6 +25,7 @@ class MerlinError(RuntimeError):
 _P = c_void_p
 _PROTOTYPES = {
     "merlin_gemm_bf16": [_P, _P, c_int64, _P, c_int64, _P, c_int64, _P, c_int64, _P, c_int, c_int, c_int, c_int, c_int],
+    "merlin_gemm_bf16_ex": [_P, _P, c_int64, c_int, _P, c_int64, c_int, _P, c_int64, _P, c_int64, _P, c_int, c_int, c_int, c_int, c_int],
     "merlin_gemm_qkv_rope": [_P, _P, c_int64, _P, c_int64, _P, c_int64, _P, _P, _P, c_int, c_int, c_int, c_int, c_int, c_int],
     "merlin_flash_attn_fwd": [_P, _P, c_int64, _P, c_int64, _P, _P, c_int, c_int, c_int, c_int, c_int, c_float],
     "merlin_rmsnorm": [_P, _P, c_int64, _P, _P, c_int64, c_int, c_int, c_float],
@@ -34,8 +35,20 @@ _PROTOTYPES = {
     "merlin_conv3x3_im2col": [_P, _P, _P, c_int, c_int, c_int, c_int, c_int, c_int],
     "merlin_embed_splice": [_P, _P, _P, _P, _P, _P, c_int, c_int, c_int, c_int, _P, _P, c_int64, c_int64],
     "merlin_rope_qk_inplace": [_P, _P, c_int64, _P, _P, _P, c_int, c_int, c_int],
+    "merlin_rope_qk_inplace_ex": [_P, _P, c_int64, _P, _P, _P, c_int, c_int, c_int, c_int],
+    "merlin_flash_attn_bwd": [_P, _P, c_int64, _P, _P, c_int64, _P, _P, _P, c_int64, _P, c_int, c_int, c_int, c_int, c_int, c_float],
     "merlin_cross_entropy_fwd": [_P, _P, c_int64, _P, c_int, c_int, c_int, c_int64, _P, _P],
     "merlin_argmax": [_P, _P, c_int64, c_int, c_int, _P],
+    "merlin_rmsnorm_bwd": [_P, _P, _P, _P, _P, _P, _P, c_int, c_int, c_float],
+    "merlin_swiglu_fwd": [_P, _P, _P, c_int, c_int],
+    "merlin_swiglu_bwd": [_P, _P, _P, _P, c_int, c_int],
+    "merlin_cross_entropy_bwd": [_P, _P, c_int64, _P, c_int, c_int, c_int, c_int64, _P, c_float, _P, c_int64],
+    "merlin_embed_splice_bwd": [_P, _P, _P, _P, _P, _P, c_int, c_int, c_int, c_int64],
+    "merlin_colsum": [_P, _P, c_int64, _P, c_int, c_int],
+    "merlin_attn_delta": [_P, _P, _P, _P, c_int, c_int, c_int, c_int, c_int64],
+    "merlin_grad_sumsq": [_P, _P, c_int64, _P],
+    "merlin_adamw_step": [_P, _P, _P, _P, _P, _P, _P, c_int, c_int64, c_float, c_float, c_float, c_float, c_int, c_float, c_float, _P],
+    "merlin_f32_to_bf16": [_P, _P, _P, c_int64],
     "merlin_decode_step": [_P, _P, _P, _P, _P, _P, c_int],
     "merlin_embed_token": [_P, _P, _P, _P, c_int, c_int64],
     "merlin_record_advance": [_P, _P, _P, _P, _P, c_int],
@@ -83,6 +96,8 @@ def load() -> ctypes.CDLL:
     lib.merlin_last_error.argtypes = []
     lib.merlin_decode_workspace_bytes.restype = ctypes.c_size_t
     lib.merlin_decode_workspace_bytes.argtypes = [c_int, c_int, c_int, c_int]
+    lib.merlin_flash_attn_bwd_workspace_bytes.restype = ctypes.c_size_t
+    lib.merlin_flash_attn_bwd_workspace_bytes.argtypes = [c_int, c_int, c_int, c_int]
     for name, argtypes in _PROTOTYPES.items():
         fn = getattr(lib, name)
         fn.restype = c_int

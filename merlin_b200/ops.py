@@ -109,6 +109,44 @@ def gemm(a: torch.Tensor, w: torch.Tensor, *, bias: Optional[torch.Tensor] = Non
     return out
 
 
+def gemm_nt(a: torch.Tensor, b_t: torch.Tensor, *, out: Optional[torch.Tensor] = None,
+            accumulate: bool = False, cta_group: Optional[int] = None) -> torch.Tensor:
+    """out[M,N] (+)= a[M,K] @ b_t[K,N]   (B given transposed / "MN-major").  The dgrad contraction:
+    dX = dY @ W with a = dY [tokens, out], b_t = W [out, in]."""
+    M, K, lda = _rows2d(a, "a")
+    Kb, N, ldb = _rows2d(b_t, "b_t")
+    if K != Kb:
+        raise ValueError(f"gemm_nt: K mismatch {K} vs {Kb}")
+    return _gemm_ex(a, lda, 0, b_t, ldb, 1, M, N, K, out, accumulate, cta_group)
+
+
+def gemm_tn(a_t: torch.Tensor, b_t: torch.Tensor, *, out: Optional[torch.Tensor] = None,
+            accumulate: bool = False, cta_group: Optional[int] = None) -> torch.Tensor:
+    """out[M,N] (+)= a_t[K,M].T @ b_t[K,N]   (both operands transposed).  The wgrad contraction:
+    dW = dY.T @ X with a_t = dY [tokens, out], b_t = X [tokens, in]."""
+    K, M, lda = _rows2d(a_t, "a_t")
+    Kb, N, ldb = _rows2d(b_t, "b_t")
+    if K != Kb:
+        raise ValueError(f"gemm_tn: K mismatch {K} vs {Kb}")
+    return _gemm_ex(a_t, lda, 1, b_t, ldb, 1, M, N, K, out, accumulate, cta_group)
+
+
+def _gemm_ex(a, lda, a_mn, b, ldb, b_mn, M, N, K, out, accumulate, cta_group):
+    if out is None:
+        if accumulate:
+            raise ValueError("accumulate=True needs an output tensor")
+        out = torch.empty((M, (N + 7) // 8 * 8), dtype=_BF16, device=a.device)[:, :N]
+    Mo, No, ldc = _rows2d(out, "out")
+    if (Mo, No) != (M, N):
+        raise ValueError(f"gemm: out shape {(Mo, No)} != {(M, N)}")
+    L = _lib.load()
+    epi = EPI_RESIDUAL if accumulate else EPI_STORE
+    check(_gemm_call(L.merlin_gemm_bf16_ex, 2 * M * N * K, _stream(), a.data_ptr(), lda, a_mn, b.data_ptr(), ldb,
+                     b_mn, out.data_ptr(), ldc, out.data_ptr() if accumulate else None, ldc, None, M, N, K, epi,
+                     cta_group or DEFAULT_CTA_GROUP), "merlin_gemm_bf16_ex")
+    return out
+
+
 def gemm_qkv_rope(a: torch.Tensor, w_qkv: torch.Tensor, rope_cos: torch.Tensor, rope_sin: torch.Tensor,
                   seq_len: int, *, positions: Optional[torch.Tensor] = None,
                   out: Optional[torch.Tensor] = None, cta_group: Optional[int] = None) -> torch.Tensor:
@@ -280,3 +318,113 @@ def swiglu_interleave(gate_w: torch.Tensor, up_w: torch.Tensor) -> torch.Tensor:
     g = gate_w.view(FF // 128, 128, D)
     u = up_w.view(FF // 128, 128, D)
     return torch.stack((g, u), dim=1).reshape(2 * FF, D).contiguous()
+
+
+# ----------------------------------------------------------------------------- backward / optimizer ops
+def flash_attn_bwd(qkv: torch.Tensor, out: torch.Tensor, dout: torch.Tensor, lse: torch.Tensor, batch: int, seq: int,
+                   heads: int, head_dim: int, *, causal: bool, seqlens: Optional[torch.Tensor] = None,
+                   dqkv: Optional[torch.Tensor] = None, softmax_scale: float = 0.0) -> torch.Tensor:
+    """Packed gradient [batch*seq, 3*heads*head_dim] w.r.t. the (rotated) packed qkv."""
+    M, N, ld = _rows2d(qkv, "qkv")
+    _, _, ldo = _rows2d(out, "out")
+    _, _, ldd = _rows2d(dout, "dout")
+    if ldo != ldd:
+        raise ValueError("flash_attn_bwd: out and dout must share a row pitch")
+    if dqkv is None:
+        dqkv = torch.empty_like(qkv)
+    _, _, ldg = _rows2d(dqkv, "dqkv")
+    L = _lib.load()
+    ws = torch.empty(L.merlin_flash_attn_bwd_workspace_bytes(batch, seq, heads, head_dim), dtype=torch.uint8,
+                     device=qkv.device)
+    check(L.merlin_flash_attn_bwd(_stream(), qkv.data_ptr(), ld, out.data_ptr(), dout.data_ptr(), ldo,
+                                  lse.data_ptr(), _ptr(seqlens), dqkv.data_ptr(), ldg, ws.data_ptr(), batch, seq,
+                                  heads, head_dim, int(causal), float(softmax_scale)), "merlin_flash_attn_bwd", 4)
+    return dqkv
+
+
+def rope_qk_inverse_inplace(dqkv: torch.Tensor, rope_cos: torch.Tensor, rope_sin: torch.Tensor, heads: int,
+                            seq_len: int) -> torch.Tensor:
+    M, _, ld = _rows2d(dqkv, "dqkv")
+    check(_lib.load().merlin_rope_qk_inplace_ex(_stream(), dqkv.data_ptr(), ld, rope_cos.data_ptr(),
+                                                rope_sin.data_ptr(), None, M, heads, seq_len, 1),
+          "merlin_rope_qk_inplace_ex", 1)
+    return dqkv
+
+
+def rmsnorm_bwd(x: torch.Tensor, weight: torch.Tensor, dy: torch.Tensor, dres: Optional[torch.Tensor],
+                dweight: Optional[torch.Tensor], eps: float, out: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """dx = rmsnorm'(dy) (+ dres); dweight (fp32 [D]) accumulates.  x, dy, dres, out: contiguous [M, D]."""
+    M, D, _ = _rows2d(x, "x")
+    for t, n in ((x, "x"), (dy, "dy")):
+        if not t.is_contiguous():
+            raise ValueError(f"rmsnorm_bwd: {n} must be contiguous")
+    if out is None:
+        out = torch.empty_like(x)
+    if dweight is not None and dweight.dtype != torch.float32:
+        raise ValueError("rmsnorm_bwd: dweight accumulates in fp32")
+    check(_lib.load().merlin_rmsnorm_bwd(_stream(), x.data_ptr(), weight.data_ptr(), dy.data_ptr(), _ptr(dres),
+                                         out.data_ptr(), _ptr(dweight), M, D, float(eps)), "merlin_rmsnorm_bwd", 1)
+    return out
+
+
+def swiglu_fwd(gate_up: torch.Tensor, out: Optional[torch.Tensor] = None) -> torch.Tensor:
+    M, N2, _ = _rows2d(gate_up, "gate_up")
+    if out is None:
+        out = torch.empty((M, N2 // 2), dtype=_BF16, device=gate_up.device)
+    check(_lib.load().merlin_swiglu_fwd(_stream(), gate_up.data_ptr(), out.data_ptr(), M, N2 // 2), "merlin_swiglu_fwd", 1)
+    return out
+
+
+def swiglu_bwd(gate_up: torch.Tensor, dmid: torch.Tensor, out: Optional[torch.Tensor] = None) -> torch.Tensor:
+    M, N2, _ = _rows2d(gate_up, "gate_up")
+    if out is None:
+        out = torch.empty_like(gate_up)
+    check(_lib.load().merlin_swiglu_bwd(_stream(), gate_up.data_ptr(), dmid.data_ptr(), out.data_ptr(), M, N2 // 2),
+          "merlin_swiglu_bwd", 1)
+    return out
+
+
+def cross_entropy_with_grad(logits: torch.Tensor, labels: torch.Tensor, batch: int, seq: int,
+                            ignore_index: int = -100, grad_scale: float = 1.0):
+    """Returns (mean loss, dlogits written IN PLACE over `logits`)."""
+    M, V, ld = _rows2d(logits, "logits")
+    acc = torch.empty((2,), dtype=torch.float32, device=logits.device)
+    L = _lib.load()
+    check(L.merlin_cross_entropy_fwd(_stream(), logits.data_ptr(), ld, labels.data_ptr(), batch, seq, V, ignore_index,
+                                     None, acc.data_ptr()), "merlin_cross_entropy_fwd", 1)
+    check(L.merlin_cross_entropy_bwd(_stream(), logits.data_ptr(), ld, labels.data_ptr(), batch, seq, V, ignore_index,
+                                     acc.data_ptr(), float(grad_scale), logits.data_ptr(), ld),
+          "merlin_cross_entropy_bwd", 1)
+    return acc[0] / acc[1], logits
+
+
+def embed_splice_bwd(input_ids: torch.Tensor, rank: Optional[torch.Tensor], dx: torch.Tensor,
+                     dtable: Optional[torch.Tensor], dfeats: Optional[torch.Tensor], vocab: int) -> None:
+    T, D, _ = _rows2d(dx, "dx")
+    nfeat = 0 if dfeats is None else dfeats.shape[0]
+    check(_lib.load().merlin_embed_splice_bwd(_stream(), input_ids.data_ptr(), _ptr(rank), dx.data_ptr(),
+                                              _ptr(dtable), _ptr(dfeats), T, D, nfeat, vocab),
+          "merlin_embed_splice_bwd", 1)
+
+
+def colsum_accumulate(x: torch.Tensor, out_f32: torch.Tensor) -> None:
+    M, N, ld = _rows2d(x, "x")
+    check(_lib.load().merlin_colsum(_stream(), x.data_ptr(), ld, out_f32.data_ptr(), M, N), "merlin_colsum", 1)
+
+
+def grad_sumsq(grads: torch.Tensor, out_f32: torch.Tensor) -> None:
+    check(_lib.load().merlin_grad_sumsq(_stream(), grads.data_ptr(), grads.numel(), out_f32.data_ptr()),
+          "merlin_grad_sumsq", 1)
+
+
+def adamw_step(params, grads, exp_avg, exp_avg_sq, lr_mult, weight_decay, chunk: int, lr: float, beta1: float,
+               beta2: float, eps: float, step: int, grad_scale: float = 1.0, max_grad_norm: float = 0.0,
+               sumsq: Optional[torch.Tensor] = None) -> None:
+    check(_lib.load().merlin_adamw_step(_stream(), params.data_ptr(), grads.data_ptr(), exp_avg.data_ptr(),
+                                        exp_avg_sq.data_ptr(), lr_mult.data_ptr(), weight_decay.data_ptr(), chunk,
+                                        params.numel(), float(lr), float(beta1), float(beta2), float(eps), int(step),
+                                        float(grad_scale), float(max_grad_norm), _ptr(sumsq)), "merlin_adamw_step", 1)
+
+
+def f32_to_bf16(x: torch.Tensor, y: torch.Tensor) -> None:
+    check(_lib.load().merlin_f32_to_bf16(_stream(), x.data_ptr(), y.data_ptr(), x.numel()), "merlin_f32_to_bf16", 1)

@@ -223,3 +223,178 @@ def test_cross_entropy_and_argmax():
     tie = torch.zeros(1, 64, device=DEV, dtype=torch.bfloat16)
     tie[0, 5] = tie[0, 40] = 3.0
     assert ops.argmax(tie).item() == 5                                           # lowest index on ties
+
+
+@pytest.mark.parametrize("cg", [1, 2])
+@pytest.mark.parametrize("mnk", [(256, 256, 64), (512, 384, 200), (4096, 1024, 2048), (300, 1000, 577), (1000, 264, 2885)])
+def test_gemm_backward_layouts(cg, mnk):
+    """dgrad (B transposed) and wgrad (both transposed) operand layouts, exact on {-1,0,1} operands."""
+    torch.manual_seed(11)
+    M, N, K = mnk
+    a, bt, at = ints((M, K)), ints((K, N)), ints((K, M))
+    assert torch.equal(ops.gemm_nt(a, bt, cta_group=cg).float(), a.float() @ bt.float())
+    assert torch.equal(ops.gemm_tn(at, bt, cta_group=cg).float(), at.float().t() @ bt.float())
+    acc = ints((M, N))
+    want = acc.float() + at.float().t() @ bt.float()
+    ops.gemm_tn(at, bt, out=acc, accumulate=True, cta_group=cg)          # gradient accumulation
+    assert torch.equal(acc.float(), want)
+
+
+def test_linear_backward_matches_autograd():
+    torch.manual_seed(12)
+    x = torch.randn(777, 512, device=DEV).to(torch.bfloat16)
+    w = (torch.randn(1024, 512, device=DEV) * 0.05).to(torch.bfloat16)
+    dy = torch.randn(777, 1024, device=DEV).to(torch.bfloat16)
+    close(ops.gemm_nt(dy, w), dy.float() @ w.float())                      # dX = dY·W
+    close(ops.gemm_tn(dy, x), dy.float().t() @ x.float())                  # dW = dYᵀ·X
+
+
+@pytest.mark.parametrize("causal", [True, False])
+@pytest.mark.parametrize("bsh", [(1, 128, 1), (1, 256, 2), (2, 384, 2), (1, 1000, 2), (1, 2048, 2)])
+def test_flash_attention_backward(causal, bsh):
+    torch.manual_seed(13)
+    B, S, H, hd = *bsh, 128
+    qkv = torch.randn(B * S, 3 * H * hd, device=DEV).to(torch.bfloat16)
+    dout = torch.randn(B * S, H * hd, device=DEV).to(torch.bfloat16)
+    out, lse = ops.flash_attn(qkv, B, S, H, hd, causal=causal, return_lse=True)
+    dqkv = ops.flash_attn_bwd(qkv, out, dout, lse, B, S, H, hd, causal=causal)
+    ref_in = qkv.float().clone().requires_grad_(True)
+    q, k, v = ref_in.view(B, S, 3, H, hd).permute(2, 0, 3, 1, 4)
+    s = (q @ k.transpose(-1, -2)) / hd ** 0.5
+    if causal:
+        idx = torch.arange(S, device=DEV)
+        s = s.masked_fill((idx[None, :] > idx[:, None])[None, None], float("-inf"))
+    o = (torch.softmax(s, -1) @ v).permute(0, 2, 1, 3).reshape(B * S, H * hd)
+    o.backward(dout.float())
+    g = ref_in.grad.view(B * S, 3, H * hd)
+    mine = dqkv.float().view(B * S, 3, H * hd)
+    for blk in range(3):
+        close(mine[:, blk], g[:, blk], tol=2.0 ** -6)
+
+
+def test_flash_attention_backward_padding():
+    torch.manual_seed(14)
+    B, S, H, hd = 2, 300, 2, 128
+    qkv = torch.randn(B * S, 3 * H * hd, device=DEV).to(torch.bfloat16)
+    dout = torch.randn(B * S, H * hd, device=DEV).to(torch.bfloat16)
+    sl = torch.tensor([300, 77], dtype=torch.int32, device=DEV)
+    out, lse = ops.flash_attn(qkv, B, S, H, hd, causal=True, seqlens=sl, return_lse=True)
+    dqkv = ops.flash_attn_bwd(qkv, out, dout, lse, B, S, H, hd, causal=True, seqlens=sl).view(B, S, -1)
+    ref_in = qkv.float().clone().requires_grad_(True)
+    ref, _ = attn_ref(ref_in, B, S, H, hd, True, sl)
+    ref.backward(dout.float())
+    g = ref_in.grad.view(B, S, -1)
+    close(dqkv[0], g[0], tol=2.0 ** -6)
+    close(dqkv[1, :77], g[1, :77], tol=2.0 ** -6)
+    assert bool((dqkv[1, 77:] == 0).all())
+
+
+def test_elementwise_backward_kernels():
+    torch.manual_seed(15)
+    M, D, FF = 333, 4096, 1408
+    x = torch.randn(M, D, device=DEV).to(torch.bfloat16)
+    w = (1 + 0.1 * torch.randn(D, device=DEV)).to(torch.bfloat16)
+    dy = torch.randn(M, D, device=DEV).to(torch.bfloat16)
+    dres = torch.randn(M, D, device=DEV).to(torch.bfloat16)
+    xr, wr = x.float().requires_grad_(True), w.float().requires_grad_(True)
+    y = wr * (xr * torch.rsqrt(xr.pow(2).mean(-1, keepdim=True) + 1e-5))
+    y.backward(dy.float())
+    dw = torch.zeros(D, dtype=torch.float32, device=DEV)
+    dx = ops.rmsnorm_bwd(x, w, dy, dres, dw, 1e-5)
+    close(dx, xr.grad + dres.float())
+    close(dw, wr.grad, tol=2.0 ** -9)
+    close(ops.rmsnorm_bwd(x, w, dy, None, None, 1e-5), xr.grad)
+    # swiglu
+    g = torch.randn(M, FF, device=DEV).to(torch.bfloat16)
+    u = torch.randn(M, FF, device=DEV).to(torch.bfloat16)
+    gu = torch.stack((g.view(M, FF // 128, 128), u.view(M, FF // 128, 128)), dim=2).reshape(M, 2 * FF).contiguous()
+    gr, ur = g.float().requires_grad_(True), u.float().requires_grad_(True)
+    mid = torch.nn.functional.silu(gr) * ur
+    close(ops.swiglu_fwd(gu), mid)
+    dmid = torch.randn(M, FF, device=DEV).to(torch.bfloat16)
+    mid.backward(dmid.float())
+    dgu = ops.swiglu_bwd(gu, dmid).view(M, FF // 128, 2, 128)
+    close(dgu[:, :, 0].reshape(M, FF), gr.grad)
+    close(dgu[:, :, 1].reshape(M, FF), ur.grad)
+    # rope inverse undoes rope
+    H, S = 4, 200
+    qkv = torch.randn(S, 3 * H * 128, device=DEV).to(torch.bfloat16)
+    cos, sin = ops.rope_tables(256)
+    rot = ops.rope_qk_inplace(qkv.clone(), cos, sin, H, S)
+    close(ops.rope_qk_inverse_inplace(rot, cos, sin, H, S), qkv, tol=2.0 ** -6)
+    # cross-entropy backward
+    B, S2, V = 2, 40, 1003
+    logits = torch.randn(B * S2, 1008, device=DEV).to(torch.bfloat16)[:, :V]
+    labels = torch.randint(0, V, (B, S2), device=DEV)
+    labels[:, :10] = -100
+    lr_ = logits.float().clone().requires_grad_(True)
+    loss_ref = torch.nn.functional.cross_entropy(lr_.view(B, S2, V)[:, :-1].reshape(-1, V), labels[:, 1:].reshape(-1))
+    loss_ref.backward()
+    loss, dlog = ops.cross_entropy_with_grad(logits, labels, B, S2)
+    assert abs(loss.item() - loss_ref.item()) < 1e-4
+    close(dlog, lr_.grad, tol=2.0 ** -7)
+    # embedding / splice backward + column sums
+    Vv, Dd = 500, 256
+    ids = torch.randint(0, Vv - 1, (1, 300), device=DEV)
+    ids[0, 50:60] = Vv - 1
+    ids[0, 100] = ids[0, 101] = 7                          # duplicate token: gradients add
+    table = torch.randn(Vv, Dd, device=DEV).to(torch.bfloat16)
+    feats = torch.randn(10, Dd, device=DEV).to(torch.bfloat16)
+    off = torch.zeros(1, dtype=torch.int32, device=DEV)
+    lim = torch.full((1,), 10, dtype=torch.int32, device=DEV)
+    _, _ = ops.embed_splice(ids, table, feats, Vv - 1, off, lim)
+    rank = torch.full((300,), -1, dtype=torch.int32, device=DEV)
+    rank[50:60] = torch.arange(10, dtype=torch.int32, device=DEV)
+    dxx = torch.randn(300, Dd, device=DEV).to(torch.bfloat16)
+    dtable = torch.zeros(Vv, Dd, device=DEV, dtype=torch.bfloat16)
+    dfeats = torch.zeros(10, Dd, device=DEV, dtype=torch.bfloat16)
+    ops.embed_splice_bwd(ids.view(-1), rank, dxx, dtable, dfeats, Vv)
+    assert torch.equal(dfeats, dxx[50:60])
+    ref_t = torch.zeros(Vv, Dd, device=DEV)
+    text = torch.ones(300, dtype=torch.bool, device=DEV)
+    text[50:60] = False
+    ref_t.index_add_(0, ids.view(-1)[text], dxx.float()[text])
+    close(dtable, ref_t, tol=2.0 ** -7)
+    cs = torch.zeros(Dd, dtype=torch.float32, device=DEV)
+    ops.colsum_accumulate(dxx, cs)
+    close(cs, dxx.float().sum(0), tol=1e-5)
+
+
+def test_adamw_matches_fp32_reference_rule():
+    torch.manual_seed(16)
+    n, chunk = 8192 * 3, 8192
+    p = torch.randn(n, device=DEV).to(torch.bfloat16)
+    g = (torch.randn(n, device=DEV) * 0.1).to(torch.bfloat16)
+    m = torch.zeros(n, device=DEV, dtype=torch.bfloat16)
+    v = torch.zeros(n, device=DEV, dtype=torch.bfloat16)
+    lr_mult = torch.tensor([1.0, 0.5, 0.0], device=DEV)
+    wd = torch.tensor([0.05, 0.0, 0.05], device=DEV)
+    ss = torch.zeros(1, device=DEV)
+    ops.grad_sumsq(g, ss)
+    close(ss, g.float().pow(2).sum().view(1), tol=1e-4)
+    pr, mr, vr = p.float().clone(), m.float().clone(), v.float().clone()
+    lr, b1, b2, eps, max_norm = 1e-2, 0.9, 0.95, 1e-8, 1.0
+    for step in (1, 2):
+        ops.grad_sumsq(g, ss)
+        ops.adamw_step(p, g, m, v, lr_mult, wd, chunk, lr, b1, b2, eps, step, 1.0, max_norm, ss)
+        clip = min(1.0, max_norm / (g.float().norm().item() + 1e-6))
+        gg = g.float() * clip
+        for c in range(3):
+            sl = slice(c * chunk, (c + 1) * chunk)
+            lrc = lr * lr_mult[c].item()
+            if lrc == 0:
+                continue
+            mr[sl] = (b1 * mr[sl] + (1 - b1) * gg[sl]).to(torch.bfloat16).float()
+            vr[sl] = (b2 * vr[sl] + (1 - b2) * gg[sl] ** 2).to(torch.bfloat16).float()
+        # (reference rule evaluated in fp32 on the bf16-rounded state, like the kernel)
+        for c in range(3):
+            sl = slice(c * chunk, (c + 1) * chunk)
+            lrc = lr * lr_mult[c].item()
+            if lrc == 0:
+                continue
+            m_pre = (mr[sl])
+            denom = vr[sl].sqrt() / (1 - b2 ** step) ** 0.5 + eps
+            pr[sl] = (pr[sl] * (1 - lrc * wd[c].item()) - lrc / (1 - b1 ** step) * m_pre / denom).to(torch.bfloat16).float()
+    assert torch.equal(p[2 * chunk:], p[2 * chunk:])           # frozen chunk untouched below
+    close(p[:2 * chunk], pr[:2 * chunk], tol=2.0 ** -6)
+    close(m[:2 * chunk], mr[:2 * chunk], tol=2.0 ** -6)
