@@ -241,22 +241,24 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid_constan
       mbar_arrive(dq_read);
     }
 
-    // ---- dK, dV of this key tile (thread = key row)
+    // ---- dK, dV of this key tile (thread = key row).  The TMEM loads are warp-collective
+    // (.sync.aligned): every lane executes them, only the global stores are predicated.
     const int kv_idx = kv0 + row;
-    if (kv_idx < p.S) {
-      __nv_bfloat16* out_row = p.dqkv + (static_cast<size_t>(batch) * p.S + kv_idx) * p.ld_dqkv;
-      const bool live = n_steps > 0 && kv_idx < len;
+    const bool in_range = kv_idx < p.S;
+    const bool live = n_steps > 0 && kv_idx < len;
+    __nv_bfloat16* out_row = p.dqkv + (static_cast<size_t>(batch) * p.S + (in_range ? kv_idx : 0)) * p.ld_dqkv;
 #pragma unroll
-      for (int which = 0; which < 2; ++which) {
-        const uint32_t t_acc = which == 0 ? t_dk : t_dv;
-        __nv_bfloat16* dst = out_row + (which == 0 ? p.k_col0 : p.v_col0) + head * HD;
+    for (int which = 0; which < 2; ++which) {
+      const uint32_t t_acc = which == 0 ? t_dk : t_dv;
+      __nv_bfloat16* dst = out_row + (which == 0 ? p.k_col0 : p.v_col0) + head * HD;
 #pragma unroll
-        for (int ch = 0; ch < 4; ++ch) {
-          uint32_t v[32];
-          if (n_steps > 0) {
-            tmem_ld32(t_acc + lane_sel + ch * 32, v);
-            tmem_ld_wait();
-          }
+      for (int ch = 0; ch < 4; ++ch) {
+        uint32_t v[32];
+        if (n_steps > 0) {  // block-uniform
+          tmem_ld32(t_acc + lane_sel + ch * 32, v);
+          tmem_ld_wait();
+        }
+        if (in_range) {
 #pragma unroll
           for (int q4 = 0; q4 < 4; ++q4) {
             uint4 w = make_uint4(0, 0, 0, 0);

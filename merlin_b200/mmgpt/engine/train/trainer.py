@@ -1,0 +1,250 @@
+"""MMGPTTrainer on B200 kernels — the data-parallel training step loop.
+
+Replaces the reference's `MMGPTTrainer(transformers.Trainer)` (mmgpt/engine/train/trainer.py:13-74) and
+the HF `Trainer._inner_training_loop` + FSDP + autograd machinery underneath it:
+
+  * `create_optimizer()`  — LLRD AdamW param groups (trainer.py:45-74 -> llrd_utils.get_param_groups) laid
+    over a flat parameter arena; the update is ONE fused kernel (merlin_adamw_step) with per-chunk
+    lr-multiplier / weight-decay tables, bf16 weights and state like the reference (builder.py:110-114,163).
+  * `training_step(batch)` — explicit forward + backward of MMGPTLlamaForCausalLM.forward
+    (llama_mmgpt.py:53-112) as a fixed schedule of kernel launches (no autograd graph): per decoder layer
+    7 forward and 13 backward kernels, activations kept in HBM (17 GB at S=4096 — no re-computation, the
+    reference needs gradient checkpointing, pretrain.sh:35).
+  * gradients are exchanged with bucketed NCCL all-reduces over slices of the flat gradient arena, launched
+    while backward is still running (engine/train/dp.py); north_star: data-parallel only.
+  * cosine schedule with warm-up ratio, gradient accumulation, global-norm clipping (HF defaults used by
+    pretrain.sh: warmup_ratio 0.01, max_grad_norm 1.0, adam betas (0.9, 0.95) — pretrain.sh:23-31).
+
+Scope of this round: the language model, lm_head, embeddings and the projector train; the vision tower
+runs frozen (`freeze_vision_tower=True`, a configuration the reference supports, arguments.py:11).
+"""
+from __future__ import annotations
+
+import math
+from dataclasses import dataclass
+from typing import Dict, List, Optional
+
+import torch
+
+from .... import ops
+from ....lib import EPI_RESIDUAL
+from ...utils.constants import IGNORE_INDEX
+from ...utils.llrd_utils import llm_lr_scale_func, param_hyper, vit_lr_scale_func
+from .arena import ParamArena
+from .dp import GradBucketReducer
+
+
+@dataclass
+class TrainingArguments:
+    """The subset of the reference's TrainingArguments the step loop consumes (arguments.py:39-58 + the
+    transformers.TrainingArguments fields set in pretrain.sh)."""
+    learning_rate: float = 2e-5
+    weight_decay: float = 0.05
+    adam_beta1: float = 0.9
+    adam_beta2: float = 0.95
+    adam_epsilon: float = 1e-8
+    max_grad_norm: float = 1.0
+    warmup_ratio: float = 0.01
+    max_steps: int = 1000
+    gradient_accumulation_steps: int = 1
+    llrd: bool = False
+    llm_llrd: bool = False
+    bucket_mb: int = 256
+
+
+def cosine_lr(step: int, base_lr: float, max_steps: int, warmup_ratio: float) -> float:
+    """transformers.get_cosine_schedule_with_warmup (lr_scheduler_type cosine, pretrain.sh:27)."""
+    warm = math.ceil(max_steps * warmup_ratio)
+    if step < warm:
+        return base_lr * step / max(1, warm)
+    progress = (step - warm) / max(1, max_steps - warm)
+    return base_lr * max(0.0, 0.5 * (1.0 + math.cos(math.pi * progress)))
+
+
+class MMGPTTrainer:
+    def __init__(self, model, args: TrainingArguments):
+        self.model, self.args = model, args
+        self.arena: Optional[ParamArena] = None
+        self.reducer: Optional[GradBucketReducer] = None
+        self.global_step = 0
+        self.micro_step = 0
+        self._f32: Dict[str, torch.Tensor] = {}
+        tower = getattr(model.get_model(), "vision_tower", None)
+        if tower is not None and any(p.requires_grad for p in tower.parameters()):
+            raise NotImplementedError("training the vision tower is not built yet: use freeze_vision_tower=True")
+        self.create_optimizer()
+
+    # ------------------------------------------------------------------ trainer.py:45-74
+    def create_optimizer(self):
+        a = self.args
+        scale = vit_lr_scale_func if a.llrd else (llm_lr_scale_func if a.llm_llrd else None)
+        named = self.model.named_parameters_reference(trainable_only=True)
+        self.arena = ParamArena(named, lambda n, s: param_hyper(n, s, scale, a.weight_decay))
+        self.names = [n for n, _ in named]
+        self.reducer = GradBucketReducer(self.arena.grads, bucket_elems=a.bucket_mb * 1024 * 1024 // 2)
+        dev = self.arena.params.device
+        self._sumsq = torch.zeros(1, dtype=torch.float32, device=dev)
+        # fp32 accumulators for 1-D gradients (norm weights, projector bias)
+        for n, p in named:
+            if p.dim() == 1:
+                self._f32[n] = torch.zeros(p.numel(), dtype=torch.float32, device=dev)
+        return self.arena
+
+    # ------------------------------------------------------------------ forward + backward
+    def _forward_backward(self, batch, accumulate: bool, grad_scale: float):
+        model = self.model
+        m, cfg, g = model.model, model.config, self.arena.grad
+        D, H, L = cfg.hidden_size, cfg.num_attention_heads, cfg.num_hidden_layers
+        dev = model.device
+        input_ids, labels, images = batch["input_ids"], batch["labels"], batch["images"]
+        am = batch.get("attention_mask")
+        B, S = input_ids.shape
+        M = B * S
+        seqlens = None
+        if am is not None:
+            lens = am.sum(-1)
+            if bool((lens != S).any()):
+                seqlens = lens.to(device=dev, dtype=torch.int32)
+
+        # ---- forward: vision (frozen tower) -> projector -> splice
+        tower, proj = m.vision_tower, m.projector
+        concat = torch.cat([im for im in images], dim=0)
+        n_img = concat.shape[0]
+        hidden_v = tower.encode(concat)
+        grid = tower.config.image_size // tower.config.patch_size
+        conv = hasattr(proj, "project") and tower.select_feature == "patch"
+        if conv:
+            col = ops.conv3x3_im2col(hidden_v, n_img, grid, proj.in_channels, proj.conv_stride, tower.tokens, 1)
+        else:
+            col = tower.feature_select(hidden_v, n_img).reshape(-1, hidden_v.shape[-1]).contiguous()
+        feats = ops.gemm(col, proj.weight, bias=proj.bias)
+        per_image = feats.shape[0] // n_img
+        ids_host = input_ids if not input_ids.is_cuda else input_ids.cpu()
+        model._validate_image_grammar(ids_host, images, per_image)
+        rows = [im.shape[0] * per_image for im in images]
+        offs = [sum(rows[:b]) for b in range(B)]
+        feat_offset = torch.tensor(offs, dtype=torch.int32).to(dev)
+        feat_limit = torch.tensor(rows[:B], dtype=torch.int32).to(dev)
+        ids_dev = input_ids.to(dev).contiguous()
+        labels_dev = labels.to(dev).contiguous()
+        x, _, rank = ops.embed_splice(ids_dev, m.embed_tokens, feats.contiguous(), model.im_patch_token, feat_offset,
+                                      feat_limit, return_rank=True)
+
+        cos, sin = m.rope_tables(S)
+        saved = []
+        for i in range(L):
+            x_in = x
+            xn1 = ops.rmsnorm(x_in, m.ln1_w[i], cfg.rms_norm_eps)
+            qkv = ops.gemm_qkv_rope(xn1, m.qkv_w[i], cos, sin, S)
+            att, lse = ops.flash_attn(qkv, B, S, H, 128, causal=True, seqlens=seqlens, return_lse=True)
+            x_mid = ops.gemm(att, m.o_w[i], residual=x_in, epilogue=EPI_RESIDUAL)
+            xn2 = ops.rmsnorm(x_mid, m.ln2_w[i], cfg.rms_norm_eps)
+            gu = ops.gemm(xn2, m.gate_up_w[i])
+            mid = ops.swiglu_fwd(gu)
+            x = ops.gemm(mid, m.down_w[i], residual=x_mid, epilogue=EPI_RESIDUAL)
+            saved.append((x_in, xn1, qkv, att, lse, x_mid, xn2, gu, mid))
+        x_final = x
+        hn = ops.rmsnorm(x_final, m.norm_w, cfg.rms_norm_eps)
+        logits = ops.gemm(hn, model.lm_head_w)
+
+        # ---- backward
+        loss, dlogits = ops.cross_entropy_with_grad(logits, labels_dev, B, S, IGNORE_INDEX, grad_scale)
+        acc = accumulate
+        ops.gemm_tn(dlogits, hn, out=g("lm_head.weight"), accumulate=acc)
+        dhn = ops.gemm_nt(dlogits, model.lm_head_w)
+        dx = ops.rmsnorm_bwd(x_final, m.norm_w, dhn, None, self._f32["model.norm.weight"], cfg.rms_norm_eps)
+        self._ready_after("model.norm.weight")
+        for i in reversed(range(L)):
+            x_in, xn1, qkv, att, lse, x_mid, xn2, gu, mid = saved[i]
+            p = f"model.layers.{i}."
+            dmid = ops.gemm_nt(dx, m.down_w[i])
+            ops.gemm_tn(dx, mid, out=g(p + "mlp.down_proj.weight"), accumulate=acc)
+            dgu = ops.swiglu_bwd(gu, dmid, out=gu)
+            ops.gemm_tn(dgu, xn2, out=g(p + "mlp.gate_up_proj.weight"), accumulate=acc)
+            dxn2 = ops.gemm_nt(dgu, m.gate_up_w[i])
+            dx_mid = ops.rmsnorm_bwd(x_mid, m.ln2_w[i], dxn2, dx, self._f32[p + "post_attention_layernorm.weight"],
+                                     cfg.rms_norm_eps)
+            datt = ops.gemm_nt(dx_mid, m.o_w[i])
+            ops.gemm_tn(dx_mid, att, out=g(p + "self_attn.o_proj.weight"), accumulate=acc)
+            dqkv = ops.flash_attn_bwd(qkv, att, datt, lse, B, S, H, 128, causal=True, seqlens=seqlens)
+            ops.rope_qk_inverse_inplace(dqkv, cos, sin, H, S)
+            ops.gemm_tn(dqkv, xn1, out=g(p + "self_attn.qkv_proj.weight"), accumulate=acc)
+            dxn1 = ops.gemm_nt(dqkv, m.qkv_w[i])
+            dx = ops.rmsnorm_bwd(x_in, m.ln1_w[i], dxn1, dx_mid, self._f32[p + "input_layernorm.weight"],
+                                 cfg.rms_norm_eps)
+            saved[i] = None
+            self._ready_after(p + "input_layernorm.weight")
+        # embeddings + projector
+        dtable = g("model.embed_tokens.weight") if "model.embed_tokens.weight" in self.arena.offsets else None
+        train_proj = "model.projector.projector.weight" in self.arena.offsets
+        dfeats = torch.zeros_like(feats) if train_proj else None
+        if dtable is not None and not acc:
+            dtable.zero_()
+        ops.embed_splice_bwd(ids_dev.view(-1), rank, dx, dtable, dfeats, cfg.vocab_size)
+        if train_proj:
+            ops.gemm_tn(dfeats.contiguous(), col, out=g("model.projector.projector.weight"), accumulate=acc)
+            ops.colsum_accumulate(dfeats, self._f32["model.projector.projector.bias"])
+        self._ready_after(self.names[-1])
+        return loss
+
+    def _ready_after(self, name: str):
+        """Gradients of every parameter up to and including `name` (arena order = backward completion
+        order) are final: on the last micro-step fold their fp32 side accumulators into the bf16 arena
+        and hand the finished range to the bucket reducer, which overlaps the all-reduce with the rest
+        of backward."""
+        if not self._last_micro:
+            return
+        idx = self.names.index(name)
+        for k in range(self._fold_ptr, idx + 1):
+            n = self.names[k]
+            if n in self._f32:
+                ops.f32_to_bf16(self._f32[n], self.arena.grad(n))
+                self._f32[n].zero_()
+        self._fold_ptr = max(self._fold_ptr, idx + 1)
+        _, end = self.arena.span([name])
+        self.reducer.ready(end)
+
+    # ------------------------------------------------------------------ public step API
+    def training_step(self, batch) -> torch.Tensor:
+        """One micro-batch forward/backward; on the last micro-step of an accumulation window also the
+        gradient all-reduce, clipping and the AdamW update.  Returns the (detached) loss."""
+        a = self.args
+        accumulate = self.micro_step % a.gradient_accumulation_steps != 0
+        self._last_micro = (self.micro_step + 1) % a.gradient_accumulation_steps == 0
+        world = self.reducer.world
+        grad_scale = 1.0 / (a.gradient_accumulation_steps * world)
+        if not accumulate:
+            self.reducer.start_step()
+        self._fold_ptr = 0
+        with torch.no_grad():
+            loss = self._forward_backward(batch, accumulate, grad_scale)
+        self.micro_step += 1
+        if self._last_micro:
+            self.reducer.finish()
+            self.optimizer_step()
+        return loss
+
+    def optimizer_step(self):
+        a, ar = self.args, self.arena
+        self.global_step += 1
+        lr = cosine_lr(self.global_step, a.learning_rate, a.max_steps, a.warmup_ratio)
+        ops.grad_sumsq(ar.grads, self._sumsq)
+        ops.adamw_step(ar.params, ar.grads, ar.exp_avg, ar.exp_avg_sq, ar.lr_mult, ar.weight_decay, ar.chunk, lr,
+                       a.adam_beta1, a.adam_beta2, a.adam_epsilon, self.global_step, 1.0, a.max_grad_norm, self._sumsq)
+        self.last_lr = lr
+
+    def grad_norm(self) -> float:
+        return float(self._sumsq.sqrt())
+
+    def train(self, batches, log_every: int = 1):
+        """Minimal loop with the reference's logging cadence (--logging_steps 1): loss, lr, tokens/s."""
+        import time
+        for step, batch in enumerate(batches):
+            t0 = time.perf_counter()
+            loss = self.training_step(batch)
+            if (step + 1) % log_every == 0:
+                torch.cuda.synchronize()
+                dt = time.perf_counter() - t0
+                toks = batch["input_ids"].numel()
+                print(f"step {self.global_step} loss {loss.item():.4f} lr {getattr(self, 'last_lr', 0):.3e} "
+                      f"tokens/s {toks / dt:.0f}", flush=True)

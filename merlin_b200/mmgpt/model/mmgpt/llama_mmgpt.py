@@ -363,6 +363,27 @@ class MMGPTLlamaForCausalLM(nn.Module, MMGPTMetaForCausalLM):
         return CausalLMOutputWithPast(loss=loss, logits=logits, past_key_values=cache, hidden_states=hs,
                                       attentions=None)
 
+    def named_parameters_reference(self, trainable_only: bool = True):
+        """(reference-style name, packed parameter) pairs in the order their gradients become final
+        during backward: lm_head, final norm, decoder layers last-to-first, embeddings, projector.
+        The name is the representative reference key used for the optimizer grouping rules
+        (llrd_utils.py): fused q|k|v / gate|up tensors share the group of their members."""
+        m = self.model
+        out = [("lm_head.weight", self.lm_head_w), ("model.norm.weight", m.norm_w)]
+        for i in reversed(range(self.config.num_hidden_layers)):
+            p = f"model.layers.{i}."
+            out += [(p + "mlp.down_proj.weight", m.down_w[i]), (p + "mlp.gate_up_proj.weight", m.gate_up_w[i]),
+                    (p + "post_attention_layernorm.weight", m.ln2_w[i]),
+                    (p + "self_attn.o_proj.weight", m.o_w[i]), (p + "self_attn.qkv_proj.weight", m.qkv_w[i]),
+                    (p + "input_layernorm.weight", m.ln1_w[i])]
+        out.append(("model.embed_tokens.weight", m.embed_tokens))
+        pj = getattr(m, "projector", None)
+        if pj is not None:
+            out += [("model.projector.projector.weight", pj.weight), ("model.projector.projector.bias", pj.bias)]
+        if trainable_only:
+            out = [(n, p) for n, p in out if p.requires_grad]
+        return out
+
     def _decoder_core(self, x, B, S, seqlens, cache, collect_hidden=False):
         """Device-only tail of forward: decoder stack + lm_head (kernel launches only, graph-capturable)."""
         hidden, all_hidden = self.model.forward_layers(x, B, S, seqlens, cache, collect_hidden)

@@ -246,7 +246,7 @@ def conv3x3_im2col(feat: torch.Tensor, n_img: int, grid: int, C: int, stride: in
 
 def embed_splice(input_ids: torch.Tensor, embed_table: torch.Tensor, image_features: Optional[torch.Tensor],
                  im_patch_token: int, feat_offset: Optional[torch.Tensor] = None,
-                 feat_limit: Optional[torch.Tensor] = None) -> tuple[torch.Tensor, torch.Tensor]:
+                 feat_limit: Optional[torch.Tensor] = None, return_rank: bool = False):
     """input_ids [B, S] int64 (CUDA) -> (inputs_embeds [B*S, D], counts [B] = #<im_patch> per sample)."""
     if input_ids.dtype != torch.int64 or not input_ids.is_contiguous() or input_ids.dim() != 2:
         raise ValueError("embed_splice: input_ids must be contiguous int64 [B, S]")
@@ -262,11 +262,13 @@ def embed_splice(input_ids: torch.Tensor, embed_table: torch.Tensor, image_featu
         if t is not None and (t.dtype != torch.int32 or t.numel() != B):
             raise ValueError("embed_splice: feat_offset / feat_limit must be int32 [B]")
     if B * S == 0:
-        return out, ws[B * S:]
+        return (out, ws[B * S:], ws[:B * S]) if return_rank else (out, ws[B * S:])
     check(_lib.load().merlin_embed_splice(_stream(), input_ids.data_ptr(), embed_table.data_ptr(),
                                           _ptr(image_features), out.data_ptr(), ws.data_ptr(), B, S, D, nfeat,
                                           _ptr(feat_offset), _ptr(feat_limit), V, im_patch_token),
           "merlin_embed_splice", 2)
+    if return_rank:  # per-token feature row (-1 for text tokens): what the backward scatter needs
+        return out, ws[B * S:], ws[:B * S]
     return out, ws[B * S:]
 
 

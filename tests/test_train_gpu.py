@@ -1,0 +1,100 @@
+"""GPU: the explicit forward/backward schedule of MMGPTTrainer against autograd through the fp32 oracle
+(the oracle's forward is pinned to the real reference, so its autograd gradients are the reference's),
+plus one optimizer step and a short loss-goes-down run.  Tolerance: cosine >= 0.999 and
+max|Δ| <= 5% of max|ref| per parameter tensor (bf16 activations and gradients vs fp32)."""
+import pytest
+import torch
+
+from helpers import build_product_model, load_golden
+from merlin_b200.mmgpt.engine.train.trainer import MMGPTTrainer, TrainingArguments
+from oracle import merlin_oracle as O
+
+pytestmark = pytest.mark.gpu
+DEV = "cuda"
+
+
+def oracle_grads(cfg, sd, batch):
+    leaves = {k: v.clone().requires_grad_(True) for k, v in sd.items()}
+    out = O.forward(leaves, cfg, batch["input_ids"], batch["attention_mask"], batch["labels"], batch["images"])
+    out["loss"].backward()
+    return out["loss"].detach(), {k: v.grad for k, v in leaves.items() if v.grad is not None}
+
+
+def unpack_grads(trainer, cfg):
+    """Arena gradients under the reference's parameter names."""
+    ar = trainer.arena
+    D, FF = cfg.hidden_size, cfg.intermediate_size
+    out = {}
+    for name in trainer.names:
+        g = ar.grad(name).float().cpu()
+        if name.endswith("self_attn.qkv_proj.weight"):
+            base = name[: -len("qkv_proj.weight")]
+            for j, n in enumerate("qkv"):
+                out[base + f"{n}_proj.weight"] = g[j * D:(j + 1) * D]
+        elif name.endswith("mlp.gate_up_proj.weight"):
+            base = name[: -len("gate_up_proj.weight")]
+            gu = g.view(FF // 128, 2, 128, D)
+            out[base + "gate_proj.weight"] = gu[:, 0].reshape(FF, D)
+            out[base + "up_proj.weight"] = gu[:, 1].reshape(FF, D)
+        elif name == "model.projector.projector.weight" and cfg.projector == "conv":
+            out[name] = g.view(D, 3, 3, cfg.vit_hidden).permute(0, 3, 1, 2)
+        else:
+            out[name] = g
+    return out
+
+
+@pytest.mark.parametrize("name", ["tiny_conv", "tiny_mlp", "tiny_pad"])
+def test_gradients_match_oracle_autograd(name):
+    g, cfg = load_golden(name)
+    sd = O.init_state_dict(cfg, seed=0)
+    model = build_product_model(cfg, sd)
+    for p in model.parameters():
+        p.requires_grad_(True)
+    for p in model.get_model().vision_tower.parameters():
+        p.requires_grad_(False)
+    trainer = MMGPTTrainer(model, TrainingArguments(max_grad_norm=0.0))
+    batch = {k: g[k] for k in ("input_ids", "labels", "attention_mask")}
+    batch["images"] = [im.to(DEV) for im in g["images"]]
+    trainer._last_micro = True
+    trainer._fold_ptr = 0
+    trainer.reducer.start_step()
+    with torch.no_grad():
+        loss = trainer._forward_backward(batch, accumulate=False, grad_scale=1.0)
+    ref_loss, ref = oracle_grads(cfg, sd, {**batch, "images": g["images"]})
+    assert abs(loss.item() - ref_loss.item()) <= 2e-3
+    mine = unpack_grads(trainer, cfg)
+    checked = 0
+    for k, gm in mine.items():
+        gr = ref[k]
+        if gr.abs().max() == 0:
+            assert gm.abs().max() == 0
+            continue
+        cos = torch.nn.functional.cosine_similarity(gm.flatten(), gr.flatten(), dim=0).item()
+        err = (gm - gr).abs().max().item() / gr.abs().max().item()
+        assert cos >= 0.999 and err <= 0.05, f"{k}: cos={cos:.5f} rel-max-err={err:.4f}"
+        checked += 1
+    assert checked >= 6 * cfg.num_layers + 4
+
+
+def test_training_steps_reduce_the_loss_and_respect_frozen_tower():
+    g, cfg = load_golden("tiny_conv")
+    sd = O.init_state_dict(cfg, seed=0)
+    model = build_product_model(cfg, sd)
+    for p in model.parameters():
+        p.requires_grad_(True)
+    tower = model.get_model().vision_tower
+    for p in tower.parameters():
+        p.requires_grad_(False)
+    before = tower.qkv_w[0].clone()
+    trainer = MMGPTTrainer(model, TrainingArguments(learning_rate=2e-3, warmup_ratio=0.0, max_steps=20,
+                                                   gradient_accumulation_steps=2))
+    batch = {k: g[k] for k in ("input_ids", "labels", "attention_mask")}
+    batch["images"] = [im.to(DEV) for im in g["images"]]
+    losses = [trainer.training_step(batch).item() for _ in range(12)]
+    assert trainer.global_step == 6 and trainer.micro_step == 12
+    assert losses[-1] < losses[0] - 0.5, losses
+    assert torch.equal(tower.qkv_w[0], before)
+    assert 0 < trainer.grad_norm() < 1e3
+    # the model keeps working for inference after its weights moved into the arena
+    out = model(input_ids=g["input_ids"].to(DEV), images=[im.to(DEV) for im in g["images"]], labels=g["labels"].to(DEV))
+    assert out.loss.item() < losses[0]
