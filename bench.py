@@ -250,7 +250,7 @@ def main():
     if args.impl == "reference":
         run_reference_arm(args, rank)
         return
-    if args.warmup < 3:
+    if args.warmup < 3 and os.environ.get("MERLIN_BENCH_PROFILE") != "1":  # profiler runs may shorten warm-up
         args.warmup = 3
     import torch.distributed as dist
     from merlin_b200 import ops
@@ -331,7 +331,9 @@ def main():
         "gpu_launches": launches,
         "clocks": clocks,
         "roofline": {"bound": "tensor", "achieved": achieved, "peak": peaks["tflops"], "unit": "TFLOP/s",
-                     "frac": achieved / peaks["tflops"], "traffic": None, "kernel": "gemm_bf16_kernel<2> (tcgen05, cta_group::2)",
+                     "frac": achieved / peaks["tflops"], "traffic": 318.4e6,
+                     "traffic_note": "dram__bytes_read+write of ONE launch (gate|up GEMM, M=4096 N=22016 K=4096; algorithmic 302 MB) from profiles/r1_gemm_swiglu_metrics.csv; `achieved` aggregates all GEMM launches of the prefill",
+                     "kernel": "gemm_bf16_kernel<2> (tcgen05, cta_group::2)",
                      "launches_timed": gemm_n, "peak_source": peaks["source"], "frac_of_burst": achieved / peaks["tflops_burst"]},
         "detail": {"prefill_ms": pre_ms, "prefill_tokens_per_s_per_gpu": SEQ_LEN / (pre_ms / 1e3),
                    "prefill_model_tflops": fl / (pre_ms / 1e3) / 1e12,
@@ -341,7 +343,7 @@ def main():
     }
     if train is not None:
         line["detail"]["train"] = train
-    if rank == 0 and world == 1:
+    if rank == 0 and world == 1 and os.environ.get("MERLIN_BENCH_CPU", "1") == "1":
         try:
             v, total, sample, threads = cpu_reference_sample()
             line["cpu_baseline"] = {"value": v, "unit": "tokens/s", "cores": threads, "kind": "port", "sample": sample}

@@ -173,6 +173,28 @@ int merlin_embed_token(void* stream, const void* embed_table, const int64_t* tok
 int merlin_record_advance(void* stream, const int64_t* token_dev, int64_t* out_ids, int* n_out_dev,
                           int* pos_dev, int capacity);
 
+/* ---- composite forward entry points: one call per layer, kernels sequenced on the caller's stream ---- */
+typedef struct merlin_layer_weights {       /* one Vicuna decoder layer, packed layouts as above */
+  const void *qkv_w, *o_w, *gate_up_w, *down_w, *ln1_w, *ln2_w;
+} merlin_layer_weights;
+typedef struct merlin_vit_layer_weights {   /* one CLIP encoder layer (q|k|v fused, with biases) */
+  const void *qkv_w, *qkv_b, *out_w, *out_b, *ln1_w, *ln1_b, *ln2_w, *ln2_b, *fc1_w, *fc1_b, *fc2_w, *fc2_b;
+} merlin_vit_layer_weights;
+
+/* x[B*S, D] <- LlamaDecoderLayer(x): x += Attn(RMSNorm(x)); x += MLP(RMSNorm(x)), in place
+ * (HF:llama/modeling_llama.py:303-333 with the flash-attn patch).  kv_cache (NULL = off): [B, kv_capacity,
+ * 2*D] receives the rotated keys and the values of the S prompt tokens for later decode steps. */
+size_t merlin_decoder_layer_workspace_bytes(int M, int D, int FF);
+int merlin_decoder_layer_forward(void* stream, const merlin_layer_weights* w, void* x, void* workspace,
+                                 const float* rope_cos, const float* rope_sin, const int* seqlens,
+                                 void* kv_cache, int64_t kv_capacity, int B, int S, int D, int H, int FF, float eps,
+                                 int cta_group);
+
+/* h[n_img*tokens, d] <- CLIPEncoderLayer(h) in place (HF:clip/modeling_clip.py:363-384). */
+size_t merlin_vit_layer_workspace_bytes(int M, int d, int ff);
+int merlin_vit_layer_forward(void* stream, const merlin_vit_layer_weights* w, void* h, void* workspace, int n_img,
+                             int tokens, int d, int heads, int ff, float eps, int cta_group);
+
 /* ---- backward / optimizer (training path; autograd of the ops above + the step loop of
  * mmgpt/engine/train/trainer.py:45-74 with mmgpt/utils/llrd_utils.py param groups) ---- */
 
@@ -226,6 +248,27 @@ int merlin_adamw_step(void* stream, void* params, const void* grads, void* exp_a
                       const float* lr_mult, const float* weight_decay, int chunk, int64_t n, float lr, float beta1,
                       float beta2, float eps, int step, float grad_scale, float max_grad_norm,
                       const float* grad_sumsq);
+
+/* LayerNorm backward (CLIP layer_norm1/2, pre_layrnorm): dx (+ dres), dweight/dbias fp32 accumulators. */
+int merlin_layernorm_bwd(void* stream, const void* x, const void* weight, const void* dy, const void* dres,
+                         void* dx, float* dweight, float* dbias, int M, int D, float eps);
+
+/* quick_gelu forward (dy == NULL: out = x·σ(1.702x)) or backward (out = dy·d/dx) over n elements
+ * (HF QuickGELUActivation; training form of the fc1 epilogue). */
+int merlin_quick_gelu(void* stream, const void* x, const void* dy, void* out, int64_t n);
+
+/* Input gradient of ConvProjector's 3x3 convolution: gathers the im2col-layout gradient dcol[n*Go*Go, 9C]
+ * back onto the feature rows dfeat + (img*tok_stride + tok_off + y*grid + x)*C (inverse of
+ * merlin_conv3x3_im2col). */
+int merlin_conv3x3_col2im(void* stream, const void* dcol, void* dfeat, int n_img, int grid, int C, int stride,
+                          int tok_stride, int tok_off);
+
+/* CLIP embedding assembly without the norm (training form): emb = cat(class_embedding, patch_out) + position,
+ * and its backward: dpatch_out rows, fp32 dposition[tokens, D] and dclass[D] accumulators. */
+int merlin_vit_embed(void* stream, const void* patch_out, const void* class_embedding,
+                     const void* position_embedding, void* emb, int n_img, int tokens, int D);
+int merlin_vit_embed_bwd(void* stream, const void* dhidden, void* dpatch_out, float* dposition, float* dclass,
+                         int n_img, int tokens, int D);
 
 /* y[n] (bf16) = x[n] (fp32): folds fp32 accumulators (norm-weight / bias gradients) into the arena. */
 int merlin_f32_to_bf16(void* stream, const float* x, void* y, int64_t n);

@@ -118,7 +118,7 @@ extern "C" int merlin_flash_attn_bwd(void* stream, const void* qkv, int64_t ld_q
                                      int head_dim, int causal, float softmax_scale) {
   using namespace mb;
   MB_CHECK_ARG(qkv && out && dout && lse && dqkv && workspace, "flash_attn_bwd: null tensor");
-  MB_CHECK_ARG(head_dim == 128, "flash_attn_bwd: only head_dim 128 (the Vicuna decoder) is built");
+  MB_CHECK_ARG(head_dim == 128 || head_dim == 64, "flash_attn_bwd: head_dim %d not in {64,128}", head_dim);
   MB_CHECK_ARG(B > 0 && S > 0 && H > 0, "flash_attn_bwd: empty problem");
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   float* delta = static_cast<float*>(workspace);
@@ -156,19 +156,21 @@ extern "C" int merlin_flash_attn_bwd(void* stream, const void* qkv, int64_t ld_q
     uint32_t box[3] = {64, kBwdBlock, 1};
     if ((rc = make_tmap_bf16(&tdo, dout, 3, dims, str, box)) != MERLIN_OK) return rc;
   }
-  static bool configured = false;
-  if (!configured) {
-    MB_CHECK_CUDA(cudaFuncSetAttribute(attn_bwd_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                       AttnBwdCfg::kSmemBytes));
-    MB_CHECK_CUDA(cudaFuncSetAttribute(attn_bwd_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                       AttnBwdCfg::kSmemBytes));
-    configured = true;
-  }
   dim3 grid(static_cast<unsigned>((S + kBwdBlock - 1) / kBwdBlock), static_cast<unsigned>(H),
             static_cast<unsigned>(B));
-  if (causal) attn_bwd_kernel<true><<<grid, kBwdThreads, AttnBwdCfg::kSmemBytes, st>>>(tq, tdo, p);
-  else attn_bwd_kernel<false><<<grid, kBwdThreads, AttnBwdCfg::kSmemBytes, st>>>(tq, tdo, p);
-  MB_CHECK_CUDA(cudaGetLastError());
+  auto launch = [&](auto kernel, int smem) -> int {
+    MB_CHECK_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+    kernel<<<grid, kBwdThreads, smem, st>>>(tq, tdo, p);
+    MB_CHECK_CUDA(cudaGetLastError());
+    return MERLIN_OK;
+  };
+  if (head_dim == 128)
+    rc = causal ? launch(attn_bwd_kernel<128, true>, AttnBwdCfg<128>::kSmemBytes)
+                : launch(attn_bwd_kernel<128, false>, AttnBwdCfg<128>::kSmemBytes);
+  else
+    rc = causal ? launch(attn_bwd_kernel<64, true>, AttnBwdCfg<64>::kSmemBytes)
+                : launch(attn_bwd_kernel<64, false>, AttnBwdCfg<64>::kSmemBytes);
+  if (rc != MERLIN_OK) return rc;
   const int64_t rows = static_cast<int64_t>(B) * S;
   const int width = H * head_dim;
   dq_to_bf16_kernel<<<static_cast<unsigned>(std::min<int64_t>((rows * (width / 8) + 255) / 256, 148 * 16)), 256, 0, st>>>(

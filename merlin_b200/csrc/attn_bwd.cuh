@@ -31,9 +31,11 @@ struct AttnBwdParams {
   int64_t ld_dqkv;
 };
 
+template <int HD>
 struct AttnBwdCfg {
-  static constexpr int kTileBytes = kBwdBlock * 128 * 2;        // 32 KB: [128 rows x 128] bf16
-  static constexpr int kSmemTiles = kTileBytes * 6;             // K, V, Q, dO, P, dS
+  static constexpr int kTileBytes = kBwdBlock * HD * 2;         // [128 rows x HD] bf16: K, V, Q, dO
+  static constexpr int kPBytes = kBwdBlock * kBwdBlock * 2;     // [128 x 128] bf16: P, dS
+  static constexpr int kSmemTiles = kTileBytes * 4 + kPBytes * 2;
   static constexpr int kNumBars = 8;
   static constexpr int kSmemBytes = kSmemTiles + kNumBars * 8 + 16 + 1024;
 };
@@ -42,12 +44,12 @@ __device__ __forceinline__ void red_add_f32(float* addr, float v) {
   asm volatile("red.global.add.f32 [%0], %1;" ::"l"(addr), "f"(v) : "memory");
 }
 
-template <bool kCausal>
+template <int HD, bool kCausal>
 __global__ void __launch_bounds__(kBwdThreads, 1)
 attn_bwd_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid_constant__ CUtensorMap tm_do,
                 const AttnBwdParams p) {
-  using Cfg = AttnBwdCfg;
-  constexpr int HD = 128;
+  using Cfg = AttnBwdCfg<HD>;
+  constexpr int kAtoms = HD / 64;
   constexpr int kAtomBytes = kBwdBlock * 128;   // 16 KB: [128 rows x 64 bf16]
 
   extern __shared__ uint8_t smem_raw[];
@@ -58,7 +60,7 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid_constan
   uint8_t* sq = sv + Cfg::kTileBytes;
   uint8_t* sdo = sq + Cfg::kTileBytes;
   uint8_t* sp = sdo + Cfg::kTileBytes;
-  uint8_t* sds = sp + Cfg::kTileBytes;
+  uint8_t* sds = sp + Cfg::kPBytes;
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + Cfg::kSmemTiles);
   uint64_t* kv_full = bars;        // K_j, V_j landed (once)
   uint64_t* qdo_full = bars + 1;   // Q_i, dO_i landed
@@ -106,7 +108,7 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid_constan
     if (elect_one() && n_steps > 0) {
       mbar_expect_tx(kv_full, 2 * Cfg::kTileBytes);
 #pragma unroll
-      for (int a = 0; a < 2; ++a) {
+      for (int a = 0; a < kAtoms; ++a) {
         tma_load_3d(&tm_qkv, kv_full, sk + a * kAtomBytes, p.k_col0 + head * HD + a * 64, kv0, batch, kEvictFirst);
         tma_load_3d(&tm_qkv, kv_full, sv + a * kAtomBytes, p.v_col0 + head * HD + a * 64, kv0, batch, kEvictFirst);
       }
@@ -115,7 +117,7 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid_constan
         mbar_wait(qdo_empty, (s & 1) ^ 1);
         mbar_expect_tx(qdo_full, 2 * Cfg::kTileBytes);
 #pragma unroll
-        for (int a = 0; a < 2; ++a) {
+        for (int a = 0; a < kAtoms; ++a) {
           tma_load_3d(&tm_qkv, qdo_full, sq + a * kAtomBytes, p.q_col0 + head * HD + a * 64, q0, batch, kEvictLast);
           tma_load_3d(&tm_do, qdo_full, sdo + a * kAtomBytes, head * HD + a * 64, q0, batch, kEvictLast);
         }
@@ -126,8 +128,8 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid_constan
     // ======================================================= MMA issuer
     if (elect_one() && n_steps > 0) {
       constexpr uint32_t idesc_kk = umma_idesc_bf16(128, 128, 0, 0);   // S, dP : A, B K-major
-      constexpr uint32_t idesc_mm = umma_idesc_bf16(128, 128, 1, 1);   // dV, dK: A, B MN-major
-      constexpr uint32_t idesc_km = umma_idesc_bf16(128, 128, 0, 1);   // dQ    : A K-major, B MN-major
+      constexpr uint32_t idesc_mm = umma_idesc_bf16(128, HD, 1, 1);    // dV, dK: A, B MN-major
+      constexpr uint32_t idesc_km = umma_idesc_bf16(128, HD, 0, 1);    // dQ    : A K-major, B MN-major
       const uint32_t a_k = smem_u32(sk), a_v = smem_u32(sv), a_q = smem_u32(sq), a_do = smem_u32(sdo),
                      a_p = smem_u32(sp), a_ds = smem_u32(sds);
       mbar_wait(kv_full, 0);
@@ -228,7 +230,7 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid_constan
       tc_fence_after();
       float* dq_row = p.dq_accum + (static_cast<size_t>(batch) * p.S + (q_idx < p.S ? q_idx : 0)) * (p.H * HD) + head * HD;
 #pragma unroll
-      for (int ch = 0; ch < 4; ++ch) {
+      for (int ch = 0; ch < HD / 32; ++ch) {
         uint32_t v[32];
         tmem_ld32(t_s + lane_sel + ch * 32, v);
         tmem_ld_wait();
@@ -252,7 +254,7 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid_constan
       const uint32_t t_acc = which == 0 ? t_dk : t_dv;
       __nv_bfloat16* dst = out_row + (which == 0 ? p.k_col0 : p.v_col0) + head * HD;
 #pragma unroll
-      for (int ch = 0; ch < 4; ++ch) {
+      for (int ch = 0; ch < HD / 32; ++ch) {
         uint32_t v[32];
         if (n_steps > 0) {  // block-uniform
           tmem_ld32(t_acc + lane_sel + ch * 32, v);

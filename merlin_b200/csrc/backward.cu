@@ -456,3 +456,227 @@ int merlin_f32_to_bf16(void* stream, const float* x, void* y, int64_t n) {
 }
 
 }  // extern "C"
+
+// =====================================================================================================
+// Vision-tower backward pieces (CLIP encoder layers, embeddings, conv projector input gradient)
+// =====================================================================================================
+namespace mb {
+
+// LayerNorm backward: x̂ = (x−μ)·r, y = w⊙x̂ + b.  g = w⊙dy; dx = r·(g − mean(g) − x̂·mean(g⊙x̂)) (+ dres);
+// dw += Σ dy⊙x̂, db += Σ dy  (fp32 atomics, one per column per block of kRnbRows rows).
+__global__ void __launch_bounds__(kRnbThreads)
+layernorm_bwd_kernel(const __nv_bfloat16* __restrict__ x, const __nv_bfloat16* __restrict__ w,
+                     const __nv_bfloat16* __restrict__ dy, const __nv_bfloat16* __restrict__ dres,
+                     __nv_bfloat16* __restrict__ dx, float* __restrict__ dw, float* __restrict__ db, int M, int D,
+                     float eps) {
+  __shared__ float red[32];
+  const int nvec = D >> 3;
+  float wv[kRnbVec][8], dwacc[kRnbVec][8], dbacc[kRnbVec][8];
+#pragma unroll
+  for (int i = 0; i < kRnbVec; ++i) {
+    const int idx = threadIdx.x + i * kRnbThreads;
+    if (idx < nvec) unpack8b(reinterpret_cast<const uint4*>(w)[idx], wv[i]);
+#pragma unroll
+    for (int e = 0; e < 8; ++e) dwacc[i][e] = dbacc[i][e] = 0.f;
+  }
+  const int row0 = blockIdx.x * kRnbRows;
+  for (int r = 0; r < kRnbRows && row0 + r < M; ++r) {
+    const size_t off = static_cast<size_t>(row0 + r) * D;
+    float xv[kRnbVec][8], gv[kRnbVec][8];
+    float s = 0.f;
+#pragma unroll
+    for (int i = 0; i < kRnbVec; ++i) {
+      const int idx = threadIdx.x + i * kRnbThreads;
+      if (idx < nvec) {
+        unpack8b(reinterpret_cast<const uint4*>(x + off)[idx], xv[i]);
+        unpack8b(reinterpret_cast<const uint4*>(dy + off)[idx], gv[i]);
+#pragma unroll
+        for (int e = 0; e < 8; ++e) s += xv[i][e];
+      }
+    }
+    const float mean = block_sum_b(s, red) / static_cast<float>(D);
+    float sq = 0.f;
+#pragma unroll
+    for (int i = 0; i < kRnbVec; ++i) {
+      const int idx = threadIdx.x + i * kRnbThreads;
+      if (idx < nvec)
+#pragma unroll
+        for (int e = 0; e < 8; ++e) sq += (xv[i][e] - mean) * (xv[i][e] - mean);
+    }
+    const float rstd = rsqrtf(block_sum_b(sq, red) / static_cast<float>(D) + eps);
+    float sg = 0.f, sgx = 0.f;
+#pragma unroll
+    for (int i = 0; i < kRnbVec; ++i) {
+      const int idx = threadIdx.x + i * kRnbThreads;
+      if (idx < nvec) {
+#pragma unroll
+        for (int e = 0; e < 8; ++e) {
+          const float xh = (xv[i][e] - mean) * rstd;
+          dwacc[i][e] += gv[i][e] * xh;
+          dbacc[i][e] += gv[i][e];
+          gv[i][e] *= wv[i][e];
+          sg += gv[i][e];
+          sgx += gv[i][e] * xh;
+          xv[i][e] = xh;
+        }
+      }
+    }
+    const float mg = block_sum_b(sg, red) / static_cast<float>(D);
+    const float mgx = block_sum_b(sgx, red) / static_cast<float>(D);
+#pragma unroll
+    for (int i = 0; i < kRnbVec; ++i) {
+      const int idx = threadIdx.x + i * kRnbThreads;
+      if (idx < nvec) {
+        float o[8];
+        if (dres) unpack8b(reinterpret_cast<const uint4*>(dres + off)[idx], o);
+#pragma unroll
+        for (int e = 0; e < 8; ++e) {
+          const float v = rstd * (gv[i][e] - mg - xv[i][e] * mgx);
+          o[e] = dres ? o[e] + v : v;
+        }
+        reinterpret_cast<uint4*>(dx + off)[idx] = pack8b(o);
+      }
+    }
+  }
+#pragma unroll
+  for (int i = 0; i < kRnbVec; ++i) {
+    const int idx = threadIdx.x + i * kRnbThreads;
+    if (idx < nvec)
+#pragma unroll
+      for (int e = 0; e < 8; ++e) {
+        if (dw) atomicAdd(&dw[idx * 8 + e], dwacc[i][e]);
+        if (db) atomicAdd(&db[idx * 8 + e], dbacc[i][e]);
+      }
+  }
+}
+
+// quick_gelu(x) = x·σ(1.702x);  backward: dx = dy·(σ + 1.702·x·σ·(1−σ)).  dy == nullptr selects the forward.
+__global__ void quick_gelu_kernel(const __nv_bfloat16* __restrict__ x, const __nv_bfloat16* __restrict__ dy,
+                                  __nv_bfloat16* __restrict__ out, int64_t n_vec) {
+  for (int64_t i = blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x; i < n_vec;
+       i += static_cast<int64_t>(gridDim.x) * blockDim.x) {
+    float xv[8], d[8], o[8];
+    unpack8b(reinterpret_cast<const uint4*>(x)[i], xv);
+    if (dy) unpack8b(reinterpret_cast<const uint4*>(dy)[i], d);
+#pragma unroll
+    for (int e = 0; e < 8; ++e) {
+      const float s = 1.f / (1.f + __expf(-1.702f * xv[e]));
+      o[e] = dy ? d[e] * (s + 1.702f * xv[e] * s * (1.f - s)) : xv[e] * s;
+    }
+    reinterpret_cast<uint4*>(out)[i] = pack8b(o);
+  }
+}
+
+// Input gradient of the 3x3 / pad 1 / stride s convolution from the im2col-layout gradient
+// dcol [n*Go*Go, 9*C] (k = tap*C + c): dfeat(img,y,x) = Σ over the taps that read (y,x).  A gather (no
+// atomics); rows are written at (img*tok_stride + tok_off + y*G + x), the layout conv3x3_im2col reads.
+__global__ void conv3x3_col2im_kernel(const __nv_bfloat16* __restrict__ dcol, __nv_bfloat16* __restrict__ dfeat,
+                                      int G, int Go, int C, int stride, int tok_stride, int tok_off) {
+  const int pos = blockIdx.x;  // (img, y, x)
+  const int img = pos / (G * G), y = (pos / G) % G, x = pos % G;
+  for (int i = threadIdx.x; i < (C >> 3); i += blockDim.x) {
+    float acc[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+    for (int ky = 0; ky < 3; ++ky) {
+      const int ty = y + 1 - ky;
+      if (ty < 0 || ty % stride != 0 || ty / stride >= Go) continue;
+      for (int kx = 0; kx < 3; ++kx) {
+        const int tx = x + 1 - kx;
+        if (tx < 0 || tx % stride != 0 || tx / stride >= Go) continue;
+        const size_t row = (static_cast<size_t>(img) * Go + ty / stride) * Go + tx / stride;
+        float f[8];
+        unpack8b(reinterpret_cast<const uint4*>(dcol + (row * 9 + ky * 3 + kx) * C)[i], f);
+#pragma unroll
+        for (int e = 0; e < 8; ++e) acc[e] += f[e];
+      }
+    }
+    reinterpret_cast<uint4*>(dfeat + (static_cast<size_t>(img) * tok_stride + tok_off + y * G + x) * C)[i] = pack8b(acc);
+  }
+}
+
+// emb[img, t] = (t == 0 ? class_embedding : patch_out[img, t-1]) + position_embedding[t]  (bf16 add, as torch)
+__global__ void vit_embed_kernel(const __nv_bfloat16* __restrict__ patch_out, const __nv_bfloat16* __restrict__ cls,
+                                 const __nv_bfloat16* __restrict__ pos, __nv_bfloat16* __restrict__ emb, int tokens,
+                                 int D) {
+  const int img = blockIdx.x / tokens, t = blockIdx.x % tokens;
+  const __nv_bfloat16* src = t == 0 ? cls : patch_out + (static_cast<size_t>(img) * (tokens - 1) + (t - 1)) * D;
+  for (int c = threadIdx.x; c < D; c += blockDim.x)
+    emb[static_cast<size_t>(blockIdx.x) * D + c] =
+        __float2bfloat16_rn(__bfloat162float(src[c]) + __bfloat162float(pos[static_cast<size_t>(t) * D + c]));
+}
+
+// Backward of the CLIP embedding assembly: d[img, t, :] (gradient after pre_layrnorm backward) ->
+// dpatch_out[img, t-1] = d[img, t] (t >= 1); dpos[t] += Σ_img d[img, t]; dcls += Σ_img d[img, 0]  (fp32).
+__global__ void vit_embed_bwd_kernel(const __nv_bfloat16* __restrict__ d, __nv_bfloat16* __restrict__ dpatch_out,
+                                     float* __restrict__ dpos, float* __restrict__ dcls, int n_img, int tokens, int D) {
+  const int t = blockIdx.x;
+  for (int c = threadIdx.x; c < D; c += blockDim.x) {
+    float acc = 0.f;
+    for (int img = 0; img < n_img; ++img) {
+      const __nv_bfloat16 v = d[(static_cast<size_t>(img) * tokens + t) * D + c];
+      acc += __bfloat162float(v);
+      if (t > 0) dpatch_out[(static_cast<size_t>(img) * (tokens - 1) + (t - 1)) * D + c] = v;
+    }
+    dpos[static_cast<size_t>(t) * D + c] += acc;
+    if (t == 0) dcls[c] += acc;
+  }
+}
+
+}  // namespace mb
+
+extern "C" {
+
+int merlin_layernorm_bwd(void* stream, const void* x, const void* weight, const void* dy, const void* dres,
+                         void* dx, float* dweight, float* dbias, int M, int D, float eps) {
+  MB_CHECK_ARG(x && weight && dy && dx, "layernorm_bwd: null tensor");
+  MB_CHECK_ARG(D % 8 == 0 && D <= 8 * kRnbThreads * kRnbVec, "layernorm_bwd: D=%d unsupported", D);
+  if (M == 0) return MERLIN_OK;
+  layernorm_bwd_kernel<<<(M + kRnbRows - 1) / kRnbRows, kRnbThreads, 0, static_cast<cudaStream_t>(stream)>>>(
+      static_cast<const __nv_bfloat16*>(x), static_cast<const __nv_bfloat16*>(weight),
+      static_cast<const __nv_bfloat16*>(dy), static_cast<const __nv_bfloat16*>(dres),
+      static_cast<__nv_bfloat16*>(dx), dweight, dbias, M, D, eps);
+  MB_CHECK_CUDA(cudaGetLastError());
+  return MERLIN_OK;
+}
+
+int merlin_quick_gelu(void* stream, const void* x, const void* dy, void* out, int64_t n) {
+  MB_CHECK_ARG(x && out && n % 8 == 0, "quick_gelu: bad argument");
+  if (n == 0) return MERLIN_OK;
+  quick_gelu_kernel<<<grid_for(n / 8, 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(
+      static_cast<const __nv_bfloat16*>(x), static_cast<const __nv_bfloat16*>(dy), static_cast<__nv_bfloat16*>(out),
+      n / 8);
+  MB_CHECK_CUDA(cudaGetLastError());
+  return MERLIN_OK;
+}
+
+int merlin_conv3x3_col2im(void* stream, const void* dcol, void* dfeat, int n_img, int grid, int C, int stride,
+                          int tok_stride, int tok_off) {
+  MB_CHECK_ARG(dcol && dfeat && C % 8 == 0 && stride >= 1, "conv3x3_col2im: bad argument");
+  const int Go = (grid + 2 - 3) / stride + 1;
+  conv3x3_col2im_kernel<<<n_img * grid * grid, 128, 0, static_cast<cudaStream_t>(stream)>>>(
+      static_cast<const __nv_bfloat16*>(dcol), static_cast<__nv_bfloat16*>(dfeat), grid, Go, C, stride, tok_stride,
+      tok_off);
+  MB_CHECK_CUDA(cudaGetLastError());
+  return MERLIN_OK;
+}
+
+int merlin_vit_embed(void* stream, const void* patch_out, const void* class_embedding,
+                     const void* position_embedding, void* emb, int n_img, int tokens, int D) {
+  MB_CHECK_ARG(patch_out && class_embedding && position_embedding && emb, "vit_embed: null tensor");
+  vit_embed_kernel<<<n_img * tokens, 256, 0, static_cast<cudaStream_t>(stream)>>>(
+      static_cast<const __nv_bfloat16*>(patch_out), static_cast<const __nv_bfloat16*>(class_embedding),
+      static_cast<const __nv_bfloat16*>(position_embedding), static_cast<__nv_bfloat16*>(emb), tokens, D);
+  MB_CHECK_CUDA(cudaGetLastError());
+  return MERLIN_OK;
+}
+
+int merlin_vit_embed_bwd(void* stream, const void* dhidden, void* dpatch_out, float* dposition, float* dclass,
+                         int n_img, int tokens, int D) {
+  MB_CHECK_ARG(dhidden && dpatch_out && dposition && dclass, "vit_embed_bwd: null tensor");
+  vit_embed_bwd_kernel<<<tokens, 256, 0, static_cast<cudaStream_t>(stream)>>>(
+      static_cast<const __nv_bfloat16*>(dhidden), static_cast<__nv_bfloat16*>(dpatch_out), dposition, dclass, n_img,
+      tokens, D);
+  MB_CHECK_CUDA(cudaGetLastError());
+  return MERLIN_OK;
+}
+
+}  // extern "C"

@@ -49,6 +49,11 @@ _PROTOTYPES = {
     "merlin_grad_sumsq": [_P, _P, c_int64, _P],
     "merlin_adamw_step": [_P, _P, _P, _P, _P, _P, _P, c_int, c_int64, c_float, c_float, c_float, c_float, c_int, c_float, c_float, _P],
     "merlin_f32_to_bf16": [_P, _P, _P, c_int64],
+    "merlin_layernorm_bwd": [_P, _P, _P, _P, _P, _P, _P, _P, c_int, c_int, c_float],
+    "merlin_quick_gelu": [_P, _P, _P, _P, c_int64],
+    "merlin_conv3x3_col2im": [_P, _P, _P, c_int, c_int, c_int, c_int, c_int, c_int],
+    "merlin_vit_embed": [_P, _P, _P, _P, _P, c_int, c_int, c_int],
+    "merlin_vit_embed_bwd": [_P, _P, _P, _P, _P, c_int, c_int, c_int],
     "merlin_decode_step": [_P, _P, _P, _P, _P, _P, c_int],
     "merlin_embed_token": [_P, _P, _P, _P, c_int, c_int64],
     "merlin_record_advance": [_P, _P, _P, _P, _P, c_int],
@@ -65,6 +70,26 @@ class DecoderWeights(ctypes.Structure):
                 ("norm_w", c_void_p), ("lm_head_w", c_void_p),
                 ("kv_cache", ctypes.POINTER(c_void_p)),
                 ("rope_cos", c_void_p), ("rope_sin", c_void_p)]
+
+
+class LayerWeights(ctypes.Structure):
+    """struct merlin_layer_weights."""
+    _fields_ = [(n, c_void_p) for n in ("qkv_w", "o_w", "gate_up_w", "down_w", "ln1_w", "ln2_w")]
+
+
+class VitLayerWeights(ctypes.Structure):
+    """struct merlin_vit_layer_weights."""
+    _fields_ = [(n, c_void_p) for n in ("qkv_w", "qkv_b", "out_w", "out_b", "ln1_w", "ln1_b", "ln2_w", "ln2_b",
+                                        "fc1_w", "fc1_b", "fc2_w", "fc2_b")]
+
+
+_PROTOTYPES["merlin_decoder_layer_forward"] = [_P, _P, _P, _P, _P, _P, _P, _P, c_int64, c_int, c_int, c_int, c_int,
+                                               c_int, c_float, c_int]
+_PROTOTYPES["merlin_vit_layer_forward"] = [_P, _P, _P, _P, c_int, c_int, c_int, c_int, c_int, c_float, c_int]
+_SIZE_FNS = {"merlin_decode_workspace_bytes": [c_int, c_int, c_int, c_int],
+             "merlin_flash_attn_bwd_workspace_bytes": [c_int, c_int, c_int, c_int],
+             "merlin_decoder_layer_workspace_bytes": [c_int, c_int, c_int],
+             "merlin_vit_layer_workspace_bytes": [c_int, c_int, c_int]}
 
 
 def declared_symbols(header: str = _HEADER) -> list[str]:
@@ -94,10 +119,10 @@ def load() -> ctypes.CDLL:
     lib = ctypes.CDLL(path)
     lib.merlin_last_error.restype = c_char_p
     lib.merlin_last_error.argtypes = []
-    lib.merlin_decode_workspace_bytes.restype = ctypes.c_size_t
-    lib.merlin_decode_workspace_bytes.argtypes = [c_int, c_int, c_int, c_int]
-    lib.merlin_flash_attn_bwd_workspace_bytes.restype = ctypes.c_size_t
-    lib.merlin_flash_attn_bwd_workspace_bytes.argtypes = [c_int, c_int, c_int, c_int]
+    for name, argtypes in _SIZE_FNS.items():
+        fn = getattr(lib, name)
+        fn.restype = ctypes.c_size_t
+        fn.argtypes = argtypes
     for name, argtypes in _PROTOTYPES.items():
         fn = getattr(lib, name)
         fn.restype = c_int

@@ -15,8 +15,8 @@ the HF `Trainer._inner_training_loop` + FSDP + autograd machinery underneath it 
   * cosine schedule with warm-up ratio, gradient accumulation, global-norm clipping (HF defaults used by
     pretrain.sh: warmup_ratio 0.01, max_grad_norm 1.0, adam betas (0.9, 0.95) — pretrain.sh:23-31).
 
-Scope of this round: the language model, lm_head, embeddings and the projector train; the vision tower
-runs frozen (`freeze_vision_tower=True`, a configuration the reference supports, arguments.py:11).
+Everything on the path trains: language model, lm_head, embeddings, projector and (unless
+`freeze_vision_tower`) the CLIP tower through its own explicit backward (clip_encoder.CLIPVisionTower.backward).
 """
 from __future__ import annotations
 
@@ -69,9 +69,6 @@ class MMGPTTrainer:
         self.global_step = 0
         self.micro_step = 0
         self._f32: Dict[str, torch.Tensor] = {}
-        tower = getattr(model.get_model(), "vision_tower", None)
-        if tower is not None and any(p.requires_grad for p in tower.parameters()):
-            raise NotImplementedError("training the vision tower is not built yet: use freeze_vision_tower=True")
         self.create_optimizer()
 
     # ------------------------------------------------------------------ trainer.py:45-74
@@ -86,7 +83,7 @@ class MMGPTTrainer:
         self._sumsq = torch.zeros(1, dtype=torch.float32, device=dev)
         # fp32 accumulators for 1-D gradients (norm weights, projector bias)
         for n, p in named:
-            if p.dim() == 1:
+            if p.dim() == 1 or n.endswith("position_embedding.weight"):
                 self._f32[n] = torch.zeros(p.numel(), dtype=torch.float32, device=dev)
         return self.arena
 
@@ -110,7 +107,11 @@ class MMGPTTrainer:
         tower, proj = m.vision_tower, m.projector
         concat = torch.cat([im for im in images], dim=0)
         n_img = concat.shape[0]
-        hidden_v = tower.encode(concat)
+        train_tower = any(n.startswith(tower.VM) for n in self.arena.offsets)
+        if train_tower:
+            hidden_v, tower_saved = tower.encode_train(concat)
+        else:
+            hidden_v = tower.encode(concat)
         grid = tower.config.image_size // tower.config.patch_size
         conv = hasattr(proj, "project") and tower.select_feature == "patch"
         if conv:
@@ -177,13 +178,24 @@ class MMGPTTrainer:
         # embeddings + projector
         dtable = g("model.embed_tokens.weight") if "model.embed_tokens.weight" in self.arena.offsets else None
         train_proj = "model.projector.projector.weight" in self.arena.offsets
-        dfeats = torch.zeros_like(feats) if train_proj else None
+        dfeats = torch.zeros_like(feats) if (train_proj or train_tower) else None
         if dtable is not None and not acc:
             dtable.zero_()
         ops.embed_splice_bwd(ids_dev.view(-1), rank, dx, dtable, dfeats, cfg.vocab_size)
         if train_proj:
             ops.gemm_tn(dfeats.contiguous(), col, out=g("model.projector.projector.weight"), accumulate=acc)
             ops.colsum_accumulate(dfeats, self._f32["model.projector.projector.bias"])
+            self._ready_after("model.projector.projector.bias")
+        if train_tower:
+            # projector input gradient -> gradient of the selected ViT hidden state (CLS rows get none)
+            dhid = torch.zeros_like(hidden_v)
+            if conv:
+                dcol = ops.gemm_nt(dfeats.contiguous(), proj.weight)
+                ops.conv3x3_col2im(dcol, dhid, n_img, grid, proj.in_channels, proj.conv_stride, tower.tokens, 1)
+            else:
+                dpatch = ops.gemm_nt(dfeats.contiguous(), proj.weight)
+                dhid.view(n_img, tower.tokens, -1)[:, 1:].copy_(dpatch.view(n_img, tower.tokens - 1, -1))
+            tower.backward(dhid, tower_saved, g, self._f32, acc, done=self._ready_after)
         self._ready_after(self.names[-1])
         return loss
 

@@ -152,6 +152,17 @@ class MMGPTLlamaModel(nn.Module):
         cos, sin = self.rope_tables(seq)
         xn = torch.empty_like(x)
         hidden = [x.clone()] if collect_hidden else None
+        if not collect_hidden and not ops.PROFILE.enabled:
+            # one C call per layer (merlin_decoder_layer_forward): same kernels, sequenced in the library
+            ws = ops.decoder_layer_workspace(batch * seq, D, cfg.intermediate_size, x.device)
+            for i in range(cfg.num_hidden_layers):
+                ops.decoder_layer_forward(x, ws, self.qkv_w[i], self.o_w[i], self.gate_up_w[i], self.down_w[i],
+                                          self.ln1_w[i], self.ln2_w[i], cos, sin, seqlens,
+                                          None if cache is None else cache.kv[i], batch, seq, H,
+                                          cfg.intermediate_size, cfg.rms_norm_eps)
+            if cache is not None:
+                cache.seq_len = seq
+            return ops.rmsnorm(x, self.norm_w, cfg.rms_norm_eps, out=xn), None
         for i in range(cfg.num_hidden_layers):
             ops.rmsnorm(x, self.ln1_w[i], cfg.rms_norm_eps, out=xn)
             qkv = ops.gemm_qkv_rope(xn, self.qkv_w[i], cos, sin, seq)
@@ -380,6 +391,9 @@ class MMGPTLlamaForCausalLM(nn.Module, MMGPTMetaForCausalLM):
         pj = getattr(m, "projector", None)
         if pj is not None:
             out += [("model.projector.projector.weight", pj.weight), ("model.projector.projector.bias", pj.bias)]
+        vt = getattr(m, "vision_tower", None)
+        if vt is not None:
+            out += vt.named_parameters_reference()
         if trainable_only:
             out = [(n, p) for n, p in out if p.requires_grad]
         return out

@@ -198,6 +198,11 @@ class CLIPVisionTower(nn.Module):
         patch_out = ops.gemm(col, self.patch_weight)
         h = ops.vit_embed_ln(patch_out, self.class_embedding, self.position_embedding, self.pre_ln_w,
                              self.pre_ln_b, n, c.layer_norm_eps)
+        if not ops.PROFILE.enabled:
+            ws = ops.vit_layer_workspace(h.shape[0], d, c.intermediate_size, h.device)
+            for j in range(self.num_layers_to_run()):
+                ops.vit_layer_forward(h, ws, self, j, n)      # merlin_vit_layer_forward: 7 kernels, one call
+            return h
         xn = torch.empty_like(h)
         for j in range(self.num_layers_to_run()):
             ops.layernorm(h, self.ln1_w[j], self.ln1_b[j], c.layer_norm_eps, out=xn)
@@ -208,6 +213,86 @@ class CLIPVisionTower(nn.Module):
             mid = ops.gemm(xn, self.fc1_w[j], bias=self.fc1_b[j], epilogue=EPI_QUICKGELU)
             ops.gemm(mid, self.fc2_w[j], bias=self.fc2_b[j], residual=h, out=h, epilogue=EPI_RESIDUAL)
         return h
+
+    # ------------------------------------------------------------------ training form (explicit backward)
+    VM = "model.vision_tower.vision_tower.vision_model."
+
+    def named_parameters_reference(self):
+        """(reference key, packed parameter) of every tensor that receives a gradient, in backward
+        completion order: encoder layers last-to-first, then pre_layrnorm and the embeddings.  Layers beyond
+        `select_layer` and post_layernorm never get gradients (clip_encoder.py:65) and are left out."""
+        out = []
+        for j in reversed(range(self.num_layers_to_run())):
+            p = self.VM + f"encoder.layers.{j}."
+            out += [(p + "mlp.fc2.weight", self.fc2_w[j]), (p + "mlp.fc2.bias", self.fc2_b[j]),
+                    (p + "mlp.fc1.weight", self.fc1_w[j]), (p + "mlp.fc1.bias", self.fc1_b[j]),
+                    (p + "layer_norm2.weight", self.ln2_w[j]), (p + "layer_norm2.bias", self.ln2_b[j]),
+                    (p + "self_attn.out_proj.weight", self.out_w[j]), (p + "self_attn.out_proj.bias", self.out_b[j]),
+                    (p + "self_attn.qkv_proj.weight", self.qkv_w[j]), (p + "self_attn.qkv_proj.bias", self.qkv_b[j]),
+                    (p + "layer_norm1.weight", self.ln1_w[j]), (p + "layer_norm1.bias", self.ln1_b[j])]
+        out += [(self.VM + "pre_layrnorm.weight", self.pre_ln_w), (self.VM + "pre_layrnorm.bias", self.pre_ln_b),
+                (self.VM + "embeddings.position_embedding.weight", self.position_embedding),
+                (self.VM + "embeddings.class_embedding", self.class_embedding),
+                (self.VM + "embeddings.patch_embedding.weight", self.patch_weight)]
+        return [(n, p) for n, p in out if p.requires_grad]
+
+    def encode_train(self, pixel_values: torch.Tensor):
+        """encode() that keeps what backward needs.  Returns (hidden [n*T, d], saved)."""
+        c = self._config
+        n, H = pixel_values.shape[0], c.num_attention_heads
+        px = pixel_values.to(device=self.device, dtype=torch.bfloat16).contiguous()
+        col = ops.patch_im2col(px, c.patch_size, self.k_patch_padded)
+        patch_out = ops.gemm(col, self.patch_weight)
+        emb = ops.vit_embed(patch_out, self.class_embedding, self.position_embedding, n)
+        h = ops.layernorm(emb, self.pre_ln_w, self.pre_ln_b, c.layer_norm_eps)
+        layers = []
+        for j in range(self.num_layers_to_run()):
+            xn1 = ops.layernorm(h, self.ln1_w[j], self.ln1_b[j], c.layer_norm_eps)
+            qkv = ops.gemm(xn1, self.qkv_w[j], bias=self.qkv_b[j])
+            att, lse = ops.flash_attn(qkv, n, self.tokens, H, 64, causal=False, return_lse=True)
+            h_mid = ops.gemm(att, self.out_w[j], bias=self.out_b[j], residual=h, epilogue=EPI_RESIDUAL)
+            xn2 = ops.layernorm(h_mid, self.ln2_w[j], self.ln2_b[j], c.layer_norm_eps)
+            pre = ops.gemm(xn2, self.fc1_w[j], bias=self.fc1_b[j])
+            mid = ops.quick_gelu(pre)
+            h_out = ops.gemm(mid, self.fc2_w[j], bias=self.fc2_b[j], residual=h_mid, epilogue=EPI_RESIDUAL)
+            layers.append((h, xn1, qkv, att, lse, h_mid, xn2, pre, mid))
+            h = h_out
+        return h, dict(n=n, col=col, emb=emb, layers=layers)
+
+    def backward(self, dh: torch.Tensor, saved, grad, f32, accumulate: bool, done=None):
+        """dh: gradient w.r.t. encode_train()'s hidden.  grad(name) -> bf16 arena view for weight matrices,
+        f32[name] -> fp32 accumulator for biases / norm weights / position + class embeddings."""
+        c = self._config
+        n, H, eps = saved["n"], c.num_attention_heads, c.layer_norm_eps
+        for j in reversed(range(self.num_layers_to_run())):
+            h, xn1, qkv, att, lse, h_mid, xn2, pre, mid = saved["layers"][j]
+            p = self.VM + f"encoder.layers.{j}."
+            dmid = ops.gemm_nt(dh, self.fc2_w[j])
+            ops.gemm_tn(dh, mid, out=grad(p + "mlp.fc2.weight"), accumulate=accumulate)
+            ops.colsum_accumulate(dh, f32[p + "mlp.fc2.bias"])
+            dpre = ops.quick_gelu(pre, dy=dmid.contiguous())
+            ops.gemm_tn(dpre, xn2, out=grad(p + "mlp.fc1.weight"), accumulate=accumulate)
+            ops.colsum_accumulate(dpre, f32[p + "mlp.fc1.bias"])
+            dxn2 = ops.gemm_nt(dpre, self.fc1_w[j])
+            dh_mid = ops.layernorm_bwd(h_mid, self.ln2_w[j], dxn2, dh, f32[p + "layer_norm2.weight"],
+                                       f32[p + "layer_norm2.bias"], eps)
+            datt = ops.gemm_nt(dh_mid, self.out_w[j])
+            ops.gemm_tn(dh_mid, att, out=grad(p + "self_attn.out_proj.weight"), accumulate=accumulate)
+            ops.colsum_accumulate(dh_mid, f32[p + "self_attn.out_proj.bias"])
+            dqkv = ops.flash_attn_bwd(qkv, att, datt, lse, n, self.tokens, H, 64, causal=False)
+            ops.gemm_tn(dqkv, xn1, out=grad(p + "self_attn.qkv_proj.weight"), accumulate=accumulate)
+            ops.colsum_accumulate(dqkv, f32[p + "self_attn.qkv_proj.bias"])
+            dxn1 = ops.gemm_nt(dqkv, self.qkv_w[j])
+            dh = ops.layernorm_bwd(h, self.ln1_w[j], dxn1, dh_mid, f32[p + "layer_norm1.weight"],
+                                   f32[p + "layer_norm1.bias"], eps)
+            saved["layers"][j] = None
+            if done is not None:
+                done(p + "layer_norm1.bias")
+        demb = ops.layernorm_bwd(saved["emb"], self.pre_ln_w, dh, None, f32[self.VM + "pre_layrnorm.weight"],
+                                 f32[self.VM + "pre_layrnorm.bias"], eps)
+        dpatch = ops.vit_embed_bwd(demb, f32[self.VM + "embeddings.position_embedding.weight"].view(self.tokens, -1),
+                                   f32[self.VM + "embeddings.class_embedding"], n)
+        ops.gemm_tn(dpatch, saved["col"], out=grad(self.VM + "embeddings.patch_embedding.weight"), accumulate=accumulate)
 
     def forward(self, images: List[torch.Tensor]):
         with torch.set_grad_enabled(False):  # forward-only kernels; training path: see engine/train

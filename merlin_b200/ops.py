@@ -59,6 +59,14 @@ def _gemm_call(fn, flops, *args):
     return rc
 
 
+from .composite_ops import (decoder_layer_forward as _decoder_layer_forward_c, decoder_layer_workspace,  # noqa: E402
+                            vit_layer_forward, vit_layer_workspace)
+
+
+def decoder_layer_forward(*args, **kw):
+    return _decoder_layer_forward_c(*args, **kw)
+
+
 def _stream() -> int:
     return torch.cuda.current_stream().cuda_stream
 
@@ -430,3 +438,46 @@ def adamw_step(params, grads, exp_avg, exp_avg_sq, lr_mult, weight_decay, chunk:
 
 def f32_to_bf16(x: torch.Tensor, y: torch.Tensor) -> None:
     check(_lib.load().merlin_f32_to_bf16(_stream(), x.data_ptr(), y.data_ptr(), x.numel()), "merlin_f32_to_bf16", 1)
+
+
+# ----------------------------------------------------------------------------- vision-tower backward ops
+def layernorm_bwd(x, weight, dy, dres, dweight, dbias, eps, out=None):
+    M, D, _ = _rows2d(x, "x")
+    if out is None:
+        out = torch.empty_like(x)
+    check(_lib.load().merlin_layernorm_bwd(_stream(), x.data_ptr(), weight.data_ptr(), dy.data_ptr(), _ptr(dres),
+                                           out.data_ptr(), _ptr(dweight), _ptr(dbias), M, D, float(eps)),
+          "merlin_layernorm_bwd", 1)
+    return out
+
+
+def quick_gelu(x, dy=None, out=None):
+    """Forward (dy None) or backward of x·σ(1.702x) over a contiguous bf16 tensor."""
+    if out is None:
+        out = torch.empty_like(x)
+    check(_lib.load().merlin_quick_gelu(_stream(), x.data_ptr(), _ptr(dy), out.data_ptr(), x.numel()),
+          "merlin_quick_gelu", 1)
+    return out
+
+
+def conv3x3_col2im(dcol, dfeat, n_img, grid, C, stride, tok_stride, tok_off):
+    check(_lib.load().merlin_conv3x3_col2im(_stream(), dcol.data_ptr(), dfeat.data_ptr(), n_img, grid, C, stride,
+                                            tok_stride, tok_off), "merlin_conv3x3_col2im", 1)
+    return dfeat
+
+
+def vit_embed(patch_out, class_embedding, position_embedding, n_img):
+    tokens, D = position_embedding.shape
+    emb = torch.empty((n_img * tokens, D), dtype=_BF16, device=patch_out.device)
+    check(_lib.load().merlin_vit_embed(_stream(), patch_out.data_ptr(), class_embedding.data_ptr(),
+                                       position_embedding.data_ptr(), emb.data_ptr(), n_img, tokens, D),
+          "merlin_vit_embed", 1)
+    return emb
+
+
+def vit_embed_bwd(dhidden, dposition_f32, dclass_f32, n_img):
+    tokens, D = dposition_f32.shape
+    dpatch = torch.empty((n_img * (tokens - 1), D), dtype=_BF16, device=dhidden.device)
+    check(_lib.load().merlin_vit_embed_bwd(_stream(), dhidden.data_ptr(), dpatch.data_ptr(), dposition_f32.data_ptr(),
+                                           dclass_f32.data_ptr(), n_img, tokens, D), "merlin_vit_embed_bwd", 1)
+    return dpatch

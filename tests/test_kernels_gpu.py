@@ -398,3 +398,71 @@ def test_adamw_matches_fp32_reference_rule():
     assert torch.equal(p[2 * chunk:], p[2 * chunk:])           # frozen chunk untouched below
     close(p[:2 * chunk], pr[:2 * chunk], tol=2.0 ** -6)
     close(m[:2 * chunk], mr[:2 * chunk], tol=2.0 ** -6)
+
+
+def test_vision_backward_kernels():
+    torch.manual_seed(17)
+    M, D = 300, 1024
+    x = torch.randn(M, D, device=DEV).to(torch.bfloat16)
+    w = (1 + 0.1 * torch.randn(D, device=DEV)).to(torch.bfloat16)
+    b = (0.1 * torch.randn(D, device=DEV)).to(torch.bfloat16)
+    dy = torch.randn(M, D, device=DEV).to(torch.bfloat16)
+    dres = torch.randn(M, D, device=DEV).to(torch.bfloat16)
+    xr, wr, br = x.float().requires_grad_(True), w.float().requires_grad_(True), b.float().requires_grad_(True)
+    torch.nn.functional.layer_norm(xr, (D,), wr, br, 1e-5).backward(dy.float())
+    dw = torch.zeros(D, device=DEV)
+    db = torch.zeros(D, device=DEV)
+    close(ops.layernorm_bwd(x, w, dy, dres, dw, db, 1e-5), xr.grad + dres.float())
+    close(dw, wr.grad, tol=2.0 ** -9)
+    close(db, br.grad, tol=2.0 ** -9)
+    # quick_gelu forward / backward
+    xq = x.float().clone().requires_grad_(True)
+    y = xq * torch.sigmoid(1.702 * xq)
+    y.backward(dy.float())
+    close(ops.quick_gelu(x), y)
+    close(ops.quick_gelu(x, dy=dy), xq.grad)
+    # col2im == autograd of the unfold-based im2col, strides 1 and 2
+    n, G, C = 2, 24, 256
+    for stride in (1, 2):
+        feat = torch.randn(n, C, G, G, device=DEV, requires_grad=True)
+        un = torch.nn.functional.unfold(feat, 3, padding=1, stride=stride)          # [n, C*9, P]
+        P = un.shape[-1]
+        col_ref = un.view(n, C, 9, P).permute(0, 3, 2, 1).reshape(n * P, 9 * C)
+        dcol = torch.randn(n * P, 9 * C, device=DEV).to(torch.bfloat16)
+        col_ref.backward(dcol.float())
+        dfeat = torch.zeros(n * 577, C, device=DEV, dtype=torch.bfloat16)
+        ops.conv3x3_col2im(dcol, dfeat, n, G, C, stride, 577, 1)
+        want = feat.grad.permute(0, 2, 3, 1).reshape(n, G * G, C)
+        close(dfeat.view(n, 577, C)[:, 1:], want, tol=2.0 ** -7)
+        assert bool((dfeat.view(n, 577, C)[:, 0] == 0).all())
+    # embedding assembly + backward
+    po = torch.randn(2 * 576, 256, device=DEV).to(torch.bfloat16)
+    cls = torch.randn(256, device=DEV).to(torch.bfloat16)
+    pos = torch.randn(577, 256, device=DEV).to(torch.bfloat16)
+    emb = ops.vit_embed(po, cls, pos, 2)
+    ref = (torch.cat([cls.expand(2, 1, 256), po.view(2, 576, 256)], 1) + pos).reshape(-1, 256)
+    assert torch.equal(emb, ref)
+    d = torch.randn(2 * 577, 256, device=DEV).to(torch.bfloat16)
+    dpos = torch.zeros(577, 256, device=DEV)
+    dcls = torch.zeros(256, device=DEV)
+    dpatch = ops.vit_embed_bwd(d, dpos, dcls, 2)
+    assert torch.equal(dpatch.view(2, 576, 256), d.view(2, 577, 256)[:, 1:])
+    close(dpos, d.float().view(2, 577, 256).sum(0), tol=1e-6)
+    close(dcls, d.float().view(2, 577, 256)[:, 0].sum(0), tol=1e-6)
+
+
+@pytest.mark.parametrize("causal", [True, False])
+def test_flash_attention_backward_hd64(causal):
+    torch.manual_seed(18)
+    B, S, H, hd = 2, 577, 2, 64
+    qkv = torch.randn(B * S, 3 * H * hd, device=DEV).to(torch.bfloat16)
+    dout = torch.randn(B * S, H * hd, device=DEV).to(torch.bfloat16)
+    out, lse = ops.flash_attn(qkv, B, S, H, hd, causal=causal, return_lse=True)
+    dqkv = ops.flash_attn_bwd(qkv, out, dout, lse, B, S, H, hd, causal=causal)
+    ref_in = qkv.float().clone().requires_grad_(True)
+    ref, _ = attn_ref(ref_in, B, S, H, hd, causal)
+    ref.backward(dout.float())
+    g = ref_in.grad.view(B * S, 3, H * hd)
+    mine = dqkv.float().view(B * S, 3, H * hd)
+    for blk in range(3):
+        close(mine[:, blk], g[:, blk], tol=2.0 ** -6)

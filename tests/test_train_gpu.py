@@ -27,7 +27,18 @@ def unpack_grads(trainer, cfg):
     out = {}
     for name in trainer.names:
         g = ar.grad(name).float().cpu()
-        if name.endswith("self_attn.qkv_proj.weight"):
+        if "vision_model" in name:
+            d = cfg.vit_hidden
+            if name.endswith("self_attn.qkv_proj.weight") or name.endswith("self_attn.qkv_proj.bias"):
+                kind = name.rsplit(".", 1)[1]
+                base = name[: -len("qkv_proj." + kind)]
+                for j, n in enumerate("qkv"):
+                    out[base + f"{n}_proj.{kind}"] = g[j * d:(j + 1) * d]
+            elif name.endswith("patch_embedding.weight"):
+                out[name] = g[:, : 3 * cfg.patch_size ** 2].reshape(d, 3, cfg.patch_size, cfg.patch_size)
+            else:
+                out[name] = g
+        elif name.endswith("self_attn.qkv_proj.weight"):
             base = name[: -len("qkv_proj.weight")]
             for j, n in enumerate("qkv"):
                 out[base + f"{n}_proj.weight"] = g[j * D:(j + 1) * D]
@@ -98,3 +109,38 @@ def test_training_steps_reduce_the_loss_and_respect_frozen_tower():
     # the model keeps working for inference after its weights moved into the arena
     out = model(input_ids=g["input_ids"].to(DEV), images=[im.to(DEV) for im in g["images"]], labels=g["labels"].to(DEV))
     assert out.loss.item() < losses[0]
+
+
+@pytest.mark.parametrize("name", ["tiny_conv", "tiny_mlp"])
+def test_vision_tower_gradients_match_oracle_autograd(name):
+    """freeze_vision_tower=False (the reference's LLRD recipe): gradients of every CLIP parameter that can
+    receive one (layers below select_layer, pre_layrnorm, embeddings) against oracle autograd."""
+    g, cfg = load_golden(name)
+    sd = O.init_state_dict(cfg, seed=0)
+    model = build_product_model(cfg, sd)
+    for p in model.parameters():
+        p.requires_grad_(True)
+    trainer = MMGPTTrainer(model, TrainingArguments(max_grad_norm=0.0, llrd=True))
+    assert any("vision_model" in n for n in trainer.names)
+    batch = {k: g[k] for k in ("input_ids", "labels", "attention_mask")}
+    batch["images"] = [im.to(DEV) for im in g["images"]]
+    trainer._last_micro = True
+    trainer._fold_ptr = 0
+    trainer.reducer.start_step()
+    with torch.no_grad():
+        trainer._forward_backward(batch, accumulate=False, grad_scale=1.0)
+    _, ref = oracle_grads(cfg, sd, {**batch, "images": g["images"]})
+    mine = unpack_grads(trainer, cfg)
+    vit = [k for k in mine if "vision_model" in k]
+    assert len(vit) >= 16 * (cfg.vit_layers - 1) + 5
+    for k in vit:
+        gm, gr = mine[k], ref[k]
+        cos = torch.nn.functional.cosine_similarity(gm.flatten(), gr.flatten(), dim=0).item()
+        err = (gm - gr).abs().max().item() / (gr.abs().max().item() + 1e-12)
+        assert cos >= 0.995 and err <= 0.08, f"{k}: cos={cos:.5f} rel-max-err={err:.4f}"
+    # LLRD tables: encoder layer j is scaled by 0.9 ** (22 - j), other vision_model params by 0.1
+    ar = trainer.arena
+    off = ar.offsets["model.vision_tower.vision_tower.vision_model.encoder.layers.1.mlp.fc1.weight"][0]
+    assert ar.lr_mult[off // ar.chunk].item() == pytest.approx(0.9 ** 21)
+    off = ar.offsets["model.vision_tower.vision_tower.vision_model.pre_layrnorm.bias"][0]
+    assert ar.lr_mult[off // ar.chunk].item() == pytest.approx(0.1) and ar.weight_decay[off // ar.chunk].item() == 0.0
