@@ -109,7 +109,8 @@ extern "C" int merlin_attn_delta(void* stream, const void* out, const void* dout
                                  int H, int head_dim, int64_t ld);
 
 extern "C" size_t merlin_flash_attn_bwd_workspace_bytes(int B, int S, int H, int head_dim) {
-  return (static_cast<size_t>(B) * H * S + static_cast<size_t>(B) * S * H * head_dim) * sizeof(float);
+  const size_t delta = (static_cast<size_t>(B) * H * S + 63) / 64 * 64;  // keep the dq accumulator 256-byte aligned
+  return (delta + static_cast<size_t>(B) * S * H * head_dim) * sizeof(float);
 }
 
 extern "C" int merlin_flash_attn_bwd(void* stream, const void* qkv, int64_t ld_qkv, const void* out,
@@ -122,7 +123,7 @@ extern "C" int merlin_flash_attn_bwd(void* stream, const void* qkv, int64_t ld_q
   MB_CHECK_ARG(B > 0 && S > 0 && H > 0, "flash_attn_bwd: empty problem");
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   float* delta = static_cast<float*>(workspace);
-  float* dq_acc = delta + static_cast<size_t>(B) * H * S;
+  float* dq_acc = delta + (static_cast<size_t>(B) * H * S + 63) / 64 * 64;
   int rc = merlin_attn_delta(stream, out, dout, delta, B, S, H, head_dim, ld_out);
   if (rc != MERLIN_OK) return rc;
   MB_CHECK_CUDA(cudaMemsetAsync(dq_acc, 0, static_cast<size_t>(B) * S * H * head_dim * sizeof(float), st));

@@ -135,6 +135,11 @@ def test_vision_tower_gradients_match_oracle_autograd(name):
     assert len(vit) >= 16 * (cfg.vit_layers - 1) + 5
     for k in vit:
         gm, gr = mine[k], ref[k]
+        if k.endswith("k_proj.bias"):
+            # softmax is invariant to a constant added to every key, so this gradient is identically zero
+            # (the oracle's is ~1e-9 rounding noise); ours must be rounding noise of bf16 size
+            assert gr.abs().max().item() < 1e-6 and gm.abs().max().item() < 5e-3
+            continue
         cos = torch.nn.functional.cosine_similarity(gm.flatten(), gr.flatten(), dim=0).item()
         err = (gm - gr).abs().max().item() / (gr.abs().max().item() + 1e-12)
         assert cos >= 0.995 and err <= 0.08, f"{k}: cos={cos:.5f} rel-max-err={err:.4f}"
