@@ -237,7 +237,9 @@ int merlin_flash_attn_bwd(void* stream, const void* qkv, int64_t ld_qkv, const v
                           int64_t ld_out, const float* lse, const int* seqlens, void* dqkv, int64_t ld_dqkv,
                           void* workspace, int B, int S, int H, int head_dim, int causal, float softmax_scale);
 
-/* out[0] = Σ g² over a flat bf16 gradient arena of n elements (n % 8 == 0): global grad norm. */
+/* out[0] = Σ g² over a flat bf16 gradient arena of n elements (n % 8 == 0): global grad norm.  `out` is
+ * 4 floats (out[2..3] hold a 64-bit fixed-point accumulator: the sum is order-independent, hence
+ * bit-identical on every data-parallel rank). */
 int merlin_grad_sumsq(void* stream, const void* grads, int64_t n, float* out);
 
 /* Fused AdamW over flat bf16 arenas (params, grads, exp_avg, exp_avg_sq; n elements).  Elements

@@ -261,7 +261,14 @@ __global__ void attn_delta_kernel(const __nv_bfloat16* __restrict__ o, const __n
 }
 
 // ------------------------------------------------------------------ optimizer
-// Σ g² over the flat gradient arena (fp32 atomics into out[0]).
+// Σ g² over the flat gradient arena.  Block partials (fixed in-block order) are accumulated as 64-bit
+// FIXED-POINT integers, so the total is independent of block scheduling order: every data-parallel rank
+// derives a bit-identical clip factor from bit-identical (all-reduced) gradients and replicas never drift.
+constexpr float kSumsqScale = 1099511627776.f;  // 2^40: resolution 9e-13, range 1.6e7
+__global__ void sumsq_finalize_kernel(float* __restrict__ out) {
+  out[0] = static_cast<float>(static_cast<double>(*reinterpret_cast<unsigned long long*>(out + 2)) /
+                              static_cast<double>(kSumsqScale));
+}
 __global__ void sumsq_kernel(const __nv_bfloat16* __restrict__ g, int64_t n_vec, float* __restrict__ out) {
   __shared__ float red[32];
   float acc = 0.f;
@@ -273,7 +280,9 @@ __global__ void sumsq_kernel(const __nv_bfloat16* __restrict__ g, int64_t n_vec,
     for (int e = 0; e < 8; ++e) acc += f[e] * f[e];
   }
   acc = block_sum_b(acc, red);
-  if (threadIdx.x == 0) atomicAdd(out, acc);
+  if (threadIdx.x == 0)
+    atomicAdd(reinterpret_cast<unsigned long long*>(out + 2),
+              static_cast<unsigned long long>(static_cast<double>(acc) * static_cast<double>(kSumsqScale) + 0.5));
 }
 
 // Fused AdamW over a flat arena: p, g, m, v are bf16 (the reference keeps bf16 weights AND optimizer
@@ -422,9 +431,11 @@ int merlin_attn_delta(void* stream, const void* out, const void* dout, float* de
 int merlin_grad_sumsq(void* stream, const void* grads, int64_t n, float* out) {
   MB_CHECK_ARG(grads && out && n % 8 == 0, "grad_sumsq: bad argument");
   cudaStream_t st = static_cast<cudaStream_t>(stream);
-  MB_CHECK_CUDA(cudaMemsetAsync(out, 0, sizeof(float), st));
+  MB_CHECK_ARG((reinterpret_cast<uintptr_t>(out) & 7) == 0, "grad_sumsq: out must be 8-byte aligned (4 floats)");
+  MB_CHECK_CUDA(cudaMemsetAsync(out, 0, 4 * sizeof(float), st));
   if (n == 0) return MERLIN_OK;
   sumsq_kernel<<<grid_for(n / 8, 256), 256, 0, st>>>(static_cast<const __nv_bfloat16*>(grads), n / 8, out);
+  sumsq_finalize_kernel<<<1, 1, 0, st>>>(out);
   MB_CHECK_CUDA(cudaGetLastError());
   return MERLIN_OK;
 }

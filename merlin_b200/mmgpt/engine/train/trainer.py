@@ -80,7 +80,7 @@ class MMGPTTrainer:
         self.names = [n for n, _ in named]
         self.reducer = GradBucketReducer(self.arena.grads, bucket_elems=a.bucket_mb * 1024 * 1024 // 2)
         dev = self.arena.params.device
-        self._sumsq = torch.zeros(1, dtype=torch.float32, device=dev)
+        self._sumsq = torch.zeros(4, dtype=torch.float32, device=dev)  # [0] = Σg², [2:4] = fixed-point accumulator
         # fp32 accumulators for 1-D gradients (norm weights, projector bias)
         for n, p in named:
             if p.dim() == 1 or n.endswith("position_embedding.weight"):
@@ -246,7 +246,7 @@ class MMGPTTrainer:
         self.last_lr = lr
 
     def grad_norm(self) -> float:
-        return float(self._sumsq.sqrt())
+        return float(self._sumsq[0].sqrt())
 
     def train(self, batches, log_every: int = 1):
         """Minimal loop with the reference's logging cadence (--logging_steps 1): loss, lr, tokens/s."""

@@ -369,9 +369,13 @@ def test_adamw_matches_fp32_reference_rule():
     v = torch.zeros(n, device=DEV, dtype=torch.bfloat16)
     lr_mult = torch.tensor([1.0, 0.5, 0.0], device=DEV)
     wd = torch.tensor([0.05, 0.0, 0.05], device=DEV)
-    ss = torch.zeros(1, device=DEV)
+    ss = torch.zeros(4, device=DEV)
     ops.grad_sumsq(g, ss)
-    close(ss, g.float().pow(2).sum().view(1), tol=1e-4)
+    close(ss[:1], g.float().pow(2).sum().view(1), tol=1e-4)
+    first = ss[0].item()
+    for _ in range(5):                                   # order-independent accumulation: bitwise repeatable
+        ops.grad_sumsq(g, ss)
+        assert ss[0].item() == first
     pr, mr, vr = p.float().clone(), m.float().clone(), v.float().clone()
     lr, b1, b2, eps, max_norm = 1e-2, 0.9, 0.95, 1e-8, 1.0
     for step in (1, 2):
