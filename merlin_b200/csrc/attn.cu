@@ -157,11 +157,21 @@ extern "C" int merlin_flash_attn_bwd(void* stream, const void* qkv, int64_t ld_q
     uint32_t box[3] = {64, kBwdBlock, 1};
     if ((rc = make_tmap_bf16(&tdo, dout, 3, dims, str, box)) != MERLIN_OK) return rc;
   }
+  CUtensorMap tdq;
+  {
+    // fp32 dQ accumulator [B*S, H*hd].  A ragged last query tile of sample b overlaps the first rows of
+    // sample b+1, but its rows >= S carry P = dS = 0, i.e. exactly zero dQ: the reduce-add of zeros is a
+    // no-op there, and rows beyond B*S are clipped by the tensor map.
+    uint64_t dims[2] = {static_cast<uint64_t>(H) * head_dim, static_cast<uint64_t>(B) * S};
+    uint64_t str[1] = {static_cast<uint64_t>(H) * head_dim * sizeof(float)};
+    uint32_t box[2] = {32, kBwdBlock};
+    if ((rc = make_tmap_f32(&tdq, dq_acc, 2, dims, str, box)) != MERLIN_OK) return rc;
+  }
   dim3 grid(static_cast<unsigned>((S + kBwdBlock - 1) / kBwdBlock), static_cast<unsigned>(H),
             static_cast<unsigned>(B));
   auto launch = [&](auto kernel, int smem) -> int {
     MB_CHECK_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
-    kernel<<<grid, kBwdThreads, smem, st>>>(tq, tdo, p);
+    kernel<<<grid, kBwdThreads, smem, st>>>(tq, tdo, tdq, p);
     MB_CHECK_CUDA(cudaGetLastError());
     return MERLIN_OK;
   };

@@ -40,14 +40,16 @@ struct AttnBwdCfg {
   static constexpr int kSmemBytes = kSmemTiles + kNumBars * 8 + 16 + 1024;
 };
 
-__device__ __forceinline__ void red_add_f32(float* addr, float v) {
-  asm volatile("red.global.add.f32 [%0], %1;" ::"l"(addr), "f"(v) : "memory");
+// 16-byte vector reduction (sm_90+): one L2 atomic transaction per four floats
+__device__ __forceinline__ void red_add_f32x4(float* addr, float a, float b, float c, float d) {
+  asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(addr), "f"(a), "f"(b), "f"(c), "f"(d)
+               : "memory");
 }
 
 template <int HD, bool kCausal>
 __global__ void __launch_bounds__(kBwdThreads, 1)
 attn_bwd_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid_constant__ CUtensorMap tm_do,
-                const AttnBwdParams p) {
+                const __grid_constant__ CUtensorMap tm_dq, const AttnBwdParams p) {
   using Cfg = AttnBwdCfg<HD>;
   constexpr int kAtoms = HD / 64;
   constexpr int kAtomBytes = kBwdBlock * 128;   // 16 KB: [128 rows x 64 bf16]
@@ -85,6 +87,7 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid_constan
   if (warp == 0 && elect_one()) {
     tma_prefetch_desc(&tm_qkv);
     tma_prefetch_desc(&tm_do);
+    tma_prefetch_desc(&tm_dq);
   }
   if (warp == 1 && elect_one()) {
     mbar_init(kv_full, 1);
@@ -191,6 +194,11 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid_constan
       const float dlt = q_valid ? p.delta[stat] : 0.f;
       mbar_wait(sdp_full, s & 1);
       tc_fence_after();
+      if (s > 0) {
+        // the previous step's dQ reduction must have finished READING the P|dS staging bytes
+        if (threadIdx.x == 128) tma_store_wait_read<0>();
+        named_bar_sync(1, 128);
+      }
 #pragma unroll
       for (int ch = 0; ch < 4; ++ch) {
         uint32_t sv_[32], dpv[32];
@@ -225,23 +233,32 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid_constan
       tc_fence_before();
       mbar_arrive(pds_full);
 
-      // dQ_i tile -> fp32 global reduction
+      // dQ_i tile: TMEM -> fp32 128B-swizzled staging (aliasing P|dS, which the MMAs have finished
+      // reading) -> ONE TMA reduce-add per [128 rows x 32 floats] box into the fp32 dQ accumulator
       mbar_wait(dq_full, s & 1);
       tc_fence_after();
-      float* dq_row = p.dq_accum + (static_cast<size_t>(batch) * p.S + (q_idx < p.S ? q_idx : 0)) * (p.H * HD) + head * HD;
 #pragma unroll
       for (int ch = 0; ch < HD / 32; ++ch) {
         uint32_t v[32];
         tmem_ld32(t_s + lane_sel + ch * 32, v);
         tmem_ld_wait();
-        if (q_valid) {
 #pragma unroll
-          for (int e = 0; e < 32; ++e) red_add_f32(dq_row + ch * 32 + e, __uint_as_float(v[e]));
-        }
+        for (int c16 = 0; c16 < 8; ++c16)
+          *reinterpret_cast<uint4*>(sp + ch * kAtomBytes + sw128_offset(row, c16)) =
+              make_uint4(v[c16 * 4], v[c16 * 4 + 1], v[c16 * 4 + 2], v[c16 * 4 + 3]);
       }
       tc_fence_before();
       mbar_arrive(dq_read);
+      fence_proxy_async_smem();
+      named_bar_sync(1, 128);
+      if (threadIdx.x == 128) {
+#pragma unroll
+        for (int ch = 0; ch < HD / 32; ++ch)
+          tma_reduce_add_2d(&tm_dq, sp + ch * kAtomBytes, head * HD + ch * 32, batch * p.S + i * kBwdBlock);
+        tma_store_commit();
+      }
     }
+    if (threadIdx.x == 128) tma_store_wait_all<0>();
 
     // ---- dK, dV of this key tile (thread = key row).  The TMEM loads are warp-collective
     // (.sync.aligned): every lane executes them, only the global stores are predicated.

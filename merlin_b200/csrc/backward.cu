@@ -6,6 +6,8 @@
 #include "host.cuh"
 #include "ptx.cuh"
 
+#include <algorithm>
+
 namespace mb {
 
 __device__ __forceinline__ float warp_sum_b(float v) {
@@ -38,10 +40,10 @@ __device__ __forceinline__ uint4 pack8b(const float (&f)[8]) {
 
 // ------------------------------------------------------------------ RMSNorm backward
 // y = w ⊙ x̂, x̂ = x·r, r = rsqrt(mean(x²)+eps).  g = w ⊙ dy;  dx = r·(g − x̂·mean(g ⊙ x̂)) (+ dres);
-// dw[j] += Σ_rows dy[row,j]·x̂[row,j]   (fp32 atomics, one per column per block of kRows rows).
+// dw[j] += Σ_rows dy[row,j]·x̂[row,j]   (fp32 atomics, one per column per CTA of the persistent grid).
 constexpr int kRnbThreads = 256;
 constexpr int kRnbVec = 4;    // D <= 8192
-constexpr int kRnbRows = 16;  // rows per block (amortises the dw atomics)
+// grid = 4 CTAs per SM, rows strided over the grid: dw/db need one atomic per column per CTA only
 
 __global__ void __launch_bounds__(kRnbThreads)
 rmsnorm_bwd_kernel(const __nv_bfloat16* __restrict__ x, const __nv_bfloat16* __restrict__ w,
@@ -57,9 +59,8 @@ rmsnorm_bwd_kernel(const __nv_bfloat16* __restrict__ x, const __nv_bfloat16* __r
 #pragma unroll
     for (int e = 0; e < 8; ++e) dwacc[i][e] = 0.f;
   }
-  const int row0 = blockIdx.x * kRnbRows;
-  for (int r = 0; r < kRnbRows && row0 + r < M; ++r) {
-    const size_t off = static_cast<size_t>(row0 + r) * D;
+  for (int row = blockIdx.x; row < M; row += gridDim.x) {
+    const size_t off = static_cast<size_t>(row) * D;
     float xv[kRnbVec][8], gv[kRnbVec][8];
     float ss = 0.f;
 #pragma unroll
@@ -351,7 +352,7 @@ int merlin_rmsnorm_bwd(void* stream, const void* x, const void* weight, const vo
   MB_CHECK_ARG(x && weight && dy && dx, "rmsnorm_bwd: null tensor");
   MB_CHECK_ARG(D % 8 == 0 && D <= 8 * kRnbThreads * kRnbVec, "rmsnorm_bwd: D=%d unsupported", D);
   if (M == 0) return MERLIN_OK;
-  rmsnorm_bwd_kernel<<<(M + kRnbRows - 1) / kRnbRows, kRnbThreads, 0, static_cast<cudaStream_t>(stream)>>>(
+  rmsnorm_bwd_kernel<<<std::min(M, sm_count() * 4), kRnbThreads, 0, static_cast<cudaStream_t>(stream)>>>(
       static_cast<const __nv_bfloat16*>(x), static_cast<const __nv_bfloat16*>(weight),
       static_cast<const __nv_bfloat16*>(dy), static_cast<const __nv_bfloat16*>(dres),
       static_cast<__nv_bfloat16*>(dx), dweight, M, D, eps);
@@ -474,7 +475,7 @@ int merlin_f32_to_bf16(void* stream, const float* x, void* y, int64_t n) {
 namespace mb {
 
 // LayerNorm backward: x̂ = (x−μ)·r, y = w⊙x̂ + b.  g = w⊙dy; dx = r·(g − mean(g) − x̂·mean(g⊙x̂)) (+ dres);
-// dw += Σ dy⊙x̂, db += Σ dy  (fp32 atomics, one per column per block of kRnbRows rows).
+// dw += Σ dy⊙x̂, db += Σ dy  (fp32 atomics, one per column per CTA of the persistent grid).
 __global__ void __launch_bounds__(kRnbThreads)
 layernorm_bwd_kernel(const __nv_bfloat16* __restrict__ x, const __nv_bfloat16* __restrict__ w,
                      const __nv_bfloat16* __restrict__ dy, const __nv_bfloat16* __restrict__ dres,
@@ -490,9 +491,8 @@ layernorm_bwd_kernel(const __nv_bfloat16* __restrict__ x, const __nv_bfloat16* _
 #pragma unroll
     for (int e = 0; e < 8; ++e) dwacc[i][e] = dbacc[i][e] = 0.f;
   }
-  const int row0 = blockIdx.x * kRnbRows;
-  for (int r = 0; r < kRnbRows && row0 + r < M; ++r) {
-    const size_t off = static_cast<size_t>(row0 + r) * D;
+  for (int row = blockIdx.x; row < M; row += gridDim.x) {
+    const size_t off = static_cast<size_t>(row) * D;
     float xv[kRnbVec][8], gv[kRnbVec][8];
     float s = 0.f;
 #pragma unroll
@@ -641,7 +641,7 @@ int merlin_layernorm_bwd(void* stream, const void* x, const void* weight, const 
   MB_CHECK_ARG(x && weight && dy && dx, "layernorm_bwd: null tensor");
   MB_CHECK_ARG(D % 8 == 0 && D <= 8 * kRnbThreads * kRnbVec, "layernorm_bwd: D=%d unsupported", D);
   if (M == 0) return MERLIN_OK;
-  layernorm_bwd_kernel<<<(M + kRnbRows - 1) / kRnbRows, kRnbThreads, 0, static_cast<cudaStream_t>(stream)>>>(
+  layernorm_bwd_kernel<<<std::min(M, sm_count() * 4), kRnbThreads, 0, static_cast<cudaStream_t>(stream)>>>(
       static_cast<const __nv_bfloat16*>(x), static_cast<const __nv_bfloat16*>(weight),
       static_cast<const __nv_bfloat16*>(dy), static_cast<const __nv_bfloat16*>(dres),
       static_cast<__nv_bfloat16*>(dx), dweight, dbias, M, D, eps);

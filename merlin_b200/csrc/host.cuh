@@ -35,6 +35,9 @@ void set_error(const char* fmt, ...);
 // strides (bytes) are given for dims 1..rank-1.  Returns MERLIN_OK or an error code.
 int make_tmap_bf16(CUtensorMap* out, const void* base, int rank, const uint64_t* dims,
                    const uint64_t* strides_bytes, const uint32_t* box);
+// Same for fp32 tensors (128B swizzle => inner box of at most 32 floats).
+int make_tmap_f32(CUtensorMap* out, const void* base, int rank, const uint64_t* dims,
+                  const uint64_t* strides_bytes, const uint32_t* box);
 
 int sm_count();
 
