@@ -34,6 +34,10 @@ struct GemvParams {
   int ksplit;                     // 1, 2 or 4 warps per row pair
 };
 
+#ifndef MERLIN_GEMV_VEC
+#define MERLIN_GEMV_VEC 4
+#endif
+constexpr int kVec = MERLIN_GEMV_VEC;   // 16-byte vectors per row per batch (2*kVec loads in flight per lane)
 constexpr int kGemvWarps = 4;
 constexpr int kGemvThreads = kGemvWarps * 32;
 
@@ -97,9 +101,9 @@ gemv_pair_kernel(const GemvParams p) {
 
   // ---- prefetch the first weight batch (8 x 16 B per lane) BEFORE waiting on the producer kernel:
   // with programmatic dependent launch this overlaps the previous kernel's tail and our own prologue.
-  uint4 a[4], b[4];
+  uint4 a[kVec], b[kVec];
 #pragma unroll
-  for (int u = 0; u < 4; ++u) {
+  for (int u = 0; u < kVec; ++u) {
     const int idx = v0 + lane + 32 * u;
     a[u] = b[u] = make_uint4(0, 0, 0, 0);
     if (active && idx < v1) {
@@ -143,11 +147,11 @@ gemv_pair_kernel(const GemvParams p) {
 
   // ---- software-pipelined main loop: issue batch n+1, then consume batch n
   float sa = 0.f, sb = 0.f;
-  for (int i = v0 + lane; active && i < v1; i += 128) {
-    uint4 na[4], nb[4];
+  for (int i = v0 + lane; active && i < v1; i += 32 * kVec) {
+    uint4 na[kVec], nb[kVec];
 #pragma unroll
-    for (int u = 0; u < 4; ++u) {
-      const int idx = i + 128 + 32 * u;
+    for (int u = 0; u < kVec; ++u) {
+      const int idx = i + 32 * kVec + 32 * u;
       na[u] = nb[u] = make_uint4(0, 0, 0, 0);
       if (idx < v1) {
         na[u] = ld_stream(wa + idx);
@@ -155,7 +159,7 @@ gemv_pair_kernel(const GemvParams p) {
       }
     }
 #pragma unroll
-    for (int u = 0; u < 4; ++u) {
+    for (int u = 0; u < kVec; ++u) {
       const int idx = i + 32 * u;
       if (idx < v1) {
         const uint4 xv = xs[idx];
@@ -164,7 +168,7 @@ gemv_pair_kernel(const GemvParams p) {
       }
     }
 #pragma unroll
-    for (int u = 0; u < 4; ++u) {
+    for (int u = 0; u < kVec; ++u) {
       a[u] = na[u];
       b[u] = nb[u];
     }
@@ -228,8 +232,10 @@ constexpr int kFdThreads = 128;  // 4 warps x 4 key slots x 8 lanes (16 dims eac
 __global__ void __launch_bounds__(kFdThreads)
 flash_decode_partial_kernel(const __nv_bfloat16* __restrict__ q, const __nv_bfloat16* __restrict__ kv,
                             const int* __restrict__ pos_ptr, int D, int n_splits, float scale_log2e,
-                            float* __restrict__ part_o, float* __restrict__ part_ml) {
+                            float* __restrict__ part_o, float* __restrict__ part_ml,
+                            unsigned int* __restrict__ tickets, __nv_bfloat16* __restrict__ att_out) {
   __shared__ float s_o[16][128];
+  __shared__ unsigned int s_last;
   __shared__ float s_m[16], s_l[16];
   const int h = blockIdx.x, split = blockIdx.y;
   asm volatile("griddepcontrol.wait;" ::: "memory");
@@ -324,6 +330,28 @@ flash_decode_partial_kernel(const __nv_bfloat16* __restrict__ q, const __nv_bflo
     part_ml[idx * 2] = M;
     part_ml[idx * 2 + 1] = L;
   }
+  // The last split of this head to finish merges all partials (no separate combine kernel).
+  __threadfence();
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    const unsigned int t = atomicAdd(&tickets[h], 1u);
+    s_last = (t == static_cast<unsigned int>(n_splits) - 1u) ? 1u : 0u;
+    if (s_last) tickets[h] = 0;  // self-resetting for the next layer / token
+  }
+  __syncthreads();
+  if (!s_last) return;
+  __threadfence();
+  float Mx = -INFINITY;
+  for (int sp = 0; sp < n_splits; ++sp) Mx = fmaxf(Mx, __ldcg(&part_ml[(static_cast<size_t>(h) * n_splits + sp) * 2]));
+  float o_acc = 0.f, l_acc = 0.f;
+  for (int sp = 0; sp < n_splits; ++sp) {
+    const size_t i2 = static_cast<size_t>(h) * n_splits + sp;
+    const float m = __ldcg(&part_ml[i2 * 2]);
+    const float w = (m == -INFINITY) ? 0.f : fast_exp2(m - Mx);
+    o_acc += __ldcg(&part_o[i2 * 128 + d]) * w;
+    l_acc += __ldcg(&part_ml[i2 * 2 + 1]) * w;
+  }
+  att_out[h * 128 + d] = __float2bfloat16_rn(o_acc / l_acc);
 }
 
 __global__ void __launch_bounds__(128)
@@ -415,6 +443,7 @@ size_t merlin_decode_workspace_bytes(int hidden, int intermediate, int heads, in
   b += static_cast<size_t>(hidden) * 2 * 3;                         // q, att, xn/spare
   b += static_cast<size_t>(intermediate) * 2;                       // mlp mid
   b += static_cast<size_t>(heads) * n_splits * (128 + 2) * 4;       // flash-decode partials
+  b += static_cast<size_t>(heads) * 4;                              // per-head arrival tickets
   return (b + 255) / 256 * 256 + 1024;
 }
 
@@ -439,6 +468,15 @@ int merlin_decode_step(void* stream, const merlin_decoder_weights* w, void* x, c
   __nv_bfloat16* mid = xn + D;
   float* part_o = reinterpret_cast<float*>(ws + ((static_cast<size_t>(3 * D + FF) * 2 + 255) / 256 * 256));
   float* part_ml = part_o + static_cast<size_t>(H) * n_splits * 128;
+  unsigned int* tickets = reinterpret_cast<unsigned int*>(part_ml + static_cast<size_t>(H) * n_splits * 2);
+  {
+    // the per-head arrival counters must start at zero once; they reset themselves afterwards
+    static thread_local void* zeroed_ws = nullptr;
+    if (zeroed_ws != workspace) {
+      MB_CHECK_CUDA(cudaMemsetAsync(tickets, 0, static_cast<size_t>(H) * sizeof(unsigned int), st));
+      zeroed_ws = workspace;
+    }
+  }
   __nv_bfloat16* xb = static_cast<__nv_bfloat16*>(x);
   const float scale_log2e = 1.4426950408889634f / sqrtf(128.f);
   int rc;
@@ -463,10 +501,7 @@ int merlin_decode_step(void* stream, const merlin_decoder_weights* w, void* x, c
       cudaLaunchConfig_t cfg = pdl_config(dim3(H, n_splits), dim3(kFdThreads), 0, st);
       MB_CHECK_CUDA(cudaLaunchKernelEx(&cfg, flash_decode_partial_kernel, static_cast<const __nv_bfloat16*>(qbuf),
                                        static_cast<const __nv_bfloat16*>(w->kv_cache[i]), pos_dev, D, n_splits,
-                                       scale_log2e, part_o, part_ml));
-      cudaLaunchConfig_t cfg2 = pdl_config(dim3(H), dim3(128), 0, st);
-      MB_CHECK_CUDA(cudaLaunchKernelEx(&cfg2, flash_decode_combine_kernel, static_cast<const float*>(part_o),
-                                       static_cast<const float*>(part_ml), n_splits, att));
+                                       scale_log2e, part_o, part_ml, tickets, att));
     }
     // x += o_proj(att)
     GemvParams po = {};

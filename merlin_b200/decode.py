@@ -50,7 +50,7 @@ class DecodeRunner:
         self.n_out = torch.zeros(1, dtype=torch.int32, device=dev)
         self.out_ids = torch.zeros(max(cache.capacity, 16), dtype=torch.int64, device=dev)
         self.graph = None
-        self.launches_per_step = 5 * L + 1 + 2 * L  # gemv x4 + flash partial/combine per layer + lm_head
+        self.launches_per_step = 5 * L + 1  # 4 GEMVs + 1 flash-decode per layer, + lm_head
 
     # -- one decoder pass for an externally supplied embedding (used by forward(past_key_values=...))
     def step_logits(self, embeds: torch.Tensor) -> torch.Tensor:
