@@ -126,7 +126,29 @@ def make_case(ref, name: str, cfg: O.OracleConfig, batch, gen_tokens: int):
     close(ours["logits"][valid], out.logits[valid], "logits")
     close(ours["loss"], out.loss, "loss", tol=1e-5)
 
-    gold = dict(name=name, cfg=cfg.__dict__, weights_sha256=sha(sd), seed=0,
+    # ---- backward: the reference's own autograd (loss.backward() through the real modules) pins the
+    # oracle's autograd, which in turn is what the CUDA backward is tested against
+    model.zero_grad()
+    out_b = model(input_ids=batch["input_ids"], attention_mask=batch["attention_mask"], labels=batch["labels"],
+                  images=batch["images"], use_cache=False)
+    out_b.loss.backward()
+    ref_grads = {k: p.grad.detach().clone() for k, p in model.named_parameters() if p.grad is not None}
+    leaves = {k: v.clone().requires_grad_(True) for k, v in sd.items()}
+    O.forward(leaves, cfg, batch["input_ids"], batch["attention_mask"], batch["labels"], batch["images"])["loss"].backward()
+    worst = 0.0
+    for k, gr in ref_grads.items():
+        go = leaves[k].grad
+        assert go is not None, f"oracle has no gradient for {k}"
+        scale = gr.abs().max().item()
+        err = (go - gr).abs().max().item()
+        worst = max(worst, err / (scale + 1e-12) if scale > 1e-7 else 0.0)
+        assert err <= 1e-4 * max(scale, 1e-6) + 1e-8, f"oracle autograd deviates from the reference on {k}: {err} vs {scale}"
+    print(f"  {name}: {len(ref_grads)} parameter gradients: oracle autograd == reference autograd (worst rel {worst:.2e})")
+    grad_probe = {k: ref_grads[k].flatten()[:64].clone() for k in sorted(ref_grads)[::7]}
+    grad_norms = {k: float(g.norm()) for k, g in ref_grads.items()}
+
+    gold = dict(name=name, cfg=cfg.__dict__, weights_sha256=sha(sd), seed=0, ref_grad_probe=grad_probe,
+                ref_grad_norms=grad_norms,
                 input_ids=batch["input_ids"], labels=batch["labels"], attention_mask=batch["attention_mask"],
                 images=[im.clone() for im in batch["images"]],
                 ref_loss=out.loss.detach().clone(), ref_logits=out.logits.detach().clone(),

@@ -96,3 +96,19 @@ def test_llrd_param_groups_follow_reference_rules():
     assert by_name[names[3][0]]["lr"] == pytest.approx(1e-3 * 0.9 ** 2) and by_name[names[3][0]]["weight_decay"] == 0.0
     assert by_name[names[4][0]]["lr"] == pytest.approx(1e-4)
     assert by_name[names[5][0]]["weight_decay"] == 0.05
+
+
+@pytest.mark.parametrize("name", CASES)
+def test_oracle_autograd_matches_reference_golden(name):
+    """The reference's own loss.backward() (recorded by make_golden.py) pins the oracle's autograd, which
+    is what the CUDA backward schedule is checked against on the GPU."""
+    g, cfg = load_golden(name)
+    sd = O.init_state_dict(cfg, seed=0)
+    leaves = {k: v.clone().requires_grad_(True) for k, v in sd.items()}
+    O.forward(leaves, cfg, g["input_ids"], g["attention_mask"], g["labels"], g["images"])["loss"].backward()
+    assert len(g["ref_grad_norms"]) >= 70
+    for k, norm in g["ref_grad_norms"].items():
+        assert leaves[k].grad is not None
+        assert float(leaves[k].grad.norm()) == pytest.approx(norm, rel=1e-4, abs=1e-7), k
+    for k, probe in g["ref_grad_probe"].items():
+        torch.testing.assert_close(leaves[k].grad.flatten()[:64], probe, rtol=1e-4, atol=1e-7)
