@@ -295,6 +295,25 @@ class MMGPTLlamaForCausalLM(nn.Module, MMGPTMetaForCausalLM):
         cfg = self.config.to_dict() if hasattr(self.config, "to_dict") else dict(self.config.__dict__)
         json.dump(cfg, open(os.path.join(save_directory, "config.json"), "w"), indent=2, default=str)
 
+    @staticmethod
+    def _read_checkpoint(path: str):
+        """State dict from pytorch_model.bin, its sharded index, or safetensors files in `path`."""
+        idx = os.path.join(path, "pytorch_model.bin.index.json")
+        single = os.path.join(path, "pytorch_model.bin")
+        sd = {}
+        if os.path.exists(idx):
+            for fname in sorted(set(json.load(open(idx))["weight_map"].values())):
+                sd.update(torch.load(os.path.join(path, fname), map_location="cpu"))
+        elif os.path.exists(single):
+            sd = torch.load(single, map_location="cpu")
+        else:
+            st = [f for f in sorted(os.listdir(path)) if f.endswith(".safetensors")] if os.path.isdir(path) else []
+            if st:
+                from safetensors.torch import load_file
+                for f in st:
+                    sd.update(load_file(os.path.join(path, f)))
+        return sd
+
     @classmethod
     def from_pretrained(cls, path: str, config=None, **_):
         if config is None:
@@ -302,10 +321,12 @@ class MMGPTLlamaForCausalLM(nn.Module, MMGPTMetaForCausalLM):
             raw = {k: v for k, v in raw.items() if k not in ("model_type", "architectures", "transformers_version")}
             config = MMGPTConfig(**raw)
         model = cls(config)
-        f = os.path.join(path, "pytorch_model.bin")
-        if os.path.exists(f):
-            sd = torch.load(f, map_location="cpu")
+        sd = cls._read_checkpoint(path)
+        if sd:
             llm = {k: v for k, v in sd.items() if "vision_tower" not in k and "projector" not in k}
+            vocab = llm["model.embed_tokens.weight"].shape[0]
+            if vocab != config.vocab_size:           # checkpoint saved after the image tokens were added
+                model.resize_token_embeddings(vocab)
             model.load_state_dict(llm, strict=False)
         return model
 

@@ -55,3 +55,31 @@ def build_product_model(cfg: O.OracleConfig, sd, device="cuda"):
         model.to(device=device, dtype=torch.bfloat16)
     model.eval()
     return model
+
+
+class FakeTokenizer:
+    """Duck-typed stand-in for the sentencepiece tokenizer (no tokenizer files exist offline): the
+    subset of the HF tokenizer API that build_model_tokenizer / build_vision_tokenizer touch."""
+
+    def __init__(self, base_vocab: int, extra=()):
+        self.vocab = {f"tok{i}": i for i in range(base_vocab)}
+        self.vocab["<unk>"] = 0
+        self.unk_token, self.pad_token = "<unk>", None
+        self.unk_token_id = 0
+        self.model_max_length = 2048
+        for t in extra:
+            self.add_tokens([t], special_tokens=True)
+
+    def __len__(self):
+        return len(set(self.vocab.values()))
+
+    def add_tokens(self, tokens, special_tokens=False):
+        added = 0
+        for t in tokens:
+            if t not in self.vocab:
+                self.vocab[t] = len(self)
+                added += 1
+        return added
+
+    def convert_tokens_to_ids(self, tokens):
+        return [self.vocab[t] for t in tokens]

@@ -124,3 +124,52 @@ def test_forward_without_cuda_fails_loudly():
     model = build_product_model(cfg, O.init_state_dict(cfg, seed=0), device=None)
     with pytest.raises(RuntimeError):
         model(input_ids=g["input_ids"], images=g["images"])
+
+
+def test_build_model_tokenizer_from_checkpoint(tmp_path):
+    """builder.py contract: config + checkpoint + tokenizer in, assembled model out; tower / projector
+    slices are picked out of the same pytorch_model.bin by their key prefixes; freezing policy applied."""
+    import json
+    from types import SimpleNamespace
+    from helpers import FakeTokenizer
+    from merlin_b200.mmgpt.model.builder import build_model_tokenizer
+    from merlin_b200.mmgpt.utils.arguments import DataArguments, ModelArguments
+    from merlin_b200.mmgpt.utils.constants import (DEFAULT_IM_END_TOKEN, DEFAULT_IM_PATCH_TOKEN,
+                                                   DEFAULT_IM_START_TOKEN)
+    g, cfg = load_golden("tiny_conv")
+    sd = O.init_state_dict(cfg, seed=0)
+    torch.save(sd, tmp_path / "pytorch_model.bin")
+    json.dump(dict(vocab_size=cfg.vocab_size, hidden_size=cfg.hidden_size, intermediate_size=cfg.intermediate_size,
+                   num_hidden_layers=cfg.num_layers, num_attention_heads=cfg.num_heads,
+                   num_key_value_heads=cfg.num_heads, rms_norm_eps=cfg.rms_norm_eps, rope_theta=cfg.rope_theta,
+                   max_position_embeddings=4096, tie_word_embeddings=False), open(tmp_path / "config.json", "w"))
+    vcfg = SimpleNamespace(hidden_size=cfg.vit_hidden, intermediate_size=cfg.vit_intermediate,
+                           num_hidden_layers=cfg.vit_layers, num_attention_heads=cfg.vit_heads,
+                           image_size=cfg.image_size, patch_size=cfg.patch_size, hidden_act="quick_gelu",
+                           layer_norm_eps=cfg.vit_ln_eps, num_channels=3)
+    margs = ModelArguments(model_name_or_path=str(tmp_path), vision_tower="clip-synthetic", projector="conv",
+                           conv_stride=2, freeze_lm_model=True, freeze_vision_tower=False, freeze_projector=False)
+    dargs = DataArguments()
+    targs = SimpleNamespace(model_max_length=2048, bf16=True, fp16=False, lora_enable=False, device="cpu",
+                            cache_dir=None, gradient_checkpointing=False)
+    tok = FakeTokenizer(256, extra=(DEFAULT_IM_PATCH_TOKEN, DEFAULT_IM_START_TOKEN, DEFAULT_IM_END_TOKEN))
+    model, tok2, dargs2 = build_model_tokenizer(margs, dargs, targs, tokenizer=tok, vision_config=vcfg)
+    assert tok2.pad_token == tok2.unk_token and len(tok2) == cfg.vocab_size
+    assert (model.im_patch_token, model.im_start_token, model.im_end_token) == (256, 257, 258)
+    assert dargs2.image_token_len == cfg.num_patches and dargs2.use_im_start_end
+    assert model.dtype == torch.bfloat16
+    back = model.state_dict()
+    for k, v in sd.items():                     # weights (LLM + tower + projector) came from the checkpoint
+        assert torch.equal(back[k].float(), v), k
+    m = model.model
+    assert not m.qkv_w[0].requires_grad and m.embed_tokens.requires_grad and not model.lm_head_w.requires_grad
+    assert m.vision_tower.qkv_w[0].requires_grad and not m.vision_tower.qkv_w[cfg.vit_layers - 1].requires_grad
+    assert m.projector.weight.requires_grad
+    # a fresh tokenizer (image tokens not yet present) grows the vocabulary and mean-initialises the new rows
+    tok3 = FakeTokenizer(256)
+    model3, _, _ = build_model_tokenizer(margs, DataArguments(), targs, tokenizer=tok3, vision_config=vcfg)
+    e = model3.model.embed_tokens.float()
+    assert model3.num_new_tokens == 2 and e.shape[0] == 259
+    assert torch.allclose(e[-1], e[:-2].mean(0), atol=1e-2)
+    with pytest.raises(NotImplementedError):
+        build_model_tokenizer(SimpleNamespace(**{**margs.__dict__, "model_name_or_path": "x/baichuan-7b"}), dargs, targs)
