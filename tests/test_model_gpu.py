@@ -166,3 +166,30 @@ def test_operator_seam_in_hf_llama_matches_eager():
         got = m(input_ids=ids, attention_mask=mask).last_hidden_state.float()
     valid = mask.bool()
     assert (got[valid] - ref[valid]).abs().max().item() <= 2.0 ** -5 * ref[valid].abs().max().item()
+
+
+def test_full_width_c1_sample_matches_oracle():
+    """BASELINE config[0] shape at full WIDTH: one 336 px image through the real CLIP-L/14-336 dims (24 layers,
+    23 used), ConvProjector(1024 -> 4096, stride 2) -> 144 visual tokens, 32-token caption, Vicuna-7B width
+    (D=4096, FF=11008, H=32, V=32003) with the decoder depth cut to 2 layers so the fp32 CPU oracle runs in
+    seconds.  Every kernel runs at its production shape; logits (|ref| up to ~3, where one bf16 ulp of the
+    output is 1.6e-2) must agree within 2^-6·max|ref|, the loss within 2e-3, image features within 2^-6."""
+    cfg = O.OracleConfig(num_layers=2)
+    sd = O.init_state_dict(cfg, seed=0)
+    batch = O.synthetic_batch(cfg, 1, 181, [1], seed=1234)
+    ref = O.forward(sd, cfg, batch["input_ids"], batch["attention_mask"], batch["labels"], batch["images"])
+    model = build_product_model(cfg, sd)
+    out = model(input_ids=batch["input_ids"].to(DEV), attention_mask=batch["attention_mask"].to(DEV),
+                labels=batch["labels"].to(DEV), images=to_dev(batch["images"]))
+    logits = out.logits.float().cpu()
+    scale = ref["logits"].abs().max().item()
+    err = (logits - ref["logits"]).abs().max().item()
+    assert err <= 2.0 ** -6 * scale, f"logits max|Δ|={err:.4g} vs max|ref|={scale:.4g}"
+    assert abs(out.loss.item() - ref["loss"].item()) <= 2e-3
+    feats = model.encode_images(to_dev(batch["images"]))[0].float().cpu()
+    rf = ref["image_features"][0]
+    assert (feats - rf).abs().max().item() <= 2.0 ** -6 * rf.abs().max().item()
+    # greedy continuation: same tokens as the oracle for 4 steps
+    gen = model.generate(batch["input_ids"].to(DEV), images=to_dev(batch["images"]), max_new_tokens=4, eos_token_id=None)
+    want = O.greedy_generate(sd, cfg, batch["input_ids"], batch["images"], 4, eos_token_id=None)
+    assert torch.equal(gen.cpu(), want)
