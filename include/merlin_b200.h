@@ -195,6 +195,30 @@ size_t merlin_vit_layer_workspace_bytes(int M, int d, int ff);
 int merlin_vit_layer_forward(void* stream, const merlin_vit_layer_weights* w, void* h, void* workspace, int n_img,
                              int tokens, int d, int heads, int ff, float eps, int cta_group);
 
+/* Training forms of the decoder layer.  `saved` (merlin_decoder_layer_saved_bytes) keeps x_in, xn1, qkv, att,
+ * x_mid, xn2, gate_up, mid and lse in that order (x_in first: a layer may write its output directly into the
+ * next layer's saved block).  backward: dx [B*S, D] holds dL/dx_out on entry and dL/dx_in on return; weight
+ * gradients go to the bf16 tensors of `g` (overwritten, or accumulated when accumulate != 0), the two norm
+ * weights accumulate into fp32 [D] buffers.  Autograd of HF LlamaDecoderLayer + the flash-attn patch. */
+typedef struct merlin_layer_saved {
+  void *x_in, *xn1, *qkv, *att, *x_mid, *xn2, *gate_up, *mid;
+  float* lse;
+} merlin_layer_saved;
+typedef struct merlin_layer_grads {
+  void *qkv_w, *o_w, *gate_up_w, *down_w;
+  float *ln1_w_f32, *ln2_w_f32;
+} merlin_layer_grads;
+size_t merlin_decoder_layer_saved_bytes(int M, int D, int FF, int H, int B, int S);
+int merlin_decoder_layer_forward_train(void* stream, const merlin_layer_weights* w, const void* x, void* x_out,
+                                       void* saved, const float* rope_cos, const float* rope_sin,
+                                       const int* seqlens, int B, int S, int D, int H, int FF, float eps,
+                                       int cta_group);
+size_t merlin_decoder_layer_backward_workspace_bytes(int M, int D, int FF, int H, int B, int S);
+int merlin_decoder_layer_backward(void* stream, const merlin_layer_weights* w, const merlin_layer_grads* g,
+                                  void* saved, void* dx, void* workspace, const float* rope_cos,
+                                  const float* rope_sin, const int* seqlens, int B, int S, int D, int H, int FF,
+                                  float eps, int accumulate, int cta_group);
+
 /* ---- backward / optimizer (training path; autograd of the ops above + the step loop of
  * mmgpt/engine/train/trainer.py:45-74 with mmgpt/utils/llrd_utils.py param groups) ---- */
 

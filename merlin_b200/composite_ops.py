@@ -50,3 +50,22 @@ def vit_layer_forward(h, ws, tower, j: int, n_img: int, cta_group: int = 2):
                                                    h.data_ptr(), ws.data_ptr(), n_img, tower.tokens, c.hidden_size,
                                                    c.num_attention_heads, c.intermediate_size,
                                                    float(c.layer_norm_eps), cta_group), "merlin_vit_layer_forward")
+
+
+def decoder_layer_forward_train(w, x, x_out, saved, cos, sin, seqlens, B, S, D, H, FF, eps, cta_group: int = 2):
+    from . import ops
+    ops.PROFILE.launches += 8
+    ops.check(_lib.load().merlin_decoder_layer_forward_train(
+        torch.cuda.current_stream().cuda_stream, ctypes.byref(w), x.data_ptr(), x_out.data_ptr(), saved.data_ptr(),
+        cos.data_ptr(), sin.data_ptr(), None if seqlens is None else seqlens.data_ptr(), B, S, D, H, FF, float(eps),
+        cta_group), "merlin_decoder_layer_forward_train")
+
+
+def decoder_layer_backward(w, grads, saved, dx, ws, cos, sin, seqlens, B, S, D, H, FF, eps, accumulate,
+                           cta_group: int = 2):
+    from . import ops
+    ops.PROFILE.launches += 17
+    ops.check(_lib.load().merlin_decoder_layer_backward(
+        torch.cuda.current_stream().cuda_stream, ctypes.byref(w), ctypes.byref(grads), saved.data_ptr(), dx.data_ptr(),
+        ws.data_ptr(), cos.data_ptr(), sin.data_ptr(), None if seqlens is None else seqlens.data_ptr(), B, S, D, H, FF,
+        float(eps), int(bool(accumulate)), cta_group), "merlin_decoder_layer_backward")

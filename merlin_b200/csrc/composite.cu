@@ -87,3 +87,124 @@ int merlin_vit_layer_forward(void* stream, const merlin_vit_layer_weights* w, vo
 }
 
 }  // extern "C"
+
+// =====================================================================================================
+// Training forms: one call per decoder layer for forward-with-save and for backward.  The caller owns
+// the saved-activation buffers (persistent across steps) and a workspace; the schedule is the one of
+// mmgpt/engine/train/trainer.py (merlin_b200) and autograd of HF LlamaDecoderLayer in the reference.
+// =====================================================================================================
+extern "C" {
+
+size_t merlin_decoder_layer_saved_bytes(int M, int D, int FF, int H, int B, int S) {
+  // x_in, xn1, att, x_mid, xn2 [M,D]; qkv [M,3D]; gu [M,2FF]; mid [M,FF]  (bf16) + lse [B,H,S] fp32
+  const size_t bf16 = static_cast<size_t>(M) * (5 * static_cast<size_t>(D) + 3 * D + 3 * FF) * 2;
+  return bf16 + static_cast<size_t>(B) * H * S * 4 + 1024;
+}
+
+static void layout_saved(void* saved, int M, int D, int FF, merlin_layer_saved* s) {
+  __nv_bfloat16* p = static_cast<__nv_bfloat16*>(saved);
+  const size_t md = static_cast<size_t>(M) * D;
+  s->x_in = p;              p += md;
+  s->xn1 = p;               p += md;
+  s->qkv = p;               p += 3 * md;
+  s->att = p;               p += md;
+  s->x_mid = p;             p += md;
+  s->xn2 = p;               p += md;
+  s->gate_up = p;           p += static_cast<size_t>(M) * 2 * FF;
+  s->mid = p;               p += static_cast<size_t>(M) * FF;
+  s->lse = reinterpret_cast<float*>((reinterpret_cast<uintptr_t>(p) + 255) & ~static_cast<uintptr_t>(255));
+}
+
+int merlin_decoder_layer_forward_train(void* stream, const merlin_layer_weights* w, const void* x, void* x_out,
+                                       void* saved, const float* rope_cos, const float* rope_sin,
+                                       const int* seqlens, int B, int S, int D, int H, int FF, float eps,
+                                       int cta_group) {
+  MB_CHECK_ARG(w && x && x_out && saved && rope_cos && rope_sin, "decoder_layer_forward_train: null argument");
+  MB_CHECK_ARG(D == H * 128 && FF % 128 == 0, "decoder_layer_forward_train: needs head_dim 128, FF %% 128 == 0");
+  const int M = B * S;
+  merlin_layer_saved s;
+  layout_saved(saved, M, D, FF, &s);
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  int rc;
+  if (x != s.x_in)  // the previous layer can write its output straight into this layer's x_in slot
+    MB_CHECK_CUDA(cudaMemcpyAsync(s.x_in, x, static_cast<size_t>(M) * D * 2, cudaMemcpyDeviceToDevice, st));
+  if ((rc = merlin_rmsnorm(stream, s.x_in, D, w->ln1_w, s.xn1, D, M, D, eps)) != MERLIN_OK) return rc;
+  if ((rc = merlin_gemm_qkv_rope(stream, s.xn1, D, w->qkv_w, D, s.qkv, 3 * D, rope_cos, rope_sin, nullptr, M, 3 * D,
+                                 D, 2 * D, S, cta_group)) != MERLIN_OK)
+    return rc;
+  if ((rc = merlin_flash_attn_fwd(stream, s.qkv, 3 * D, s.att, D, s.lse, seqlens, B, S, H, 128, 1, 0.f)) != MERLIN_OK)
+    return rc;
+  if ((rc = merlin_gemm_bf16(stream, s.att, D, w->o_w, D, s.x_mid, D, s.x_in, D, nullptr, M, D, D,
+                             MERLIN_EPI_RESIDUAL, cta_group)) != MERLIN_OK)
+    return rc;
+  if ((rc = merlin_rmsnorm(stream, s.x_mid, D, w->ln2_w, s.xn2, D, M, D, eps)) != MERLIN_OK) return rc;
+  if ((rc = merlin_gemm_bf16(stream, s.xn2, D, w->gate_up_w, D, s.gate_up, 2 * FF, nullptr, 0, nullptr, M, 2 * FF, D,
+                             MERLIN_EPI_STORE, cta_group)) != MERLIN_OK)
+    return rc;
+  if ((rc = merlin_swiglu_fwd(stream, s.gate_up, s.mid, M, FF)) != MERLIN_OK) return rc;
+  return merlin_gemm_bf16(stream, s.mid, FF, w->down_w, FF, x_out, D, s.x_mid, D, nullptr, M, D, FF,
+                          MERLIN_EPI_RESIDUAL, cta_group);
+}
+
+size_t merlin_decoder_layer_backward_workspace_bytes(int M, int D, int FF, int H, int B, int S) {
+  // dmid [M,FF] + dxn [M,D] + dx_mid [M,D] + datt [M,D] + dqkv [M,3D] (bf16) + attention-backward scratch
+  return static_cast<size_t>(M) * (static_cast<size_t>(FF) + 6 * D) * 2 +
+         merlin_flash_attn_bwd_workspace_bytes(B, S, H, 128) + 2048;
+}
+
+int merlin_decoder_layer_backward(void* stream, const merlin_layer_weights* w, const merlin_layer_grads* g,
+                                  void* saved, void* dx, void* workspace, const float* rope_cos,
+                                  const float* rope_sin, const int* seqlens, int B, int S, int D, int H, int FF,
+                                  float eps, int accumulate, int cta_group) {
+  MB_CHECK_ARG(w && g && saved && dx && workspace, "decoder_layer_backward: null argument");
+  const int M = B * S;
+  merlin_layer_saved s;
+  layout_saved(saved, M, D, FF, &s);
+  __nv_bfloat16* dmid = static_cast<__nv_bfloat16*>(workspace);
+  __nv_bfloat16* dxn = dmid + static_cast<size_t>(M) * FF;
+  __nv_bfloat16* dx_mid = dxn + static_cast<size_t>(M) * D;
+  __nv_bfloat16* datt = dx_mid + static_cast<size_t>(M) * D;
+  __nv_bfloat16* dqkv = datt + static_cast<size_t>(M) * D;
+  void* attn_ws = reinterpret_cast<void*>((reinterpret_cast<uintptr_t>(dqkv + static_cast<size_t>(M) * 3 * D) + 255) &
+                                          ~static_cast<uintptr_t>(255));
+  const int epi = accumulate ? MERLIN_EPI_RESIDUAL : MERLIN_EPI_STORE;
+  int rc;
+  // ---- MLP: x_out = x_mid + down(silu(g)·u)
+  if ((rc = merlin_gemm_bf16_ex(stream, dx, D, 0, w->down_w, FF, 1, dmid, FF, nullptr, 0, nullptr, M, FF, D,
+                                MERLIN_EPI_STORE, cta_group)) != MERLIN_OK)
+    return rc;
+  if ((rc = merlin_gemm_bf16_ex(stream, dx, D, 1, s.mid, FF, 1, g->down_w, FF, g->down_w, FF, nullptr, D, FF, M, epi,
+                                cta_group)) != MERLIN_OK)
+    return rc;
+  if ((rc = merlin_swiglu_bwd(stream, s.gate_up, dmid, s.gate_up, M, FF)) != MERLIN_OK) return rc;   // dgu in place
+  if ((rc = merlin_gemm_bf16_ex(stream, s.gate_up, 2 * FF, 1, s.xn2, D, 1, g->gate_up_w, D, g->gate_up_w, D, nullptr,
+                                2 * FF, D, M, epi, cta_group)) != MERLIN_OK)
+    return rc;
+  if ((rc = merlin_gemm_bf16_ex(stream, s.gate_up, 2 * FF, 0, w->gate_up_w, D, 1, dxn, D, nullptr, 0, nullptr, M, D,
+                                2 * FF, MERLIN_EPI_STORE, cta_group)) != MERLIN_OK)
+    return rc;
+  if ((rc = merlin_rmsnorm_bwd(stream, s.x_mid, w->ln2_w, dxn, dx, dx_mid, g->ln2_w_f32, M, D, eps)) != MERLIN_OK)
+    return rc;
+  // ---- attention: x_mid = x_in + o_proj(attn(rope(qkv(norm(x_in)))))
+  if ((rc = merlin_gemm_bf16_ex(stream, dx_mid, D, 0, w->o_w, D, 1, datt, D, nullptr, 0, nullptr, M, D, D,
+                                MERLIN_EPI_STORE, cta_group)) != MERLIN_OK)
+    return rc;
+  if ((rc = merlin_gemm_bf16_ex(stream, dx_mid, D, 1, s.att, D, 1, g->o_w, D, g->o_w, D, nullptr, D, D, M, epi,
+                                cta_group)) != MERLIN_OK)
+    return rc;
+  if ((rc = merlin_flash_attn_bwd(stream, s.qkv, 3 * D, s.att, datt, D, s.lse, seqlens, dqkv, 3 * D, attn_ws, B, S, H,
+                                  128, 1, 0.f)) != MERLIN_OK)
+    return rc;
+  if ((rc = merlin_rope_qk_inplace_ex(stream, dqkv, 3 * D, rope_cos, rope_sin, nullptr, M, H, S, 1)) != MERLIN_OK)
+    return rc;
+  if ((rc = merlin_gemm_bf16_ex(stream, dqkv, 3 * D, 1, s.xn1, D, 1, g->qkv_w, D, g->qkv_w, D, nullptr, 3 * D, D, M,
+                                epi, cta_group)) != MERLIN_OK)
+    return rc;
+  if ((rc = merlin_gemm_bf16_ex(stream, dqkv, 3 * D, 0, w->qkv_w, D, 1, dxn, D, nullptr, 0, nullptr, M, D, 3 * D,
+                                MERLIN_EPI_STORE, cta_group)) != MERLIN_OK)
+    return rc;
+  // dx (in place) = dx_mid + rmsnorm'(dxn)
+  return merlin_rmsnorm_bwd(stream, s.x_in, w->ln1_w, dxn, dx_mid, dx, g->ln1_w_f32, M, D, eps);
+}
+
+}  // extern "C"

@@ -86,7 +86,17 @@ class VitLayerWeights(ctypes.Structure):
 _PROTOTYPES["merlin_decoder_layer_forward"] = [_P, _P, _P, _P, _P, _P, _P, _P, c_int64, c_int, c_int, c_int, c_int,
                                                c_int, c_float, c_int]
 _PROTOTYPES["merlin_vit_layer_forward"] = [_P, _P, _P, _P, c_int, c_int, c_int, c_int, c_int, c_float, c_int]
-_SIZE_FNS = {"merlin_decode_workspace_bytes": [c_int, c_int, c_int, c_int],
+class LayerGrads(ctypes.Structure):
+    """struct merlin_layer_grads."""
+    _fields_ = [(n, c_void_p) for n in ("qkv_w", "o_w", "gate_up_w", "down_w", "ln1_w_f32", "ln2_w_f32")]
+
+
+_PROTOTYPES["merlin_decoder_layer_forward_train"] = [_P, _P, _P, _P, _P, _P, _P, _P, c_int, c_int, c_int, c_int, c_int,
+                                                     c_float, c_int]
+_PROTOTYPES["merlin_decoder_layer_backward"] = [_P, _P, _P, _P, _P, _P, _P, _P, _P, c_int, c_int, c_int, c_int, c_int,
+                                                c_float, c_int, c_int]
+_SIZE_FNS = {"merlin_decoder_layer_saved_bytes": [c_int, c_int, c_int, c_int, c_int, c_int],
+             "merlin_decoder_layer_backward_workspace_bytes": [c_int, c_int, c_int, c_int, c_int, c_int],"merlin_decode_workspace_bytes": [c_int, c_int, c_int, c_int],
              "merlin_flash_attn_bwd_workspace_bytes": [c_int, c_int, c_int, c_int],
              "merlin_decoder_layer_workspace_bytes": [c_int, c_int, c_int],
              "merlin_vit_layer_workspace_bytes": [c_int, c_int, c_int]}

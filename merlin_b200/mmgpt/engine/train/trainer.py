@@ -27,6 +27,7 @@ from typing import Dict, List, Optional
 import torch
 
 from .... import ops
+from .... import lib as _lib
 from ....lib import EPI_RESIDUAL
 from ...utils.constants import IGNORE_INDEX
 from ...utils.llrd_utils import llm_lr_scale_func, param_hyper, vit_lr_scale_func
@@ -132,19 +133,15 @@ class MMGPTTrainer:
                                       feat_limit, return_rank=True)
 
         cos, sin = m.rope_tables(S)
-        saved = []
+        # one library call per layer (merlin_decoder_layer_forward_train); activations live in persistent
+        # per-layer blocks whose first slot is x_in, so layer i writes its output straight into block i+1
+        bufs = self._layer_buffers(B, S)
+        x_final = bufs["x_final"]
         for i in range(L):
-            x_in = x
-            xn1 = ops.rmsnorm(x_in, m.ln1_w[i], cfg.rms_norm_eps)
-            qkv = ops.gemm_qkv_rope(xn1, m.qkv_w[i], cos, sin, S)
-            att, lse = ops.flash_attn(qkv, B, S, H, 128, causal=True, seqlens=seqlens, return_lse=True)
-            x_mid = ops.gemm(att, m.o_w[i], residual=x_in, epilogue=EPI_RESIDUAL)
-            xn2 = ops.rmsnorm(x_mid, m.ln2_w[i], cfg.rms_norm_eps)
-            gu = ops.gemm(xn2, m.gate_up_w[i])
-            mid = ops.swiglu_fwd(gu)
-            x = ops.gemm(mid, m.down_w[i], residual=x_mid, epilogue=EPI_RESIDUAL)
-            saved.append((x_in, xn1, qkv, att, lse, x_mid, xn2, gu, mid))
-        x_final = x
+            x_src = x if i == 0 else bufs["saved"][i]
+            x_dst = bufs["saved"][i + 1] if i + 1 < L else x_final
+            ops.decoder_layer_forward_train(self._layer_weights(i), x_src, x_dst, bufs["saved"][i], cos, sin, seqlens,
+                                            B, S, D, H, cfg.intermediate_size, cfg.rms_norm_eps)
         hn = ops.rmsnorm(x_final, m.norm_w, cfg.rms_norm_eps)
         logits = ops.gemm(hn, model.lm_head_w)
 
@@ -156,24 +153,13 @@ class MMGPTTrainer:
         dx = ops.rmsnorm_bwd(x_final, m.norm_w, dhn, None, self._f32["model.norm.weight"], cfg.rms_norm_eps)
         self._ready_after("model.norm.weight")
         for i in reversed(range(L)):
-            x_in, xn1, qkv, att, lse, x_mid, xn2, gu, mid = saved[i]
             p = f"model.layers.{i}."
-            dmid = ops.gemm_nt(dx, m.down_w[i])
-            ops.gemm_tn(dx, mid, out=g(p + "mlp.down_proj.weight"), accumulate=acc)
-            dgu = ops.swiglu_bwd(gu, dmid, out=gu)
-            ops.gemm_tn(dgu, xn2, out=g(p + "mlp.gate_up_proj.weight"), accumulate=acc)
-            dxn2 = ops.gemm_nt(dgu, m.gate_up_w[i])
-            dx_mid = ops.rmsnorm_bwd(x_mid, m.ln2_w[i], dxn2, dx, self._f32[p + "post_attention_layernorm.weight"],
-                                     cfg.rms_norm_eps)
-            datt = ops.gemm_nt(dx_mid, m.o_w[i])
-            ops.gemm_tn(dx_mid, att, out=g(p + "self_attn.o_proj.weight"), accumulate=acc)
-            dqkv = ops.flash_attn_bwd(qkv, att, datt, lse, B, S, H, 128, causal=True, seqlens=seqlens)
-            ops.rope_qk_inverse_inplace(dqkv, cos, sin, H, S)
-            ops.gemm_tn(dqkv, xn1, out=g(p + "self_attn.qkv_proj.weight"), accumulate=acc)
-            dxn1 = ops.gemm_nt(dqkv, m.qkv_w[i])
-            dx = ops.rmsnorm_bwd(x_in, m.ln1_w[i], dxn1, dx_mid, self._f32[p + "input_layernorm.weight"],
-                                 cfg.rms_norm_eps)
-            saved[i] = None
+            grads = _lib.LayerGrads(g(p + "self_attn.qkv_proj.weight").data_ptr(), g(p + "self_attn.o_proj.weight").data_ptr(),
+                                    g(p + "mlp.gate_up_proj.weight").data_ptr(), g(p + "mlp.down_proj.weight").data_ptr(),
+                                    self._f32[p + "input_layernorm.weight"].data_ptr(),
+                                    self._f32[p + "post_attention_layernorm.weight"].data_ptr())
+            ops.decoder_layer_backward(self._layer_weights(i), grads, bufs["saved"][i], dx, bufs["ws"], cos, sin,
+                                       seqlens, B, S, D, H, cfg.intermediate_size, cfg.rms_norm_eps, acc)
             self._ready_after(p + "input_layernorm.weight")
         # embeddings + projector
         dtable = g("model.embed_tokens.weight") if "model.embed_tokens.weight" in self.arena.offsets else None
@@ -198,6 +184,27 @@ class MMGPTTrainer:
             tower.backward(dhid, tower_saved, g, self._f32, acc, done=self._ready_after)
         self._ready_after(self.names[-1])
         return loss
+
+    def _layer_weights(self, i: int):
+        m = self.model.model
+        return _lib.LayerWeights(m.qkv_w[i].data_ptr(), m.o_w[i].data_ptr(), m.gate_up_w[i].data_ptr(),
+                                 m.down_w[i].data_ptr(), m.ln1_w[i].data_ptr(), m.ln2_w[i].data_ptr())
+
+    def _layer_buffers(self, B: int, S: int):
+        """Persistent activation blocks (one per decoder layer) + backward workspace for this batch shape."""
+        if getattr(self, "_buf_key", None) != (B, S):
+            cfg = self.model.config
+            D, FF, H, L = cfg.hidden_size, cfg.intermediate_size, cfg.num_attention_heads, cfg.num_hidden_layers
+            L_ = _lib.load()
+            dev = self.model.device
+            nbytes = L_.merlin_decoder_layer_saved_bytes(B * S, D, FF, H, B, S)
+            self._bufs = dict(
+                saved=[torch.empty(nbytes, dtype=torch.uint8, device=dev) for _ in range(L)],
+                ws=torch.empty(L_.merlin_decoder_layer_backward_workspace_bytes(B * S, D, FF, H, B, S), dtype=torch.uint8,
+                               device=dev),
+                x_final=torch.empty((B * S, D), dtype=torch.bfloat16, device=dev))
+            self._buf_key = (B, S)
+        return self._bufs
 
     def _ready_after(self, name: str):
         """Gradients of every parameter up to and including `name` (arena order = backward completion

@@ -59,7 +59,8 @@ def _gemm_call(fn, flops, *args):
     return rc
 
 
-from .composite_ops import (decoder_layer_forward as _decoder_layer_forward_c, decoder_layer_workspace,  # noqa: E402
+from .composite_ops import (decoder_layer_backward, decoder_layer_forward_train,  # noqa: E402
+                            decoder_layer_forward as _decoder_layer_forward_c, decoder_layer_workspace,
                             vit_layer_forward, vit_layer_workspace)
 
 
