@@ -165,6 +165,21 @@ size_t merlin_decode_workspace_bytes(int hidden, int intermediate, int heads, in
 int merlin_decode_step(void* stream, const merlin_decoder_weights* w, void* x, const int* pos_dev,
                        void* workspace, void* logits, int n_splits);
 
+/* The same decode step as ONE persistent kernel (one CTA per SM, cooperative launch): a producer warp per
+ * CTA streams that CTA's share of every layer's weight rows and KV-cache tiles through a shared-memory
+ * ring with TMA and runs ahead across layer boundaries while the consumer warps synchronise grid-wide on
+ * the activations.  `workspace` (merlin_decode_stream_workspace_bytes, 256-byte aligned) must first be
+ * bound to the weights and caches with merlin_decode_stream_prepare — it copies the per-layer pointer
+ * tables and one TMA tensor map per cache to the device and synchronises `stream` (not capturable; call it
+ * again whenever a pointer in `w` or kv_capacity changes).  merlin_decode_stream_step is capturable:
+ * x_in[hidden] is the token embedding (read-only, may alias x), x[hidden] receives the final residual
+ * stream, logits[vocab] the lm_head output.  Same reference code as merlin_decode_step. */
+size_t merlin_decode_stream_workspace_bytes(int num_layers, int hidden, int heads, int intermediate);
+int merlin_decode_stream_prepare(void* stream, const merlin_decoder_weights* w, int64_t kv_capacity,
+                                 void* workspace);
+int merlin_decode_stream_step(void* stream, const merlin_decoder_weights* w, const void* x_in, void* x,
+                              const int* pos_dev, void* workspace, void* logits);
+
 /* x[D] = embed_table[*token_dev] (token id read on the device). */
 int merlin_embed_token(void* stream, const void* embed_table, const int64_t* token_dev, void* x, int D,
                        int64_t vocab);

@@ -13,7 +13,18 @@ from . import lib as _lib
 from . import ops as _ops
 from .lib import DecoderWeights, check
 
-N_SPLITS = int(__import__("os").environ.get("MERLIN_FD_SPLITS", "32"))  # flash-decode key splits (x 32 heads CTAs per layer)
+import os
+
+N_SPLITS = int(os.environ.get("MERLIN_FD_SPLITS", "32"))  # flash-decode key splits (x 32 heads CTAs per layer)
+
+
+def decode_mode() -> str:
+    """"stream": the whole token in ONE persistent kernel (csrc/decode_stream.cu); "kernels": one launch
+    per GEMV / attention (csrc/decode.cu).  MERLIN_DECODE overrides the default."""
+    mode = os.environ.get("MERLIN_DECODE", "stream")
+    if mode not in ("stream", "kernels"):
+        raise ValueError(f"MERLIN_DECODE={mode!r}: expected 'stream' or 'kernels'")
+    return mode
 
 
 def _ptr_array(tensors):
@@ -50,7 +61,29 @@ class DecodeRunner:
         self.n_out = torch.zeros(1, dtype=torch.int32, device=dev)
         self.out_ids = torch.zeros(max(cache.capacity, 16), dtype=torch.int64, device=dev)
         self.graph = None
-        self.launches_per_step = 5 * L + 1  # 4 GEMVs + 1 flash-decode per layer, + lm_head
+        self.mode = decode_mode()
+        if self.mode == "stream":
+            sbytes = L_.merlin_decode_stream_workspace_bytes(L, cfg.hidden_size, cfg.num_attention_heads,
+                                                             cfg.intermediate_size)
+            self.stream_ws = torch.empty(sbytes + 256, dtype=torch.uint8, device=dev)
+            off = (-self.stream_ws.data_ptr()) % 256
+            self.stream_ws_ptr = self.stream_ws.data_ptr() + off
+            check(L_.merlin_decode_stream_prepare(torch.cuda.current_stream().cuda_stream, ctypes.byref(self.w),
+                                                  cache.capacity, self.stream_ws_ptr), "merlin_decode_stream_prepare")
+            self.launches_per_step = 1
+        else:
+            self.launches_per_step = 5 * L + 1  # 4 GEMVs + 1 flash-decode per layer, + lm_head
+
+    def _decode_step(self, st):
+        """One decoder pass for the embedding in self.x at position *self.pos -> self.logits."""
+        L_ = _lib.load()
+        if self.mode == "stream":
+            check(L_.merlin_decode_stream_step(st, ctypes.byref(self.w), self.x.data_ptr(), self.x.data_ptr(),
+                                               self.pos.data_ptr(), self.stream_ws_ptr, self.logits.data_ptr()),
+                  "merlin_decode_stream_step")
+        else:
+            check(L_.merlin_decode_step(st, ctypes.byref(self.w), self.x.data_ptr(), self.pos.data_ptr(),
+                                        self.ws.data_ptr(), self.logits.data_ptr(), N_SPLITS), "merlin_decode_step")
 
     # -- one decoder pass for an externally supplied embedding (used by forward(past_key_values=...))
     def step_logits(self, embeds: torch.Tensor) -> torch.Tensor:
@@ -59,10 +92,7 @@ class DecodeRunner:
             raise RuntimeError("KV cache is full")
         self.x.copy_(embeds.reshape(-1))
         self.pos.fill_(self.cache.seq_len)
-        L_ = _lib.load()
-        check(L_.merlin_decode_step(torch.cuda.current_stream().cuda_stream, ctypes.byref(self.w),
-                                    self.x.data_ptr(), self.pos.data_ptr(), self.ws.data_ptr(),
-                                    self.logits.data_ptr(), N_SPLITS), "merlin_decode_step")
+        self._decode_step(torch.cuda.current_stream().cuda_stream)
         self.cache.seq_len += 1
         _ops.PROFILE.launches += self.launches_per_step
         return self.logits
@@ -74,8 +104,7 @@ class DecodeRunner:
         cfg = self.lm.config
         check(L_.merlin_embed_token(st, self.lm.model.embed_tokens.data_ptr(), self.token.data_ptr(),
                                     self.x.data_ptr(), cfg.hidden_size, cfg.vocab_size), "merlin_embed_token")
-        check(L_.merlin_decode_step(st, ctypes.byref(self.w), self.x.data_ptr(), self.pos.data_ptr(),
-                                    self.ws.data_ptr(), self.logits.data_ptr(), N_SPLITS), "merlin_decode_step")
+        self._decode_step(st)
         check(L_.merlin_argmax(st, self.logits.data_ptr(), self.logits.stride(0), 1, cfg.vocab_size,
                                self.token.data_ptr()), "merlin_argmax")
         check(L_.merlin_record_advance(st, self.token.data_ptr(), self.out_ids.data_ptr(),
