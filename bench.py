@@ -338,7 +338,7 @@ def main():
                      "traffic_note": "dram__bytes_read+write of ONE launch (gate|up GEMM, M=4096 N=22016 K=4096; algorithmic 302 MB) from profiles/r1_gemm_swiglu_metrics.csv; `achieved` aggregates all GEMM launches of the prefill",
                      "kernel": "gemm_bf16_kernel<2> (tcgen05, cta_group::2)",
                      "launches_timed": gemm_n, "peak_source": peaks["source"], "frac_of_burst": achieved / peaks["tflops_burst"]},
-        "roofline_hbm": {"bound": "hbm", "kernel": "gemv_pair_kernel<*> + flash_decode (decode step, 166 kernels/token)",
+        "roofline_hbm": {"bound": "hbm", "kernel": "decode_stream_kernel (whole decode step: 1 persistent launch per token, TMA weight/KV ring)",
                          "achieved": (13.48e9 + 0.524e6 * SEQ_LEN) / (dec_ms / DECODE_TOKENS / 1e3) / 1e9,
                          "peak": peaks["hbm"], "unit": "GB/s",
                          "frac": (13.48e9 + 0.524e6 * SEQ_LEN) / (dec_ms / DECODE_TOKENS / 1e3) / 1e9 / peaks["hbm"]},

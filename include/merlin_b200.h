@@ -150,7 +150,10 @@ typedef struct merlin_decoder_weights {
   const void* const* ln2_w;     /* [L] -> [hidden] post_attention_layernorm                       */
   const void* norm_w;           /* [hidden] final norm                                            */
   const void* lm_head_w;        /* [vocab, hidden]                                                */
-  void* const* kv_cache;        /* [L] -> [capacity, 2*hidden] bf16, row t = [k_t (rotated) | v_t] */
+  void* const* kv_cache;        /* [L] -> [kv_capacity/32, heads, 32, 256] bf16: row (h, t) = [k_t^h rotated (128) |
+                                 * v_t^h (128)] at ((t/32 * heads + h) * 32 + t%32) * 256 — blocks of 32 tokens, head-major
+                                 * inside a block: a (head, 32-key) tile is 16 KB contiguous, a token range is dense  */
+  int64_t kv_capacity;          /* tokens the caches can hold (a multiple of 32)                                      */
   const float* rope_cos;        /* [max_pos, 64] fp32                                             */
   const float* rope_sin;
 } merlin_decoder_weights;
@@ -165,21 +168,19 @@ size_t merlin_decode_workspace_bytes(int hidden, int intermediate, int heads, in
 int merlin_decode_step(void* stream, const merlin_decoder_weights* w, void* x, const int* pos_dev,
                        void* workspace, void* logits, int n_splits);
 
-/* The same decode step as ONE persistent kernel (one CTA per SM, cooperative launch): a producer warp per
- * CTA streams that CTA's share of every layer's weight rows and KV-cache tiles through a shared-memory
- * ring with TMA and runs ahead across layer boundaries while the consumer warps synchronise grid-wide on
- * the activations.  `workspace` (merlin_decode_stream_workspace_bytes, 256-byte aligned) must first be
- * bound to the weights and caches with merlin_decode_stream_prepare — it copies the per-layer pointer
- * tables and one TMA tensor map per cache to the device and synchronises `stream` (not capturable; call it
- * again whenever a pointer in `w` or kv_capacity changes).  merlin_decode_stream_step is capturable:
- * x_in[hidden] is the token embedding (read-only, may alias x), x[hidden] receives the final residual
- * stream, logits[vocab] the lm_head output.  Same reference code as merlin_decode_step. */
+/* The same decode step as ONE persistent kernel (one CTA per SM, cooperative launch): a producer thread per
+ * CTA streams that CTA's share of every layer's weight rows and KV-cache tiles through a shared-memory ring
+ * with TMA bulk copies and runs ahead across phase and layer boundaries while the consumer warps synchronise
+ * grid-wide on the activations.  `workspace` (merlin_decode_stream_workspace_bytes, 256-byte aligned) must
+ * first be bound to the weights and caches with merlin_decode_stream_prepare — it copies the per-layer pointer
+ * tables to the device, clears the counters and synchronises `stream` (not capturable; call it again whenever
+ * a pointer in `w` changes or after a failed launch).  merlin_decode_stream_step is capturable: x_in[hidden]
+ * is the token embedding (read-only), logits[vocab] receives the lm_head output, the new k/v go to row
+ * *pos_dev of every cache.  Same reference code as merlin_decode_step. */
 size_t merlin_decode_stream_workspace_bytes(int num_layers, int hidden, int heads, int intermediate);
-int merlin_decode_stream_prepare(void* stream, const merlin_decoder_weights* w, int64_t kv_capacity,
-                                 void* workspace);
-int merlin_decode_stream_step(void* stream, const merlin_decoder_weights* w, const void* x_in, void* x,
-                              const int* pos_dev, void* workspace, void* logits);
-
+int merlin_decode_stream_prepare(void* stream, const merlin_decoder_weights* w, void* workspace);
+int merlin_decode_stream_step(void* stream, const merlin_decoder_weights* w, const void* x_in, const int* pos_dev,
+                              void* workspace, void* logits);
 /* x[D] = embed_table[*token_dev] (token id read on the device). */
 int merlin_embed_token(void* stream, const void* embed_table, const int64_t* token_dev, void* x, int D,
                        int64_t vocab);
@@ -187,6 +188,12 @@ int merlin_embed_token(void* stream, const void* embed_table, const int64_t* tok
 /* out_ids[*n_out_dev] = *token_dev; ++*n_out_dev; ++*pos_dev  — closes one greedy step on the device. */
 int merlin_record_advance(void* stream, const int64_t* token_dev, int64_t* out_ids, int* n_out_dev,
                           int* pos_dev, int capacity);
+
+/* Append S tokens to a KV cache (layout above): for b < B, s < S, h < H copies k and v of head h out of the packed
+ * qkv row [b*S + s] (ldq elements per row; k at column D + h*128, v at 2D + h*128) into row (h, pos0 + s) of
+ * cache block b.  cache holds B blocks of kv_capacity*H*256 elements.  (HF KV-cache update.) */
+int merlin_kv_append(void* stream, const void* qkv, int64_t ldq, void* kv_cache, int64_t kv_capacity, int B, int S,
+                     int D, int H, int pos0);
 
 /* ---- composite forward entry points: one call per layer, kernels sequenced on the caller's stream ---- */
 typedef struct merlin_layer_weights {       /* one Vicuna decoder layer, packed layouts as above */
@@ -197,8 +204,9 @@ typedef struct merlin_vit_layer_weights {   /* one CLIP encoder layer (q|k|v fus
 } merlin_vit_layer_weights;
 
 /* x[B*S, D] <- LlamaDecoderLayer(x): x += Attn(RMSNorm(x)); x += MLP(RMSNorm(x)), in place
- * (HF:llama/modeling_llama.py:303-333 with the flash-attn patch).  kv_cache (NULL = off): [B, kv_capacity,
- * 2*D] receives the rotated keys and the values of the S prompt tokens for later decode steps. */
+ * (HF:llama/modeling_llama.py:303-333 with the flash-attn patch).  kv_cache (NULL = off): B blocks of
+ * [kv_capacity/32, H, 32, 256] (see merlin_decoder_weights) receive the rotated keys and the values of the S prompt
+ * tokens for later decode steps. */
 size_t merlin_decoder_layer_workspace_bytes(int M, int D, int FF);
 int merlin_decoder_layer_forward(void* stream, const merlin_layer_weights* w, void* x, void* workspace,
                                  const float* rope_cos, const float* rope_sin, const int* seqlens,

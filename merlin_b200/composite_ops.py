@@ -21,12 +21,12 @@ def decoder_layer_forward(x, ws, qkv_w, o_w, gate_up_w, down_w, ln1_w, ln2_w, co
     D = x.shape[1]
     w = _lib.LayerWeights(qkv_w.data_ptr(), o_w.data_ptr(), gate_up_w.data_ptr(), down_w.data_ptr(),
                           ln1_w.data_ptr(), ln2_w.data_ptr())
-    kv_ptr, cap = (None, 0) if kv is None else (kv.data_ptr(), kv.shape[1])
+    kv_ptr, cap = (None, 0) if kv is None else (kv.data_ptr(), kv.shape[1] * 32)  # [B, capacity/32, H, 32, 256]
     fn = _lib.load().merlin_decoder_layer_forward
     args = (torch.cuda.current_stream().cuda_stream, ctypes.byref(w), x.data_ptr(), ws.data_ptr(), cos.data_ptr(),
             sin.data_ptr(), None if seqlens is None else seqlens.data_ptr(), kv_ptr, cap, batch, seq, D, heads, ff,
             float(eps), cta_group)
-    ops.PROFILE.launches += 7 + (0 if kv is None else batch)
+    ops.PROFILE.launches += 7 + (0 if kv is None else 1)
     if ops.PROFILE.enabled:
         # the roofline leg times GEMM launches individually: fall back to the per-op path for this layer
         return False

@@ -30,13 +30,8 @@ int merlin_decoder_layer_forward(void* stream, const merlin_layer_weights* w, vo
                                  2 * D, S, cta_group)) != MERLIN_OK)
     return rc;
   if (kv_cache != nullptr) {
-    // rows of [k | v] (2D bf16) out of the packed qkv rows into cache[b, 0:S, :]
-    for (int b = 0; b < B; ++b) {
-      MB_CHECK_CUDA(cudaMemcpy2DAsync(static_cast<__nv_bfloat16*>(kv_cache) + static_cast<size_t>(b) * kv_capacity * 2 * D,
-                                      static_cast<size_t>(2) * D * 2, qkv + static_cast<size_t>(b) * S * 3 * D + D,
-                                      static_cast<size_t>(3) * D * 2, static_cast<size_t>(2) * D * 2, S,
-                                      cudaMemcpyDeviceToDevice, static_cast<cudaStream_t>(stream)));
-    }
+    // rotated keys and values of the S prompt tokens -> head-major cache [B, H, kv_capacity, 256]
+    if ((rc = merlin_kv_append(stream, qkv, 3 * D, kv_cache, kv_capacity, B, S, D, H, 0)) != MERLIN_OK) return rc;
   }
   if ((rc = merlin_flash_attn_fwd(stream, qkv, 3 * D, att, D, nullptr, seqlens, B, S, H, 128, 1, 0.f)) != MERLIN_OK)
     return rc;

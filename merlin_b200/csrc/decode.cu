@@ -9,6 +9,7 @@
 #include "host.cuh"
 #include "ptx.cuh"
 
+#include <algorithm>
 #include <cstdlib>
 
 namespace mb {
@@ -25,7 +26,7 @@ struct GemvParams {
   const __nv_bfloat16* norm_w;    // [K] RMSNorm weight applied to x first, or nullptr
   const __nv_bfloat16* residual;  // [N] or nullptr (PLAIN)
   __nv_bfloat16* out;             // PLAIN: [N]; SWIGLU: [N/2]; QKV: q buffer [D]
-  __nv_bfloat16* kv_row0;         // QKV: cache base [capacity, 2*D]
+  __nv_bfloat16* kv_row0;         // QKV: cache base, tile-major layout (kv_row_off)
   const float* rope_cos;          // [max_pos, 64]
   const float* rope_sin;
   const int* pos;                 // device scalar: position of the token being decoded
@@ -58,6 +59,13 @@ __device__ __forceinline__ uint4 ld_stream(const uint4* p) {
                : "=r"(r.x), "=r"(r.y), "=r"(r.z), "=r"(r.w)
                : "l"(p));
   return r;
+}
+
+// KV cache layout: blocks of 32 tokens, head-major inside a block: row (h, t) = [k_t^h rotated (128) | v_t^h (128)]
+// at element offset (((t / 32) * H + h) * 32 + t % 32) * 256.  One (head, 32-key tile) is 16 KB contiguous for the
+// streaming decode kernel's bulk copies, and all heads of a token range still form one dense region.
+__device__ __forceinline__ size_t kv_row_off(int h, int t, int H) {
+  return ((static_cast<size_t>(t >> 5) * H + h) * 32 + (t & 31)) * 256;
 }
 
 template <int kMode>
@@ -195,7 +203,10 @@ gemv_pair_kernel(const GemvParams p) {
 
   if (kMode == GEMV_QKV_ROPE) {
     const int pos = *p.pos;
-    __nv_bfloat16* kv = p.kv_row0 + static_cast<size_t>(pos) * 2 * p.D;
+    // element e of the k (which = 0) / v (which = 1) projection -> row (head e / 128, pos), column which * 128 + e % 128
+    auto kv_at = [&](int e, int which) {
+      return p.kv_row0 + kv_row_off(e >> 7, pos, p.D >> 7) + which * 128 + (e & 127);
+    };
     if (row_a < 2 * p.D) {
       const int j = row_a & 63;
       const float c = p.rope_cos[static_cast<size_t>(pos) * 64 + j];
@@ -206,12 +217,12 @@ gemv_pair_kernel(const GemvParams p) {
         p.out[row_a] = __float2bfloat16_rn(lo);
         p.out[row_b] = __float2bfloat16_rn(hi);
       } else {
-        kv[row_a - p.D] = __float2bfloat16_rn(lo);
-        kv[row_b - p.D] = __float2bfloat16_rn(hi);
+        *kv_at(row_a - p.D, 0) = __float2bfloat16_rn(lo);
+        *kv_at(row_b - p.D, 0) = __float2bfloat16_rn(hi);
       }
     } else {
-      kv[row_a - p.D] = __float2bfloat16_rn(sa);
-      kv[row_b - p.D] = __float2bfloat16_rn(sb);
+      *kv_at(row_a - 2 * p.D, 1) = __float2bfloat16_rn(sa);
+      *kv_at(row_b - 2 * p.D, 1) = __float2bfloat16_rn(sb);
     }
   } else if (kMode == GEMV_SWIGLU) {
     const int blk = row_a >> 8, j = row_a & 127;
@@ -231,7 +242,7 @@ constexpr int kFdThreads = 128;  // 4 warps x 4 key slots x 8 lanes (16 dims eac
 
 __global__ void __launch_bounds__(kFdThreads)
 flash_decode_partial_kernel(const __nv_bfloat16* __restrict__ q, const __nv_bfloat16* __restrict__ kv,
-                            const int* __restrict__ pos_ptr, int D, int n_splits, float scale_log2e,
+                            const int* __restrict__ pos_ptr, int H, int n_splits, float scale_log2e,
                             float* __restrict__ part_o, float* __restrict__ part_ml,
                             unsigned int* __restrict__ tickets, __nv_bfloat16* __restrict__ att_out) {
   __shared__ float s_o[16][128];
@@ -267,11 +278,11 @@ flash_decode_partial_kernel(const __nv_bfloat16* __restrict__ q, const __nv_bflo
   // software-pipelined over keys: the loads of key n+1 are in flight while key n is reduced
   auto load_key = [&](int key, uint4 (&r)[4]) {
     const bool live = key < k1;
-    const __nv_bfloat16* row = kv + static_cast<size_t>(live ? key : k0) * 2 * D + h * 128 + sub * 16;
+    const __nv_bfloat16* row = kv + kv_row_off(h, live ? key : k0, H) + sub * 16;
     r[0] = ld_stream(reinterpret_cast<const uint4*>(row));
     r[1] = ld_stream(reinterpret_cast<const uint4*>(row) + 1);
-    r[2] = ld_stream(reinterpret_cast<const uint4*>(row + D));
-    r[3] = ld_stream(reinterpret_cast<const uint4*>(row + D) + 1);
+    r[2] = ld_stream(reinterpret_cast<const uint4*>(row + 128));
+    r[3] = ld_stream(reinterpret_cast<const uint4*>(row + 128) + 1);
   };
   uint4 cur[4], nxt[4];
   if (k0 < k1) load_key(k0 + slot, cur);
@@ -373,6 +384,24 @@ flash_decode_combine_kernel(const float* __restrict__ part_o, const float* __res
   out[h * 128 + d] = __float2bfloat16_rn(acc / L);
 }
 
+// packed qkv rows -> head-major KV cache: one 16-byte chunk per thread; chunk c of token (b, s):
+// c in [0, 2*D/8): which = c / (D/8) (k or v), head = (c % (D/8)) / 16, part = c % 16
+__global__ void kv_append_kernel(const __nv_bfloat16* __restrict__ qkv, int64_t ldq, __nv_bfloat16* __restrict__ kv,
+                                 int64_t cap, int B, int S, int D, int H, int pos0) {
+  const int cpr = D >> 2;  // 16-byte chunks of [k | v] per token
+  const int64_t total = static_cast<int64_t>(B) * S * cpr;
+  for (int64_t i = blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x; i < total;
+       i += static_cast<int64_t>(gridDim.x) * blockDim.x) {
+    const int c = static_cast<int>(i % cpr);
+    const int64_t tok = i / cpr;
+    const int b = static_cast<int>(tok / S), s = static_cast<int>(tok % S);
+    const int which = c / (D >> 3), hc = c % (D >> 3);
+    const int h = hc >> 4, part = hc & 15;
+    const uint4 v = *reinterpret_cast<const uint4*>(qkv + tok * ldq + D + static_cast<size_t>(which) * D + h * 128 + part * 8);
+    *reinterpret_cast<uint4*>(kv + static_cast<size_t>(b) * cap * H * 256 + kv_row_off(h, pos0 + s, H) + which * 128 + part * 8) = v;
+  }
+}
+
 // token embedding row -> x ; token id read from device memory (graph-replayable greedy loop)
 __global__ void embed_token_kernel(const __nv_bfloat16* __restrict__ table, const int64_t* __restrict__ token,
                                    __nv_bfloat16* __restrict__ x, int D, int64_t vocab) {
@@ -452,6 +481,7 @@ int merlin_decode_step(void* stream, const merlin_decoder_weights* w, void* x, c
   MB_CHECK_ARG(w && x && pos_dev && workspace && logits, "decode_step: null argument");
   MB_CHECK_ARG(w->hidden == w->heads * 128, "decode_step: head_dim must be 128");
   MB_CHECK_ARG(w->intermediate % 128 == 0 && n_splits >= 1 && n_splits <= 64, "decode_step: bad config");
+  MB_CHECK_ARG(w->kv_capacity >= 32 && w->kv_capacity % 32 == 0, "decode_step: kv_capacity must be a multiple of 32");
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   {
     const char* e = getenv("MERLIN_PDL");
@@ -500,7 +530,7 @@ int merlin_decode_step(void* stream, const merlin_decoder_weights* w, void* x, c
     {
       cudaLaunchConfig_t cfg = pdl_config(dim3(H, n_splits), dim3(kFdThreads), 0, st);
       MB_CHECK_CUDA(cudaLaunchKernelEx(&cfg, flash_decode_partial_kernel, static_cast<const __nv_bfloat16*>(qbuf),
-                                       static_cast<const __nv_bfloat16*>(w->kv_cache[i]), pos_dev, D, n_splits,
+                                       static_cast<const __nv_bfloat16*>(w->kv_cache[i]), pos_dev, H, n_splits,
                                        scale_log2e, part_o, part_ml, tickets, att));
     }
     // x += o_proj(att)
@@ -546,6 +576,22 @@ int merlin_decode_step(void* stream, const merlin_decoder_weights* w, void* x, c
   pl.D = D;
   pl.eps = w->rms_eps;
   if ((rc = launch_gemv<GEMV_PLAIN>(st, pl, (w->vocab + 1) / 2, 1)) != MERLIN_OK) return rc;
+  MB_CHECK_CUDA(cudaGetLastError());
+  return MERLIN_OK;
+}
+
+int merlin_kv_append(void* stream, const void* qkv, int64_t ldq, void* kv_cache, int64_t kv_capacity, int B, int S,
+                     int D, int H, int pos0) {
+  MB_CHECK_ARG(qkv && kv_cache && D == H * 128 && ldq >= 3 * static_cast<int64_t>(D) && ldq % 8 == 0,
+               "kv_append: bad argument");
+  MB_CHECK_ARG(kv_capacity % 32 == 0, "kv_append: kv_capacity must be a multiple of 32");
+  MB_CHECK_ARG(B >= 1 && S >= 0 && pos0 >= 0 && static_cast<int64_t>(pos0) + S <= kv_capacity,
+               "kv_append: %d tokens at %d do not fit capacity %lld", S, pos0, static_cast<long long>(kv_capacity));
+  if (S == 0) return MERLIN_OK;
+  const int64_t total = static_cast<int64_t>(B) * S * (D >> 2);
+  const int blocks = static_cast<int>(std::min<int64_t>((total + 255) / 256, static_cast<int64_t>(sm_count()) * 16));
+  kv_append_kernel<<<blocks, 256, 0, static_cast<cudaStream_t>(stream)>>>(
+      static_cast<const __nv_bfloat16*>(qkv), ldq, static_cast<__nv_bfloat16*>(kv_cache), kv_capacity, B, S, D, H, pos0);
   MB_CHECK_CUDA(cudaGetLastError());
   return MERLIN_OK;
 }

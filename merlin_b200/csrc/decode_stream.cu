@@ -24,7 +24,7 @@ constexpr int kSC = 8;                            // consumer warps per CTA
 constexpr int kSConsThreads = kSC * 32;
 constexpr int kSThreads = kSConsThreads + 32;     // + 1 producer warp (warp index kSC)
 constexpr int kKT = 32;                           // keys per KV tile
-constexpr int kKvTileBytes = kKT * 2 * 128 * 2;   // [32 keys][k|v][128] bf16
+constexpr int kKvTileBytes = kKT * 256 * 2;       // [32 keys][k 128 | v 128] bf16, contiguous in the cache
 constexpr int kMaxParts = 96;                     // attention partials per head
 constexpr int kMaxLayers = 96;
 constexpr int kMaxStages = 16;
@@ -47,7 +47,7 @@ struct StreamTables {  // device copy of the per-layer pointer tables (written b
 };
 
 struct StreamLayout {  // byte offsets inside the caller's workspace
-  size_t ctrl, done, maps, tables, qbuf, att, mid, part_ml, part_o, total;
+  size_t ctrl, done, tables, xres, qbuf, att, mid, part_ml, part_o, total;
 };
 static StreamLayout stream_layout(int L, int D, int H, int FF) {
   auto up = [](size_t v) { return (v + 255) / 256 * 256; };
@@ -55,8 +55,8 @@ static StreamLayout stream_layout(int L, int D, int H, int FF) {
   size_t o = 0;
   s.ctrl = o;   o += 512;                                    // grid-barrier counter @0, exit counter @128
   s.done = o;   o += up(static_cast<size_t>(H) * 4);
-  s.maps = o;   o += up(static_cast<size_t>(L) * sizeof(CUtensorMap));
   s.tables = o; o += up(sizeof(StreamTables));
+  s.xres = o;   o += up(static_cast<size_t>(D) * 2);
   s.qbuf = o;   o += up(static_cast<size_t>(D) * 2);
   s.att = o;    o += up(static_cast<size_t>(D) * 2);
   s.mid = o;    o += up(static_cast<size_t>(FF) * 2);
@@ -68,7 +68,6 @@ static StreamLayout stream_layout(int L, int D, int H, int FF) {
 
 struct StreamParams {
   const StreamTables* tb;
-  const CUtensorMap* kvmaps;
   const __nv_bfloat16* norm_w;
   const __nv_bfloat16* lm_head;
   const __nv_bfloat16* x_in;   // token embedding (residual stream at layer 0)
@@ -132,8 +131,9 @@ __device__ __forceinline__ float warp_sum(float v) {
 __device__ __forceinline__ void grid_barrier(unsigned int* counter, unsigned int target, int ctid) {
   named_bar_sync(1, kSConsThreads);
   if (ctid == 0) {
-    __threadfence();
-    atomicAdd(counter, 1u);
+    // release: the CTA's epilogue stores (ordered before this thread by the bar.sync above) become visible
+    // before the arrival; every cross-CTA read in this kernel is an L2 read, so no L1 invalidation is needed
+    asm volatile("red.release.gpu.global.add.u32 [%0], 1;" ::"l"(counter) : "memory");
     // bounded: a lost arrival must end in a trap (launch failure), not in a hung GPU
     unsigned int it = 0;
     while (ld_acquire_u32(counter) < target) {
@@ -143,7 +143,6 @@ __device__ __forceinline__ void grid_barrier(unsigned int* counter, unsigned int
         __trap();
       }
     }
-    __threadfence();
   }
   named_bar_sync(1, kSConsThreads);
 }
@@ -247,31 +246,24 @@ __device__ __forceinline__ void produce_gemv(const Ring& r, ProducerState& ps, c
   }
 }
 
-// Contiguous, balanced split of the NT KV tiles (head-major) over the first NW ring warps: warp gw owns
-// tiles [lo, lo + n).  At most NW / H + 2 warps touch one head, which bounds the partials per head.
-__device__ __forceinline__ void att_range(int gw, int NT, int NW, int& lo, int& n) {
-  if (gw >= NW) {
-    lo = NT;
-    n = 0;
-    return;
-  }
-  lo = static_cast<int>((static_cast<long long>(gw) * NT) / NW);
-  n = static_cast<int>((static_cast<long long>(gw + 1) * NT) / NW) - lo;
+// KV cache layout (shared with decode.cu): blocks of 32 tokens, head-major inside a block —
+//   element (h, t, c) at (((t / 32) * H + h) * 32 + t % 32) * 256 + c,  c < 128: k (rotated), c >= 128: v
+// so one (head, 32-key tile) is 16 KB contiguous AND all heads of a token range form one dense region.
+__device__ __forceinline__ size_t kv_tile_off(int h, int kt, int H) {
+  return (static_cast<size_t>(kt) * H + h) * (kKT * 256);
 }
-
-// The ring warp whose range contains tile t, and the partial-slot bookkeeping derived from it: when every
-// warp has tiles (NT >= NW) the warps touching head h are consecutive and slot = gw - first warp of the head;
-// otherwise each warp has at most one tile and slot = index of the tile inside the head.
-__device__ __forceinline__ int att_owner(int t, int NT, int NW) {
-  return static_cast<int>((static_cast<long long>(t + 1) * NW + NT - 1) / NT) - 1;
-}
-__device__ __forceinline__ int att_ring_slots(int h, int tph, int NT, int NW) {
-  if (NT < NW) return tph;
-  return att_owner((h + 1) * tph - 1, NT, NW) - att_owner(h * tph, NT, NW) + 1;
-}
-__device__ __forceinline__ int att_slot_of(int gw, int tile, int h, int tph, int NT, int NW) {
-  if (NT < NW) return tile - h * tph;
-  return gw - att_owner(h * tph, NT, NW);
+// Attention work split.  Head h owns WPH consecutive ring warps; warp s of the head takes key tiles
+// s, s + WPH, s + 2 WPH, ...  At any time the chip therefore streams the same narrow range of key tiles of ALL
+// heads — one dense region of the cache (DRAM-friendly), not one stream per warp.  Warp s publishes partial s
+// of its head, the tail warp partial min(WPH, tph): slot indices are a pure function of the split.
+struct AttSplit {
+  int H, tph, WPH;
+};
+__device__ __forceinline__ int att_head_of(const AttSplit& a, int gw) { return gw / a.WPH; }   // >= H: no work
+__device__ __forceinline__ int att_count(const AttSplit& a, int gw) {
+  if (gw >= a.WPH * a.H) return 0;
+  const int s = gw % a.WPH;
+  return a.tph > s ? (a.tph - s + a.WPH - 1) / a.WPH : 0;
 }
 
 // ---- consumer side
@@ -308,7 +300,8 @@ __device__ __forceinline__ void consumer_release(const Ring& r, int slot, uint32
 struct GemvEpilogue {
   __nv_bfloat16* out;             // QKV: q buffer; SWIGLU: mid; PLAIN: out vector
   const __nv_bfloat16* residual;  // PLAIN (may be null)
-  __nv_bfloat16* kv_row;          // QKV: cache row of this position
+  __nv_bfloat16* kv_base;         // QKV: cache of this layer (layout: kv_tile_off)
+  int H, pos;
   const float* cos_row;           // QKV: rope tables at this position
   const float* sin_row;
 };
@@ -380,6 +373,10 @@ __device__ __forceinline__ void consume_gemv(const Ring& r, uint32_t& stage0, co
     consumer_release(r, slot, stage0 + j, lane);   // every lane's reads fed the shuffles above
     if (lane != 0) continue;
     if (ph.mode == SM_QKV) {
+      // element e of the k / v projection -> row (head e / 128, pos) of the cache, column (v: 128 +) e % 128
+      auto kv_at = [&](int e, int which) {
+        return ep.kv_base + kv_tile_off(e >> 7, ep.pos >> 5, ep.H) + (ep.pos & 31) * 256 + which * 128 + (e & 127);
+      };
       if (u < D) {
         // the prefill path rounds the projection to bf16 only after the rotation (fp32 epilogue)
         const float lo = sa * e0 - sb * e1, hi = sb * e0 + sa * e1;
@@ -387,12 +384,12 @@ __device__ __forceinline__ void consume_gemv(const Ring& r, uint32_t& stage0, co
           ep.out[ra] = __float2bfloat16_rn(lo);
           ep.out[rb] = __float2bfloat16_rn(hi);
         } else {
-          ep.kv_row[ra - D] = __float2bfloat16_rn(lo);
-          ep.kv_row[rb - D] = __float2bfloat16_rn(hi);
+          *kv_at(ra - D, 0) = __float2bfloat16_rn(lo);
+          *kv_at(rb - D, 0) = __float2bfloat16_rn(hi);
         }
       } else {
-        ep.kv_row[ra - D] = __float2bfloat16_rn(sa);
-        ep.kv_row[rb - D] = __float2bfloat16_rn(sb);
+        *kv_at(ra - 2 * D, 1) = __float2bfloat16_rn(sa);
+        *kv_at(rb - 2 * D, 1) = __float2bfloat16_rn(sb);
       }
     } else if (ph.mode == SM_SWIGLU) {
       ep.out[(ra >> 8) * 128 + (ra & 127)] = __float2bfloat16_rn(sa / (1.f + __expf(-sa)) * sb);
@@ -488,13 +485,12 @@ __device__ __forceinline__ void att_flush(AttState& s, int h, unsigned int idx, 
   __syncwarp();
   unsigned int last = 0;
   if (lane == 0) {
-    __threadfence();
-    const unsigned int old = atomicAdd(&p.done[h], cnt);
+    unsigned int old;
+    asm volatile("atom.acq_rel.gpu.global.add.u32 %0, [%1], %2;" : "=r"(old) : "l"(&p.done[h]), "r"(cnt) : "memory");
     last = (old + cnt == total) ? 1u : 0u;
   }
   last = __shfl_sync(0xffffffffu, last, 0);
   if (!last) return;
-  __threadfence();
   const int n = static_cast<int>(nslots);
   const float* ml = p.part_ml + static_cast<size_t>(h) * kMaxParts * 2;
   const float* po = p.part_o + static_cast<size_t>(h) * kMaxParts * 128;
@@ -555,8 +551,10 @@ __global__ void __launch_bounds__(kSThreads, 1) decode_stream_kernel(const Strea
   const int tph = pos / kKT;                     // full KV tiles per head (keys [0, tph*32)); tail = the rest
   const int tailCTAs = (H + kSC - 1) / kSC;      // the last CTAs process the per-head tails (incl. the new key)
   const int Gr = G - tailCTAs;
-  const int NT = H * tph;
-  const int NWu = min(Gr * kSC, 64 * H);         // ring warps that take KV tiles
+  AttSplit as;
+  as.H = H;
+  as.tph = tph;
+  as.WPH = max(min(Gr * kSC, 64 * H) / H, 1);    // ring warps per head (<= 64: bounds the partials per head)
   const StreamTables& tb = *p.tb;
 
   // phase list of one layer; `rot` spreads the remainder units of every phase over different CTAs
@@ -586,21 +584,21 @@ __global__ void __launch_bounds__(kSThreads, 1) decode_stream_kernel(const Strea
       produce_gemv(r, ps, ph, first_of(rot), G, D);
       rot = (rot + ph.U) % G;
       if (b < Gr && tph > 0) {  // KV tiles of this CTA's ring warps, interleaved so stage order == consumption order
-        int lo[kSC], n[kSC], maxn = 0;
+        int n[kSC], maxn = 0;
 #pragma unroll
         for (int w = 0; w < kSC; ++w) {
-          att_range(b * kSC + w, NT, NWu, lo[w], n[w]);
+          n[w] = att_count(as, b * kSC + w);
           maxn = max(maxn, n[w]);
         }
-        const CUtensorMap* map = p.kvmaps + l;
+        const __nv_bfloat16* kvl = tb.kv[l];
         for (int jj = 0; jj < maxn; ++jj) {
 #pragma unroll
           for (int w = 0; w < kSC; ++w) {
             if (jj >= n[w]) continue;
-            const int tile = lo[w] + jj;
-            const int h = tile / tph, kt = tile - h * tph;
+            const int gw = b * kSC + w;
             uint8_t* dst = producer_acquire(r, ps, kKvTileBytes);
-            tma_load_3d(map, &r.full[ps.slot], dst, h * 128, 0, kt * kKT, kEvictFirst);
+            bulk_g2s(dst, kvl + kv_tile_off(att_head_of(as, gw), gw % as.WPH + jj * as.WPH, H), kKvTileBytes,
+                     &r.full[ps.slot]);
             producer_advance(r, ps);
           }
         }
@@ -629,7 +627,7 @@ __global__ void __launch_bounds__(kSThreads, 1) decode_stream_kernel(const Strea
     // ---- RMSNorm -> fused q|k|v GEMV -> RoPE -> q buffer / KV-cache append
     stage_vec(resid, tb.ln1_w[l], D, p.eps, xs, red, ctid);
     GemvPhase ph = gemv_phase(l, 0);
-    GemvEpilogue ep = {p.qbuf, nullptr, kvl + static_cast<size_t>(pos) * 2 * D,
+    GemvEpilogue ep = {p.qbuf, nullptr, kvl, H, pos,
                        p.rope_cos + static_cast<size_t>(pos) * 64, p.rope_sin + static_cast<size_t>(pos) * 64};
     consume_gemv(r, stage, ph, first_of(rot), G, D, xs, ep, warp, lane);
     rot = (rot + ph.U) % G;
@@ -637,29 +635,23 @@ __global__ void __launch_bounds__(kSThreads, 1) decode_stream_kernel(const Strea
     grid_barrier(p.bar, bar_target, ctid);
 
     // ---- attention over keys 0..pos
+    const unsigned int nring = static_cast<unsigned int>(min(as.WPH, tph));   // ring partials per head
     if (b < Gr) {
       if (tph > 0) {
-        int n[kSC], maxn = 0, my_lo = 0, my_n = 0;
+        int n[kSC], maxn = 0;
 #pragma unroll
         for (int w = 0; w < kSC; ++w) {
-          int lo_w;
-          att_range(b * kSC + w, NT, NWu, lo_w, n[w]);
+          n[w] = att_count(as, b * kSC + w);
           maxn = max(maxn, n[w]);
-          if (w == warp) {
-            my_lo = lo_w;
-            my_n = n[w];
-          }
         }
+        const int gw = b * kSC + warp;
+        const int my_n = att_count(as, gw), my_h = att_head_of(as, gw);
         AttState st;
         float qf[16];
-        int cur_h = -1, cur_slot = 0;
-        unsigned int cnt = 0;
-        const int gw = b * kSC + warp;
-        auto flush = [&]() {
-          att_flush(st, cur_h, static_cast<unsigned int>(cur_slot),
-                    static_cast<unsigned int>(att_ring_slots(cur_h, tph, NT, NWu)) + 1u, cnt,
-                    static_cast<unsigned int>(tph) + 1u, p, lane);
-        };
+        if (my_n > 0) {
+          att_reset(st);
+          att_load_q(p.qbuf, my_h, sub, scale_log2e, qf);
+        }
         uint32_t c_row = stage;   // ring stage of (jj, warp 0)
         for (int jj = 0; jj < maxn; ++jj) {
           int before = 0, rowcnt = 0;
@@ -670,16 +662,6 @@ __global__ void __launch_bounds__(kSThreads, 1) decode_stream_kernel(const Strea
             if (w < warp) before += has;
           }
           if (jj < my_n) {
-            const int tile = my_lo + jj;
-            const int h = tile / tph;
-            if (h != cur_h) {
-              if (cur_h >= 0) flush();
-              att_reset(st);
-              att_load_q(p.qbuf, h, sub, scale_log2e, qf);
-              cur_h = h;
-              cur_slot = att_slot_of(gw, tile, h, tph, NT, NWu);
-              cnt = 0;
-            }
             int slot;
             consumer_wait(r, c_row + static_cast<uint32_t>(before), slot, lane);
             const uint4* t4 = reinterpret_cast<const uint4*>(r.base + static_cast<size_t>(slot) * r.slot_bytes);
@@ -689,12 +671,13 @@ __global__ void __launch_bounds__(kSThreads, 1) decode_stream_kernel(const Strea
               att_key(st, qf, row[sub], row[8 + sub], row[16 + sub], row[24 + sub], true);
             }
             consumer_release(r, slot, c_row + static_cast<uint32_t>(before), lane);
-            ++cnt;
           }
           c_row += static_cast<uint32_t>(rowcnt);
         }
         stage = c_row;
-        if (cur_h >= 0) flush();
+        if (my_n > 0)
+          att_flush(st, my_h, static_cast<unsigned int>(gw % as.WPH), nring + 1u, static_cast<unsigned int>(my_n),
+                    static_cast<unsigned int>(tph) + 1u, p, lane);
       }
     } else {
       const int h = (b - Gr) * kSC + warp;
@@ -704,14 +687,14 @@ __global__ void __launch_bounds__(kSThreads, 1) decode_stream_kernel(const Strea
         att_reset(st);
         att_load_q(p.qbuf, h, sub, scale_log2e, qf);
         const int k0 = tph * kKT;
-        const uint4* base = reinterpret_cast<const uint4*>(kvl + h * 128);
-        const size_t row_v4 = static_cast<size_t>(2 * D) / 8, v_off = static_cast<size_t>(D) / 8;
+        // the tail keys all live in token block `tph` of the cache
+        const uint4* base = reinterpret_cast<const uint4*>(kvl + kv_tile_off(h, tph, H));
         auto load = [&](int key, uint4 (&q4)[4]) {
-          const uint4* row = base + static_cast<size_t>(min(key, pos)) * row_v4;
+          const uint4* row = base + static_cast<size_t>(min(key, pos) - k0) * 32;
           q4[0] = __ldcg(row + sub);
           q4[1] = __ldcg(row + 8 + sub);
-          q4[2] = __ldcg(row + v_off + sub);
-          q4[3] = __ldcg(row + v_off + 8 + sub);
+          q4[2] = __ldcg(row + 16 + sub);
+          q4[3] = __ldcg(row + 24 + sub);
         };
         uint4 cur[4], nxt[4];
         load(k0 + kslot, cur);
@@ -722,7 +705,6 @@ __global__ void __launch_bounds__(kSThreads, 1) decode_stream_kernel(const Strea
 #pragma unroll
           for (int e = 0; e < 4; ++e) cur[e] = nxt[e];
         }
-        const unsigned int nring = tph > 0 ? static_cast<unsigned int>(att_ring_slots(h, tph, NT, NWu)) : 0u;
         att_flush(st, h, nring, nring + 1u, 1u, static_cast<unsigned int>(tph) + 1u, p, lane);
       }
     }
@@ -732,7 +714,7 @@ __global__ void __launch_bounds__(kSThreads, 1) decode_stream_kernel(const Strea
     // ---- x += o_proj(att)
     stage_vec(p.att, nullptr, D, 0.f, xs, red, ctid);
     ph = gemv_phase(l, 1);
-    GemvEpilogue eo = {p.x, resid, nullptr, nullptr, nullptr};
+    GemvEpilogue eo = {p.x, resid, nullptr, 0, 0, nullptr, nullptr};
     consume_gemv(r, stage, ph, first_of(rot), G, D, xs, eo, warp, lane);
     rot = (rot + ph.U) % G;
     bar_target += G;
@@ -741,7 +723,7 @@ __global__ void __launch_bounds__(kSThreads, 1) decode_stream_kernel(const Strea
     // ---- RMSNorm -> gate|up GEMV -> SwiGLU
     stage_vec(p.x, tb.ln2_w[l], D, p.eps, xs, red, ctid);
     ph = gemv_phase(l, 2);
-    GemvEpilogue eg = {p.mid, nullptr, nullptr, nullptr, nullptr};
+    GemvEpilogue eg = {p.mid, nullptr, nullptr, 0, 0, nullptr, nullptr};
     consume_gemv(r, stage, ph, first_of(rot), G, D, xs, eg, warp, lane);
     rot = (rot + ph.U) % G;
     bar_target += G;
@@ -750,7 +732,7 @@ __global__ void __launch_bounds__(kSThreads, 1) decode_stream_kernel(const Strea
     // ---- x += down(mid)
     stage_vec(p.mid, nullptr, FF, 0.f, xs, red, ctid);
     ph = gemv_phase(l, 3);
-    GemvEpilogue ed = {p.x, p.x, nullptr, nullptr, nullptr};
+    GemvEpilogue ed = {p.x, p.x, nullptr, 0, 0, nullptr, nullptr};
     consume_gemv(r, stage, ph, first_of(rot), G, D, xs, ed, warp, lane);
     rot = (rot + ph.U) % G;
     bar_target += G;
@@ -759,7 +741,7 @@ __global__ void __launch_bounds__(kSThreads, 1) decode_stream_kernel(const Strea
   // ---- final RMSNorm -> lm_head
   stage_vec(p.L > 0 ? p.x : p.x_in, p.norm_w, D, p.eps, xs, red, ctid);
   GemvPhase ph = gemv_phase(0, 4);
-  GemvEpilogue el = {p.logits, nullptr, nullptr, nullptr, nullptr};
+  GemvEpilogue el = {p.logits, nullptr, nullptr, 0, 0, nullptr, nullptr};
   consume_gemv(r, stage, ph, first_of(rot), G, D, xs, el, warp, lane);
 
   // ---- leave: the last CTA out re-arms the barrier counters for the next launch
@@ -776,35 +758,6 @@ __global__ void __launch_bounds__(kSThreads, 1) decode_stream_kernel(const Strea
 }
 
 // --------------------------------------------------------------------------------------------------- host
-typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
-                                  const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
-                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
-
-static int make_kv_map(CUtensorMap* out, void* base, int D, int64_t capacity) {
-  void* fp = nullptr;
-  cudaDriverEntryPointQueryResult q;
-  if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fp, cudaEnableDefault, &q) != cudaSuccess ||
-      q != cudaDriverEntryPointSuccess) {
-    set_error("cuTensorMapEncodeTiled entry point unavailable (no CUDA driver?)");
-    return MERLIN_E_CUDA;
-  }
-  // cache row t = [k_t (D) | v_t (D)] bf16  ->  dims (D, 2, capacity), box (128, 2, 32), no swizzle
-  cuuint64_t gdim[3] = {static_cast<cuuint64_t>(D), 2, static_cast<cuuint64_t>(capacity)};
-  cuuint64_t gstr[2] = {static_cast<cuuint64_t>(D) * 2, static_cast<cuuint64_t>(D) * 4};
-  cuuint32_t box[3] = {128, 2, kKT};
-  cuuint32_t estr[3] = {1, 1, 1};
-  CUresult rc = reinterpret_cast<EncodeTiledFn>(fp)(out, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 3, base, gdim, gstr, box,
-                                                   estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE,
-                                                   CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
-                                                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
-  if (rc != CUDA_SUCCESS) {
-    set_error("cuTensorMapEncodeTiled (KV cache, D=%d capacity=%lld) failed with CUresult %d", D,
-              static_cast<long long>(capacity), static_cast<int>(rc));
-    return MERLIN_E_CUDA;
-  }
-  return MERLIN_OK;
-}
-
 struct StreamGeometry {
   int slot_bytes, nst, down_rows, smem_bytes;
 };
@@ -831,6 +784,7 @@ static int check_stream_weights(const merlin_decoder_weights* w) {
   MB_CHECK_ARG(w->num_layers >= 1 && w->num_layers <= kMaxLayers, "decode_stream: %d layers unsupported",
                w->num_layers);
   MB_CHECK_ARG(w->intermediate % 128 == 0 && w->hidden % 128 == 0 && w->vocab >= 1, "decode_stream: bad dims");
+  MB_CHECK_ARG(w->kv_capacity >= 32 && w->kv_capacity % 32 == 0, "decode_stream: kv_capacity must be a multiple of 32");
   return MERLIN_OK;
 }
 
@@ -844,17 +798,15 @@ size_t merlin_decode_stream_workspace_bytes(int num_layers, int hidden, int head
   return stream_layout(num_layers, hidden, heads, intermediate).total;
 }
 
-int merlin_decode_stream_prepare(void* stream, const merlin_decoder_weights* w, int64_t kv_capacity,
-                                 void* workspace) {
+int merlin_decode_stream_prepare(void* stream, const merlin_decoder_weights* w, void* workspace) {
   int rc = check_stream_weights(w);
   if (rc != MERLIN_OK) return rc;
-  MB_CHECK_ARG(workspace != nullptr && kv_capacity >= 1, "decode_stream_prepare: bad argument");
+  MB_CHECK_ARG(workspace != nullptr, "decode_stream_prepare: null workspace");
   MB_CHECK_ARG((reinterpret_cast<uintptr_t>(workspace) & 255) == 0, "decode_stream_prepare: workspace must be 256-byte aligned");
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   const StreamLayout lay = stream_layout(w->num_layers, w->hidden, w->heads, w->intermediate);
   uint8_t* ws = static_cast<uint8_t*>(workspace);
   static thread_local StreamTables tb;
-  static thread_local CUtensorMap maps[kMaxLayers];
   memset(&tb, 0, sizeof(tb));
   for (int l = 0; l < w->num_layers; ++l) {
     tb.qkv_w[l] = static_cast<const __nv_bfloat16*>(w->qkv_w[l]);
@@ -868,21 +820,19 @@ int merlin_decode_stream_prepare(void* stream, const merlin_decoder_weights* w, 
                   reinterpret_cast<uintptr_t>(tb.gu_w[l]) | reinterpret_cast<uintptr_t>(tb.down_w[l]) |
                   reinterpret_cast<uintptr_t>(tb.kv[l])) % 16 == 0,
                  "decode_stream_prepare: layer %d tensors must be 16-byte aligned", l);
-    if ((rc = make_kv_map(&maps[l], tb.kv[l], w->hidden, kv_capacity)) != MERLIN_OK) return rc;
   }
   // synchronous copies: the staging buffers above are reused by the next call on this thread
   MB_CHECK_CUDA(cudaStreamSynchronize(st));
   MB_CHECK_CUDA(cudaMemcpy(ws + lay.tables, &tb, sizeof(tb), cudaMemcpyHostToDevice));
-  MB_CHECK_CUDA(cudaMemcpy(ws + lay.maps, maps, sizeof(CUtensorMap) * w->num_layers, cudaMemcpyHostToDevice));
-  MB_CHECK_CUDA(cudaMemset(ws + lay.ctrl, 0, lay.maps - lay.ctrl));  // barrier / exit / per-head counters
+  MB_CHECK_CUDA(cudaMemset(ws + lay.ctrl, 0, lay.tables - lay.ctrl));  // barrier / exit / per-head counters
   return MERLIN_OK;
 }
 
-int merlin_decode_stream_step(void* stream, const merlin_decoder_weights* w, const void* x_in, void* x,
-                              const int* pos_dev, void* workspace, void* logits) {
+int merlin_decode_stream_step(void* stream, const merlin_decoder_weights* w, const void* x_in, const int* pos_dev,
+                              void* workspace, void* logits) {
   int rc = check_stream_weights(w);
   if (rc != MERLIN_OK) return rc;
-  MB_CHECK_ARG(x_in && x && pos_dev && workspace && logits, "decode_stream_step: null argument");
+  MB_CHECK_ARG(x_in && pos_dev && workspace && logits, "decode_stream_step: null argument");
   StreamGeometry g;
   MB_CHECK_ARG(stream_geometry(w->hidden, w->intermediate, &g) == MERLIN_OK,
                "decode_stream_step: hidden=%d intermediate=%d do not fit the shared-memory ring", w->hidden,
@@ -898,11 +848,10 @@ int merlin_decode_stream_step(void* stream, const merlin_decoder_weights* w, con
   uint8_t* ws = static_cast<uint8_t*>(workspace);
   StreamParams p = {};
   p.tb = reinterpret_cast<const StreamTables*>(ws + lay.tables);
-  p.kvmaps = reinterpret_cast<const CUtensorMap*>(ws + lay.maps);
   p.norm_w = static_cast<const __nv_bfloat16*>(w->norm_w);
   p.lm_head = static_cast<const __nv_bfloat16*>(w->lm_head_w);
   p.x_in = static_cast<const __nv_bfloat16*>(x_in);
-  p.x = static_cast<__nv_bfloat16*>(x);
+  p.x = reinterpret_cast<__nv_bfloat16*>(ws + lay.xres);
   p.logits = static_cast<__nv_bfloat16*>(logits);
   p.qbuf = reinterpret_cast<__nv_bfloat16*>(ws + lay.qbuf);
   p.att = reinterpret_cast<__nv_bfloat16*>(ws + lay.att);

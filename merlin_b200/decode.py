@@ -48,7 +48,7 @@ class DecodeRunner:
         self.w = DecoderWeights(L, cfg.hidden_size, cfg.num_attention_heads, cfg.intermediate_size,
                                 cfg.vocab_size, float(cfg.rms_norm_eps), cast(self._keep[0]), cast(self._keep[1]),
                                 cast(self._keep[2]), cast(self._keep[3]), cast(self._keep[4]), cast(self._keep[5]),
-                                m.norm_w.data_ptr(), lm.lm_head_w.data_ptr(), cast(self._keep[6]),
+                                m.norm_w.data_ptr(), lm.lm_head_w.data_ptr(), cast(self._keep[6]), cache.capacity,
                                 cos.data_ptr(), sin.data_ptr())
         L_ = _lib.load()
         nbytes = L_.merlin_decode_workspace_bytes(cfg.hidden_size, cfg.intermediate_size,
@@ -69,7 +69,7 @@ class DecodeRunner:
             off = (-self.stream_ws.data_ptr()) % 256
             self.stream_ws_ptr = self.stream_ws.data_ptr() + off
             check(L_.merlin_decode_stream_prepare(torch.cuda.current_stream().cuda_stream, ctypes.byref(self.w),
-                                                  cache.capacity, self.stream_ws_ptr), "merlin_decode_stream_prepare")
+                                                  self.stream_ws_ptr), "merlin_decode_stream_prepare")
             self.launches_per_step = 1
         else:
             self.launches_per_step = 5 * L + 1  # 4 GEMVs + 1 flash-decode per layer, + lm_head
@@ -78,8 +78,8 @@ class DecodeRunner:
         """One decoder pass for the embedding in self.x at position *self.pos -> self.logits."""
         L_ = _lib.load()
         if self.mode == "stream":
-            check(L_.merlin_decode_stream_step(st, ctypes.byref(self.w), self.x.data_ptr(), self.x.data_ptr(),
-                                               self.pos.data_ptr(), self.stream_ws_ptr, self.logits.data_ptr()),
+            check(L_.merlin_decode_stream_step(st, ctypes.byref(self.w), self.x.data_ptr(), self.pos.data_ptr(),
+                                               self.stream_ws_ptr, self.logits.data_ptr()),
                   "merlin_decode_stream_step")
         else:
             check(L_.merlin_decode_step(st, ctypes.byref(self.w), self.x.data_ptr(), self.pos.data_ptr(),

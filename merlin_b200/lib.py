@@ -55,9 +55,10 @@ _PROTOTYPES = {
     "merlin_vit_embed": [_P, _P, _P, _P, _P, c_int, c_int, c_int],
     "merlin_vit_embed_bwd": [_P, _P, _P, _P, _P, c_int, c_int, c_int],
     "merlin_decode_step": [_P, _P, _P, _P, _P, _P, c_int],
-    "merlin_decode_stream_prepare": [_P, _P, c_int64, _P],
-    "merlin_decode_stream_step": [_P, _P, _P, _P, _P, _P, _P],
+    "merlin_decode_stream_prepare": [_P, _P, _P],
+    "merlin_decode_stream_step": [_P, _P, _P, _P, _P, _P],
     "merlin_embed_token": [_P, _P, _P, _P, c_int, c_int64],
+    "merlin_kv_append": [_P, _P, c_int64, _P, c_int64, c_int, c_int, c_int, c_int, c_int],
     "merlin_record_advance": [_P, _P, _P, _P, _P, c_int],
 }
 
@@ -70,7 +71,7 @@ class DecoderWeights(ctypes.Structure):
                 ("gate_up_w", ctypes.POINTER(c_void_p)), ("down_w", ctypes.POINTER(c_void_p)),
                 ("ln1_w", ctypes.POINTER(c_void_p)), ("ln2_w", ctypes.POINTER(c_void_p)),
                 ("norm_w", c_void_p), ("lm_head_w", c_void_p),
-                ("kv_cache", ctypes.POINTER(c_void_p)),
+                ("kv_cache", ctypes.POINTER(c_void_p)), ("kv_capacity", c_int64),
                 ("rope_cos", c_void_p), ("rope_sin", c_void_p)]
 
 

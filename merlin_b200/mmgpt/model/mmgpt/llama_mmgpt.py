@@ -76,12 +76,15 @@ def vicuna_13b_config(**kw) -> "MMGPTConfig":
 
 
 class MerlinKVCache:
-    """Per-layer key/value store for generate(): kv[l] is [B, capacity, 2*D] bf16 ([k | v] per token,
-    keys already rotated).  Stands in for the legacy tuple cache the reference indexes
-    (base_mmgpt.py:88) and for HF 5.x Cache objects (`get_seq_length`)."""
+    """Per-layer key/value store for generate(): kv[l] is [B, capacity/32, H, 32, 256] bf16 — blocks of 32
+    tokens, head-major inside a block, row (h, t) = [k_t^h (128, already rotated) | v_t^h (128)] — so a
+    (head, 32-key) tile is 16 KB contiguous for the decode kernels' bulk copies while a token range stays
+    one dense region.  Stands in for the legacy tuple cache the reference indexes (base_mmgpt.py:88) and
+    for HF 5.x Cache objects (`get_seq_length`)."""
 
     def __init__(self, num_layers: int, batch: int, capacity: int, hidden: int, device):
-        self.kv = [torch.empty((batch, capacity, 2 * hidden), dtype=torch.bfloat16, device=device)
+        capacity = (capacity + 31) // 32 * 32
+        self.kv = [torch.empty((batch, capacity // 32, hidden // 128, 32, 256), dtype=torch.bfloat16, device=device)
                    for _ in range(num_layers)]
         self.capacity = capacity
         self.seq_len = 0
@@ -167,7 +170,7 @@ class MMGPTLlamaModel(nn.Module):
             ops.rmsnorm(x, self.ln1_w[i], cfg.rms_norm_eps, out=xn)
             qkv = ops.gemm_qkv_rope(xn, self.qkv_w[i], cos, sin, seq)
             if cache is not None:
-                cache.kv[i][:, :seq].copy_(qkv.view(batch, seq, 3 * D)[:, :, D:])
+                ops.kv_append(qkv, cache.kv[i], batch, seq, D, H)
             att = ops.flash_attn(qkv, batch, seq, H, 128, causal=True, seqlens=seqlens)
             ops.gemm(att, self.o_w[i], residual=x, out=x, epilogue=EPI_RESIDUAL)
             ops.rmsnorm(x, self.ln2_w[i], cfg.rms_norm_eps, out=xn)

@@ -178,6 +178,20 @@ def gemm_qkv_rope(a: torch.Tensor, w_qkv: torch.Tensor, rope_cos: torch.Tensor, 
     return out
 
 
+def kv_append(qkv: torch.Tensor, kv_cache: torch.Tensor, batch: int, seq: int, hidden: int, heads: int,
+              pos0: int = 0) -> None:
+    """Packed qkv rows [batch*seq, 3*hidden] -> cache [batch, capacity/32, heads, 32, 256] at tokens
+    pos0 .. pos0+seq-1 (k rotated | v)."""
+    _, _, ldq = _rows2d(qkv, "qkv")
+    if kv_cache.dim() != 5 or kv_cache.shape[0] != batch or kv_cache.shape[2] != heads or kv_cache.shape[3] != 32 \
+            or kv_cache.shape[4] != 256 or not kv_cache.is_contiguous():
+        raise ValueError("kv_append: cache must be a contiguous [batch, capacity/32, heads, 32, 256] tensor")
+    L = _lib.load()
+    check(L.merlin_kv_append(_stream(), qkv.data_ptr(), ldq, kv_cache.data_ptr(), kv_cache.shape[1] * 32, batch, seq,
+                             hidden, heads, pos0), "merlin_kv_append")
+    PROFILE.launches += 1
+
+
 def flash_attn(qkv: torch.Tensor, batch: int, seq: int, heads: int, head_dim: int, *, causal: bool,
                seqlens: Optional[torch.Tensor] = None, return_lse: bool = False,
                softmax_scale: float = 0.0, out: Optional[torch.Tensor] = None):

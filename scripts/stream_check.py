@@ -23,7 +23,7 @@ def runner(model, cache, mode):
 
 
 def clone_cache(model, cache):
-    c = MerlinKVCache(len(cache.kv), 1, cache.capacity, cache.kv[0].shape[-1] // 2, DEV)
+    c = MerlinKVCache(len(cache.kv), 1, cache.capacity, cache.kv[0].shape[2] * 128, DEV)
     for a, b in zip(c.kv, cache.kv):
         a.copy_(b)
     c.seq_len = cache.seq_len
@@ -55,7 +55,8 @@ def compare(model, ctx, steps=3, label="", full_ref=True, verbose=False):
             print(f"  stream step {s} done", flush=True)
         ref = model(input_ids=toks).logits[0, -1].float() if full_ref else la[0]
         pos = ctx + s
-        dkv = max((a[0, pos].float() - b[0, pos].float()).abs().max().item() for a, b in zip(ca.kv, cb.kv))
+        dkv = max((a[0, pos // 32, :, pos % 32].float() - b[0, pos // 32, :, pos % 32].float()).abs().max().item()
+                  for a, b in zip(ca.kv, cb.kv))
         dl = (la - lb).abs().max().item()
         scale = ref.abs().max().item()
         ea, eb = (la[0] - ref).abs().max().item(), (lb[0] - ref).abs().max().item()
@@ -93,7 +94,22 @@ def timed_replays(r, n):
     return e0.elapsed_time(e1) / n
 
 
-def full(ctx=4096, layers=32):
+def copy_bandwidth():
+    """Reference point for box-to-box variance: torch copy of 1 GiB (read + write), best of 5."""
+    a = torch.empty(1 << 29, dtype=torch.bfloat16, device=DEV)
+    b = torch.empty_like(a)
+    best = 1e9
+    for _ in range(5):
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        b.copy_(a)
+        e1.record()
+        torch.cuda.synchronize()
+        best = min(best, e0.elapsed_time(e1))
+    return 2 * a.numel() * 2 / (best / 1e3) / 1e9
+
+
+def full(ctx=4096, layers=32, check=True):
     cfg = vicuna_7b_config(num_hidden_layers=layers)
     torch.manual_seed(0)
     t0 = time.time()
@@ -103,8 +119,10 @@ def full(ctx=4096, layers=32):
         model = MMGPTLlamaForCausalLM(cfg)
     torch.set_default_dtype(prev)
     print(f"model built in {time.time() - t0:.1f}s", flush=True)
-    compare(model, ctx, steps=3, label="7B", verbose=os.environ.get("VERBOSE") == "1")
-    for mode in ("kernels", "stream"):
+    print(f"copy bandwidth {copy_bandwidth():.0f} GB/s", flush=True)
+    if check:
+        compare(model, ctx, steps=3, label="7B", verbose=os.environ.get("VERBOSE") == "1")
+    for mode in (("kernels", "stream") if check else ("stream",)):
         cache = MerlinKVCache(layers, 1, ctx + 128, cfg.hidden_size, DEV)
         for kv in cache.kv:
             kv.normal_(0, 0.5)
@@ -122,6 +140,8 @@ if __name__ == "__main__":
             small()
         elif what == "full":
             full(int(sys.argv[2]) if len(sys.argv) > 2 else 4096)
+        elif what == "time":
+            full(int(sys.argv[2]) if len(sys.argv) > 2 else 4096, check=False)
         else:
             small()
             full()
