@@ -10,8 +10,10 @@ weak scaling, `value` = tokens all ranks processed / max-over-ranks device time.
 
   value : inputs already resident in HBM when the timed region starts
   e2e   : same step through the public API (model.generate) with pinned HOST inputs, H2D + D2H inside
-  roofline : the tcgen05 GEMM kernel (dominant), algorithmic FLOPs / CUDA-event time of its launches
-             inside the timed region, vs MEASURED_PEAKS.json
+  roofline : the dominant kernel of the step = the streaming decode kernel (32 launches, ~63 % of the step):
+             algorithmic bytes per launch / CUDA-event time per launch vs the measured HBM peak;
+  roofline_tensor : the tcgen05 GEMM kernel (dominant in the prefill), algorithmic FLOPs / CUDA-event time
+             of its launches, vs the measured sustained bf16 peak (MEASURED_PEAKS.json)
   cpu_baseline / --impl reference : the oracle port of the reference's CPU path on the host cores.
 """
 from __future__ import annotations
@@ -310,6 +312,24 @@ def main():
     gen = next(iter(model._graphed.values()))
     pre_ms, _ = timed(gen.graph.replay, args.steps)
     pre_ms /= args.steps
+    # The dominant kernel of the step is the decode kernel (32 launches x ~3 ms of a ~150 ms step): time it
+    # launch by launch, un-graphed, with a CUDA event pair on the launching stream, at the positions the timed
+    # steps decode (context 4096 .. 4127).
+    runner = gen.runner
+    st = torch.cuda.current_stream().cuda_stream
+    dec_kernel_ms = []
+    if runner.mode == "stream":
+        runner.pos.fill_(SEQ_LEN)
+        pairs = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True))
+                 for _ in range(DECODE_TOKENS + 2)]
+        torch.cuda.synchronize()
+        for k0, k1 in pairs:          # back to back like the graph-replayed loop, one sync at the end
+            k0.record()
+            runner._decode_step(st)
+            k1.record()
+            runner.pos.add_(1)
+        torch.cuda.synchronize()
+        dec_kernel_ms = [k0.elapsed_time(k1) for k0, k1 in pairs[2:]]
     step_host()
     e2e_ms, _ = timed(step_host, args.steps)
     train = train_detail(model, input_ids_h, img_d, world, device, timed) if os.environ.get("MERLIN_BENCH_TRAIN", "1") == "1" else None
@@ -322,6 +342,26 @@ def main():
     achieved = gemm_flops / (gemm_ms / 1e3) / 1e12 if gemm_ms > 0 else 0.0
     dec_ms = max(ms_per_step - pre_ms, 1e-6)
     fl = algorithmic_flops_prefill(SEQ_LEN, N_FRAMES)
+    # algorithmic bytes of one decode launch: every decoder + lm_head weight once, the cached
+    # keys/values of the context once (average context of the timed tokens)
+    dec_bytes = 13.48e9 + 0.524e6 * (SEQ_LEN + DECODE_TOKENS / 2)
+    if dec_kernel_ms:
+        dk_ms = statistics.mean(dec_kernel_ms)
+        roof_hbm = {"bound": "hbm", "achieved": dec_bytes / (dk_ms / 1e3) / 1e9, "peak": peaks["hbm"], "unit": "GB/s",
+                    "frac": dec_bytes / (dk_ms / 1e3) / 1e9 / peaks["hbm"], "traffic": 15.38e9,
+                    "traffic_note": "dram__bytes_read+write of ONE launch from profiles/r1_decode_stream_metrics.csv (algorithmic 15.63 GB)",
+                    "kernel": "decode_stream_kernel (whole decode step: 1 persistent launch per token, TMA weight/KV ring)",
+                    "launches_timed": len(dec_kernel_ms), "avg_launch_ms": dk_ms,
+                    "share_of_step": DECODE_TOKENS * dk_ms / ms_per_step,
+                    "peak_source": "measured (MEASURED_PEAKS.json, hbm_gbs)" if "measured" in peaks["source"] else peaks["source"]}
+    else:
+        roof_hbm = None
+    roof_tensor = {"bound": "tensor", "achieved": achieved, "peak": peaks["tflops"], "unit": "TFLOP/s",
+                     "frac": achieved / peaks["tflops"], "traffic": 318.4e6,
+                     "traffic_note": "dram__bytes_read+write of ONE launch (gate|up GEMM, M=4096 N=22016 K=4096; algorithmic 302 MB) from profiles/r1_gemm_swiglu_metrics.csv; `achieved` aggregates all GEMM launches of the prefill",
+                     "kernel": "gemm_bf16_kernel<2> (tcgen05, cta_group::2)",
+                     "launches_timed": gemm_n, "peak_source": peaks["source"], "frac_of_burst": achieved / peaks["tflops_burst"],
+                     "share_of_step": (gemm_ms / max(n_pre, 1)) / ms_per_step}
     line = {
         "metric": "tokens/sec (prefill+decode) Merlin-7B 5-frame interpair", "value": value, "unit": "tokens/s",
         "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_per_step,
@@ -333,15 +373,8 @@ def main():
                 "d2h_bytes_per_step": DECODE_TOKENS * 8},
         "gpu_launches": launches,
         "clocks": clocks,
-        "roofline": {"bound": "tensor", "achieved": achieved, "peak": peaks["tflops"], "unit": "TFLOP/s",
-                     "frac": achieved / peaks["tflops"], "traffic": 318.4e6,
-                     "traffic_note": "dram__bytes_read+write of ONE launch (gate|up GEMM, M=4096 N=22016 K=4096; algorithmic 302 MB) from profiles/r1_gemm_swiglu_metrics.csv; `achieved` aggregates all GEMM launches of the prefill",
-                     "kernel": "gemm_bf16_kernel<2> (tcgen05, cta_group::2)",
-                     "launches_timed": gemm_n, "peak_source": peaks["source"], "frac_of_burst": achieved / peaks["tflops_burst"]},
-        "roofline_hbm": {"bound": "hbm", "kernel": "decode_stream_kernel (whole decode step: 1 persistent launch per token, TMA weight/KV ring)",
-                         "achieved": (13.48e9 + 0.524e6 * SEQ_LEN) / (dec_ms / DECODE_TOKENS / 1e3) / 1e9,
-                         "peak": peaks["hbm"], "unit": "GB/s",
-                         "frac": (13.48e9 + 0.524e6 * SEQ_LEN) / (dec_ms / DECODE_TOKENS / 1e3) / 1e9 / peaks["hbm"]},
+        "roofline": roof_hbm if roof_hbm is not None else roof_tensor,
+        "roofline_tensor": roof_tensor,
         "detail": {"prefill_ms": pre_ms, "prefill_eager_profiled_ms": eager_ms / n_pre, "prefill_tokens_per_s_per_gpu": SEQ_LEN / (pre_ms / 1e3),
                    "prefill_model_tflops": fl / (pre_ms / 1e3) / 1e12,
                    "prefill_frac_of_sustained_peak": fl / (pre_ms / 1e3) / 1e12 / peaks["tflops"],
