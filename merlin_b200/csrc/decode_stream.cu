@@ -86,7 +86,7 @@ struct StreamParams {
   const int* pos;
   int L, D, H, FF, V;
   float eps;
-  int slot_bytes, nst, down_rows;
+  int slot_bytes, nst, down_rows, down_split;
 };
 
 // ------------------------------------------------------------------------------------------ device helpers
@@ -206,6 +206,7 @@ __device__ __forceinline__ void unit_rows(int mode, int u, int D, int N, int& ra
 struct GemvPhase {
   const __nv_bfloat16* W;
   int mode, U, K, N;
+  int spu;   // ring stages per unit: single-row units (SM_PLAIN1) are split into spu K-chunks of K / spu
 };
 
 struct Ring {
@@ -235,14 +236,17 @@ __device__ __forceinline__ void producer_advance(const Ring& r, ProducerState& p
 
 __device__ __forceinline__ void produce_gemv(const Ring& r, ProducerState& ps, const GemvPhase& ph, int first, int G,
                                              int D) {
-  const uint32_t row_bytes = static_cast<uint32_t>(ph.K) * 2;
+  const int kc = ph.K / ph.spu;                      // elements per stage and row
+  const uint32_t row_bytes = static_cast<uint32_t>(kc) * 2;
   for (int u = first; u < ph.U; u += G) {
     int ra, rb;
     unit_rows(ph.mode, u, D, ph.N, ra, rb);
-    uint8_t* dst = producer_acquire(r, ps, rb >= 0 ? 2 * row_bytes : row_bytes);
-    bulk_g2s(dst, ph.W + static_cast<size_t>(ra) * ph.K, row_bytes, &r.full[ps.slot]);
-    if (rb >= 0) bulk_g2s(dst + row_bytes, ph.W + static_cast<size_t>(rb) * ph.K, row_bytes, &r.full[ps.slot]);
-    producer_advance(r, ps);
+    for (int c = 0; c < ph.spu; ++c) {
+      uint8_t* dst = producer_acquire(r, ps, rb >= 0 ? 2 * row_bytes : row_bytes);
+      bulk_g2s(dst, ph.W + static_cast<size_t>(ra) * ph.K + c * kc, row_bytes, &r.full[ps.slot]);
+      if (rb >= 0) bulk_g2s(dst + row_bytes, ph.W + static_cast<size_t>(rb) * ph.K + c * kc, row_bytes, &r.full[ps.slot]);
+      producer_advance(r, ps);
+    }
   }
 }
 
@@ -326,11 +330,11 @@ __device__ __forceinline__ void consume_gemv(const Ring& r, uint32_t& stage0, co
       if (rb >= 0)
         e1 = __bfloat162float(__ushort_as_bfloat16(__ldcg(reinterpret_cast<const unsigned short*>(ep.residual + rb))));
     }
-    int slot;
-    consumer_wait(r, stage0 + j, slot, lane);
-    const uint4* wa = reinterpret_cast<const uint4*>(r.base + static_cast<size_t>(slot) * r.slot_bytes);
     float sa, sb = 0.f;
-    if (rb >= 0) {
+    if (rb >= 0) {   // row pair: one stage (spu == 1)
+      int slot;
+      consumer_wait(r, stage0 + j, slot, lane);
+      const uint4* wa = reinterpret_cast<const uint4*>(r.base + static_cast<size_t>(slot) * r.slot_bytes);
       const uint4* wb = wa + nvec;
       float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f, b0 = 0.f, b1 = 0.f, b2 = 0.f, b3 = 0.f;
       int i = lane;
@@ -352,25 +356,34 @@ __device__ __forceinline__ void consume_gemv(const Ring& r, uint32_t& stage0, co
         a0 = fma8(wa[i], x0, a0);
         b0 = fma8(wb[i], x0, b0);
       }
-      sa = (a0 + a1) + (a2 + a3);
-      sb = (b0 + b1) + (b2 + b3);
-    } else {
+      sa = warp_sum((a0 + a1) + (a2 + a3));
+      sb = warp_sum((b0 + b1) + (b2 + b3));
+      consumer_release(r, slot, stage0 + j, lane);   // every lane's reads fed the shuffles above
+    } else {         // single row in spu K-chunks, one stage each, all consumed by this warp
+      const int nvc = nvec / ph.spu;
       float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f;
-      int i = lane;
-      for (; i + 96 < nvec; i += 128) {
-        const uint4 x0 = xs[i], x1 = xs[i + 32], x2 = xs[i + 64], x3 = xs[i + 96];
-        const uint4 p0 = wa[i], p1 = wa[i + 32], p2 = wa[i + 64], p3 = wa[i + 96];
-        a0 = fma8(p0, x0, a0);
-        a1 = fma8(p1, x1, a1);
-        a2 = fma8(p2, x2, a2);
-        a3 = fma8(p3, x3, a3);
+      for (int c = 0; c < ph.spu; ++c) {
+        int slot;
+        consumer_wait(r, stage0 + j * ph.spu + c, slot, lane);
+        const uint4* wa = reinterpret_cast<const uint4*>(r.base + static_cast<size_t>(slot) * r.slot_bytes);
+        const uint4* xc = xs + c * nvc;
+        int i = lane;
+        for (; i + 96 < nvc; i += 128) {
+          const uint4 x0 = xc[i], x1 = xc[i + 32], x2 = xc[i + 64], x3 = xc[i + 96];
+          const uint4 p0 = wa[i], p1 = wa[i + 32], p2 = wa[i + 64], p3 = wa[i + 96];
+          a0 = fma8(p0, x0, a0);
+          a1 = fma8(p1, x1, a1);
+          a2 = fma8(p2, x2, a2);
+          a3 = fma8(p3, x3, a3);
+        }
+        for (; i < nvc; i += 32) a0 = fma8(wa[i], xc[i], a0);
+        // the partial sums carry a dependency on every lane's loads of this stage only through the final
+        // reduction, so order the release behind the loads explicitly
+        __syncwarp();
+        consumer_release(r, slot, stage0 + j * ph.spu + c, lane);
       }
-      for (; i < nvec; i += 32) a0 = fma8(wa[i], xs[i], a0);
-      sa = (a0 + a1) + (a2 + a3);
+      sa = warp_sum((a0 + a1) + (a2 + a3));
     }
-    sa = warp_sum(sa);
-    sb = warp_sum(sb);
-    consumer_release(r, slot, stage0 + j, lane);   // every lane's reads fed the shuffles above
     if (lane != 0) continue;
     if (ph.mode == SM_QKV) {
       // element e of the k / v projection -> row (head e / 128, pos) of the cache, column (v: 128 +) e % 128
@@ -398,7 +411,7 @@ __device__ __forceinline__ void consume_gemv(const Ring& r, uint32_t& stage0, co
       if (rb >= 0) ep.out[rb] = __float2bfloat16_rn(sb + e1);
     }
   }
-  stage0 += static_cast<uint32_t>(j);
+  stage0 += static_cast<uint32_t>(j * ph.spu);
 }
 
 // ---- attention: one warp = 4 key slots x 8 lanes; lane `sub` owns dims [8 sub, 8 sub + 8) and [64 + 8 sub, ...)
@@ -560,12 +573,13 @@ __global__ void __launch_bounds__(kSThreads, 1) decode_stream_kernel(const Strea
   // phase list of one layer; `rot` spreads the remainder units of every phase over different CTAs
   auto gemv_phase = [&](int l, int which) {
     GemvPhase ph;
+    ph.spu = 1;
     if (which == 0) { ph.W = tb.qkv_w[l]; ph.mode = SM_QKV; ph.U = 3 * D / 2; ph.K = D; ph.N = 3 * D; }
     else if (which == 1) { ph.W = tb.o_w[l]; ph.mode = SM_PLAIN2; ph.U = D / 2; ph.K = D; ph.N = D; }
     else if (which == 2) { ph.W = tb.gu_w[l]; ph.mode = SM_SWIGLU; ph.U = FF; ph.K = D; ph.N = 2 * FF; }
     else if (which == 3) {
       ph.W = tb.down_w[l]; ph.K = FF; ph.N = D;
-      if (p.down_rows == 2) { ph.mode = SM_PLAIN2; ph.U = D / 2; } else { ph.mode = SM_PLAIN1; ph.U = D; }
+      if (p.down_rows == 2) { ph.mode = SM_PLAIN2; ph.U = D / 2; } else { ph.mode = SM_PLAIN1; ph.U = D; ph.spu = p.down_split; }
     } else { ph.W = p.lm_head; ph.mode = SM_PLAIN2; ph.U = (p.V + 1) / 2; ph.K = D; ph.N = p.V; }
     return ph;
   };
@@ -759,15 +773,23 @@ __global__ void __launch_bounds__(kSThreads, 1) decode_stream_kernel(const Strea
 
 // --------------------------------------------------------------------------------------------------- host
 struct StreamGeometry {
-  int slot_bytes, nst, down_rows, smem_bytes;
+  int slot_bytes, nst, down_rows, down_split, smem_bytes;
 };
 static int stream_geometry(int D, int FF, StreamGeometry* g) {
   const int budget = 227 * 1024 - 1024;  // barriers, reduction scratch, alignment slack
   const int xs_bytes = ((D > FF ? D : FF) * 2 + 127) / 128 * 128;
   int pair = 4 * D > kKvTileBytes ? 4 * D : kKvTileBytes;
   g->down_rows = (4 * FF <= pair) ? 2 : 1;
+  g->down_split = 1;
   int slot = pair;
-  if (g->down_rows * 2 * FF > slot) slot = g->down_rows * 2 * FF;
+  if (g->down_rows == 1) {
+    // a down_proj row (2 FF bytes) is streamed in K-chunks no larger than a row pair of the other phases, so the
+    // ring slot stays small and the ring deep
+    int chunks = (2 * FF + pair - 1) / pair;
+    while (chunks <= 8 && FF % (8 * chunks) != 0) ++chunks;
+    if (chunks <= 8) g->down_split = chunks;
+    if (2 * FF / g->down_split > slot) slot = 2 * FF / g->down_split;
+  }
   slot = (slot + 127) / 128 * 128;
   int nst = (budget - xs_bytes) / slot;
   if (nst > kMaxStages) nst = kMaxStages;
@@ -873,6 +895,7 @@ int merlin_decode_stream_step(void* stream, const merlin_decoder_weights* w, con
   p.slot_bytes = g.slot_bytes;
   p.nst = g.nst;
   p.down_rows = g.down_rows;
+  p.down_split = g.down_split;
 
   // cooperative launch: every CTA must be resident (grid-wide barriers); the runtime refuses the launch
   // instead of letting it hang when they cannot be.

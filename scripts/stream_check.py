@@ -75,6 +75,12 @@ def small():
     worst = 0.0
     for ctx in (5, 31, 32, 33, 100, 700, 1500):
         worst = max(worst, compare(model, ctx, label="small"))
+    # wide MLP: a down_proj row no longer fits one ring slot and is streamed in K-chunks
+    cfg = vicuna_7b_config(hidden_size=512, num_attention_heads=4, num_key_value_heads=4, intermediate_size=11008,
+                           num_hidden_layers=2, vocab_size=1003)
+    model = MMGPTLlamaForCausalLM(cfg).to(device=DEV, dtype=torch.bfloat16)
+    for ctx in (33, 700):
+        worst = max(worst, compare(model, ctx, label="small-wide"))
     print("small worst rel diff", worst)
 
 
