@@ -137,8 +137,16 @@ class CLIPVisionTower(nn.Module):
         put(vm + "post_layernorm.bias", self.post_ln_b)
         return out
 
-    def load_state_dict(self, state_dict, strict: bool = True, assign: bool = False):
+    def load_state_dict(self, state_dict, strict: bool = True, assign: bool = False, interpolate: bool = False):
+        """interpolate=True: a position table saved at another image size (e.g. the 577-row 336 px CLIP-L/14
+        table loaded into a 448 px tower) is resized like mmgpt/utils/interpolate_model.py:11-28 does."""
         own = self.state_dict(keep_vars=True)
+        pos_key = "vision_tower.vision_model.embeddings.position_embedding.weight"
+        if interpolate and pos_key in state_dict and state_dict[pos_key].shape[0] != self.tokens:
+            from ...utils.interpolate_model import interpolate_position_embedding
+            state_dict = dict(state_dict)
+            grid = self._config.image_size // self._config.patch_size
+            state_dict[pos_key] = interpolate_position_embedding(state_dict[pos_key], grid)
         missing = [k for k in own if k not in state_dict]
         unexpected = [k for k in state_dict if k not in own and not k.endswith("position_ids")]
         if strict and (missing or unexpected):
