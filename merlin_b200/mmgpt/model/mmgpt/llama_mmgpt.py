@@ -465,18 +465,75 @@ class MMGPTLlamaForCausalLM(nn.Module, MMGPTMetaForCausalLM):
         return self._decoder
 
     @torch.no_grad()
+    def _generate_beam(self, input_ids, images, num_beams, max_new_tokens, eos_token_id, stopping_criteria,
+                       length_penalty, early_stopping, length_norm):
+        """generate(num_beams=k) (eval_box.py:246-254): ONE multimodal prefill (the reference prefills k
+        identical copies, base_mmgpt.py:162-163), then k single-sequence decode steps per position — each beam
+        has its own KV cache and decode kernel binding — with the beam bookkeeping of merlin_b200/beam.py
+        (pinned against HF `generate`) on the host and the caches re-gathered by parent beam after every step,
+        as HF's `_reorder_cache` does."""
+        from ....beam import BeamSearch
+        device = self.device
+        ids = input_ids.to(device)
+        S = ids.shape[1]
+        self._cache_capacity = S + max_new_tokens + 8
+        flag, self.use_beam_search = getattr(self, "use_beam_search", False), False
+        try:
+            out = self.forward(**self.prepare_inputs_for_generation(ids, None, None, use_cache=True, images=images))
+        finally:
+            self.use_beam_search = flag
+        cfg = self.config
+        caches = [out.past_key_values]
+        for _ in range(2 * num_beams - 1):      # beams 1..k-1 and k spares for the re-gather
+            caches.append(MerlinKVCache(cfg.num_hidden_layers, 1, caches[0].capacity, cfg.hidden_size, device))
+        blocks = lambda n: (n + 31) // 32
+
+        def copy_cache(dst, src, n_tokens):
+            for a, b in zip(dst.kv, src.kv):
+                a[:, :blocks(n_tokens)].copy_(b[:, :blocks(n_tokens)])
+            dst.seq_len = src.seq_len
+
+        for c in caches[1:num_beams]:
+            copy_cache(c, caches[0], S)
+        live, spare = caches[:num_beams], caches[num_beams:]
+        runners = {id(c): _decode.DecodeRunner(self, c) for c in caches}
+        bs = BeamSearch(input_ids.cpu(), num_beams, eos_token_id, max_new_tokens, length_penalty, early_stopping,
+                        length_norm, stopping_criteria)
+        res = bs.step(out.logits[:, -1, :].float().repeat(num_beams, 1))
+        logits = torch.empty((num_beams, cfg.vocab_size), dtype=torch.float32, device=device)
+        while res is not None:
+            tokens, parents = res
+            # beam j continues parent[j]: gather the caches (copies only where the parent changed)
+            moved = [j for j in range(num_beams) if parents[j] != j]
+            for j in moved:
+                copy_cache(spare[j], live[parents[j]], live[parents[j]].seq_len)
+            for j in moved:
+                live[j], spare[j] = spare[j], live[j]
+            tok = torch.tensor(tokens, dtype=torch.int64, device=device)
+            emb = self.model.embed_tokens[tok]
+            for j in range(num_beams):
+                logits[j].copy_(runners[id(live[j])].step_logits(emb[j:j + 1])[0])
+            res = bs.step(logits)
+        return bs.finalize().to(device)
+
+    @torch.no_grad()
     def generate(self, input_ids: torch.LongTensor, images: Optional[List[torch.Tensor]] = None,
                  max_new_tokens: int = 1024, do_sample: bool = False, temperature: float = 1.0,
                  top_p: float = 1.0, num_beams: int = 1, eos_token_id: Optional[int] = 2,
                  stopping_criteria=None, attention_mask=None, use_cache: bool = True, streamer=None,
-                 generator: Optional[torch.Generator] = None, **_):
-        """Greedy / temperature sampling with a KV cache.  Step 0 is the full multimodal prefill, later
-        steps feed one token and skip the vision path.  Returns [1, S + new] ids."""
-        if num_beams != 1:
-            raise NotImplementedError("beam search is a 'next' row (SURVEY.md §8f N4)")
+                 generator: Optional[torch.Generator] = None, **kw):
+        """Greedy decoding, temperature / top-p sampling or beam search (num_beams > 1; extra keywords
+        length_penalty, early_stopping as in HF) with a KV cache.  Step 0 is the full multimodal prefill,
+        later steps feed one token and skip the vision path.  Returns [1, S + new] ids."""
         if input_ids.shape[0] != 1:
             raise NotImplementedError("generate() handles one sequence at a time (reference eval scripts)")
         device = self.device
+        if num_beams != 1:
+            if do_sample or streamer is not None:
+                raise NotImplementedError("beam search runs without sampling and without a streamer")
+            return self._generate_beam(input_ids, images, num_beams, max_new_tokens, eos_token_id,
+                                       stopping_criteria, float(kw.get("length_penalty", 1.0)),
+                                       kw.get("early_stopping", False), kw.get("length_norm", "generated"))
         fast = (not do_sample and stopping_criteria is None and streamer is None and max_new_tokens > 0
                 and attention_mask is None and images is not None and len(images) == 1
                 and getattr(self, "use_cuda_graphs", True) and not getattr(self, "use_beam_search", False)
@@ -501,7 +558,7 @@ class MMGPTLlamaForCausalLM(nn.Module, MMGPTMetaForCausalLM):
         new_tokens = []
         for step in range(max_new_tokens):
             if do_sample and temperature > 0:
-                probs = torch.softmax(last.float() / temperature, dim=-1)
+                probs = sampling_distribution(last, temperature, top_p)
                 nxt = torch.multinomial(probs, 1, generator=generator)
             else:
                 nxt = ops.argmax(last).view(1, 1)
@@ -521,6 +578,21 @@ class MMGPTLlamaForCausalLM(nn.Module, MMGPTMetaForCausalLM):
         if streamer is not None:
             streamer.end()
         return ids
+
+
+def sampling_distribution(logits: torch.Tensor, temperature: float = 1.0, top_p: float = 1.0) -> torch.Tensor:
+    """Next-token distribution of HF sampling (`generate(do_sample=True, temperature, top_p)`, the call of
+    model_worker.py:169-176 / eval_box.py:256-263): logits / temperature (TemperatureLogitsWarper), then nucleus
+    filtering — sort ascending, drop every token whose cumulative probability is <= 1 - top_p, always keep the
+    most likely one (TopPLogitsWarper, min_tokens_to_keep=1) — then softmax."""
+    scores = logits.float() / temperature
+    if top_p < 1.0:
+        sorted_logits, sorted_idx = torch.sort(scores, descending=False, dim=-1)
+        cum = sorted_logits.softmax(dim=-1).cumsum(dim=-1)
+        remove = cum <= (1.0 - top_p)
+        remove[..., -1:] = False
+        scores = scores.masked_fill(remove.scatter(-1, sorted_idx, remove), float("-inf"))
+    return torch.softmax(scores, dim=-1)
 
 
 MerlinForCausalLM = MMGPTLlamaForCausalLM  # the name BASELINE.json's north_star uses

@@ -193,3 +193,55 @@ def test_full_width_c1_sample_matches_oracle():
     gen = model.generate(batch["input_ids"].to(DEV), images=to_dev(batch["images"]), max_new_tokens=4, eos_token_id=None)
     want = O.greedy_generate(sd, cfg, batch["input_ids"], batch["images"], 4, eos_token_id=None)
     assert torch.equal(gen.cpu(), want)
+
+
+def test_beam_search_generate_matches_oracle_driven_beam_search():
+    """generate(num_beams=3) over the kernels == the same beam bookkeeping (merlin_b200/beam.py, pinned against HF
+    on CPU) driven by the fp32 oracle's logits.  bf16 noise may reorder near-tied beams, so a different sequence
+    is accepted only if the oracle scores it as well as its own winner."""
+    from merlin_b200.beam import BeamSearch
+    g, cfg = load_golden("tiny_conv")
+    sd = O.init_state_dict(cfg, seed=0)
+    model = build_product_model(cfg, sd)
+    ids = g["input_ids"][:1]
+    images = g["images"][:1]
+    nb, max_new = 3, 6
+    got = model.generate(ids.to(DEV), images=to_dev(images), num_beams=nb, max_new_tokens=max_new,
+                         eos_token_id=None).cpu()
+    assert got.shape == (1, ids.shape[1] + max_new) and torch.equal(got[:, :ids.shape[1]], ids)
+
+    def oracle_logits(seqs):
+        rows = []
+        for s in seqs:
+            out = O.forward(sd, cfg, s.view(1, -1), None, None, images)
+            rows.append(out["logits"][0])
+        return rows
+
+    bs = BeamSearch(ids, nb, None, max_new)
+    while True:
+        rows = oracle_logits(list(bs.running))
+        if bs.step(torch.stack([r[-1] for r in rows])) is None:
+            break
+    want = bs.finalize()
+
+    def score(seq):
+        lp = torch.log_softmax(oracle_logits([seq[0]])[0], dim=-1)
+        idx = torch.arange(ids.shape[1] - 1, seq.shape[1] - 1)
+        return float(lp[idx, seq[0, ids.shape[1]:]].sum()) / max_new
+
+    if not torch.equal(got, want):
+        assert abs(score(got) - score(want)) <= 2e-2, (got.tolist(), want.tolist())
+
+
+def test_sampling_with_top_p_runs_on_the_kernels_and_respects_the_nucleus():
+    g, cfg = load_golden("tiny_conv")
+    model = build_product_model(cfg, O.init_state_dict(cfg, seed=0))
+    ids = g["input_ids"][:1].to(DEV)
+    gen = torch.Generator(device=DEV).manual_seed(0)
+    a = model.generate(ids, images=to_dev(g["images"][:1]), do_sample=True, temperature=0.2, top_p=0.7,
+                       max_new_tokens=5, eos_token_id=None, generator=gen)
+    # top_p -> 0 keeps only the most likely token: sampling degenerates to greedy decoding
+    b = model.generate(ids, images=to_dev(g["images"][:1]), do_sample=True, temperature=1.0, top_p=1e-6,
+                       max_new_tokens=5, eos_token_id=None, generator=gen)
+    c = model.generate(ids, images=to_dev(g["images"][:1]), max_new_tokens=5, eos_token_id=None)
+    assert a.shape == b.shape == c.shape and torch.equal(b, c)
