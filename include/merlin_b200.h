@@ -195,6 +195,20 @@ int merlin_record_advance(void* stream, const int64_t* token_dev, int64_t* out_i
 int merlin_kv_append(void* stream, const void* qkv, int64_t ldq, void* kv_cache, int64_t kv_capacity, int B, int S,
                      int D, int H, int pos0);
 
+/* ---- data-loader image path ----
+ * out[3, S, S] = normalize(rescale(resize(src))) for one uint8 RGB image src[H, W, 3] (row pitch in bytes): PIL's
+ * default BICUBIC `image.resize((S, S))` reproduced bit-exactly on the uint8 pixels (third-party Pillow,
+ * libImaging/Resample.c: 22-bit fixed-point weights, horizontal pass to uint8, then vertical pass), then
+ * x / 255 and (x - mean) / std as the CLIP image processor does — the 'resize' mode of
+ * mmgpt/data/dataset/base_dataset.py:190-192 and mmgpt/utils/mm_utils.py:41-43.  out is fp32 (out_bf16 = 0) or
+ * bf16; out_resized_u8 (NULL or [S, S, 3]) also receives the resized uint8 pixels.  workspace:
+ * merlin_image_preprocess_workspace_bytes, 256-byte aligned.  The filter tables are built on the host, so this
+ * call synchronises `stream` once (data-loading path, not capturable). */
+size_t merlin_image_preprocess_workspace_bytes(int H, int W, int S);
+int merlin_image_preprocess(void* stream, const void* src_rgb_u8, int64_t src_pitch_bytes, int H, int W, int S,
+                            const float* mean3, const float* std3, void* workspace, void* out, int out_bf16,
+                            void* out_resized_u8);
+
 /* ---- composite forward entry points: one call per layer, kernels sequenced on the caller's stream ---- */
 typedef struct merlin_layer_weights {       /* one Vicuna decoder layer, packed layouts as above */
   const void *qkv_w, *o_w, *gate_up_w, *down_w, *ln1_w, *ln2_w;

@@ -58,6 +58,7 @@ _PROTOTYPES = {
     "merlin_decode_stream_prepare": [_P, _P, _P],
     "merlin_decode_stream_step": [_P, _P, _P, _P, _P, _P],
     "merlin_embed_token": [_P, _P, _P, _P, c_int, c_int64],
+    "merlin_image_preprocess": [_P, _P, c_int64, c_int, c_int, c_int, _P, _P, _P, _P, c_int, _P],
     "merlin_kv_append": [_P, _P, c_int64, _P, c_int64, c_int, c_int, c_int, c_int, c_int],
     "merlin_record_advance": [_P, _P, _P, _P, _P, c_int],
 }
@@ -101,6 +102,7 @@ _PROTOTYPES["merlin_decoder_layer_backward"] = [_P, _P, _P, _P, _P, _P, _P, _P, 
 _SIZE_FNS = {"merlin_decoder_layer_saved_bytes": [c_int, c_int, c_int, c_int, c_int, c_int],
              "merlin_decoder_layer_backward_workspace_bytes": [c_int, c_int, c_int, c_int, c_int, c_int],"merlin_decode_workspace_bytes": [c_int, c_int, c_int, c_int],
              "merlin_decode_stream_workspace_bytes": [c_int, c_int, c_int, c_int],
+             "merlin_image_preprocess_workspace_bytes": [c_int, c_int, c_int],
              "merlin_flash_attn_bwd_workspace_bytes": [c_int, c_int, c_int, c_int],
              "merlin_decoder_layer_workspace_bytes": [c_int, c_int, c_int],
              "merlin_vit_layer_workspace_bytes": [c_int, c_int, c_int]}

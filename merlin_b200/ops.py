@@ -178,6 +178,30 @@ def gemm_qkv_rope(a: torch.Tensor, w_qkv: torch.Tensor, rope_cos: torch.Tensor, 
     return out
 
 
+def image_preprocess(pixels: torch.Tensor, size: int, mean=(0.48145466, 0.4578275, 0.40821073),
+                     std=(0.26862954, 0.26130258, 0.27577711), dtype=torch.float32, return_resized: bool = False):
+    """uint8 RGB image [H, W, 3] on the GPU -> [3, size, size]: PIL-exact bicubic resize, /255, CLIP mean / std
+    (merlin_image_preprocess; base_dataset.py:190-192)."""
+    import ctypes
+    if pixels.dtype != torch.uint8 or pixels.dim() != 3 or pixels.shape[2] != 3 or not pixels.is_cuda:
+        raise ValueError("image_preprocess: expected a CUDA uint8 [H, W, 3] tensor")
+    if dtype not in (torch.float32, _BF16):
+        raise ValueError("image_preprocess: dtype must be float32 or bfloat16")
+    pixels = pixels.contiguous()
+    H, W, _ = pixels.shape
+    L = _lib.load()
+    ws = torch.empty(L.merlin_image_preprocess_workspace_bytes(H, W, size) + 256, dtype=torch.uint8, device=pixels.device)
+    ws_ptr = ws.data_ptr() + (-ws.data_ptr()) % 256
+    out = torch.empty((3, size, size), dtype=dtype, device=pixels.device)
+    resized = torch.empty((size, size, 3), dtype=torch.uint8, device=pixels.device) if return_resized else None
+    m = (ctypes.c_float * 3)(*[float(v) for v in mean])
+    s = (ctypes.c_float * 3)(*[float(v) for v in std])
+    check(L.merlin_image_preprocess(_stream(), pixels.data_ptr(), W * 3, H, W, size, m, s, ws_ptr, out.data_ptr(),
+                                    1 if dtype == _BF16 else 0, _ptr(resized)), "merlin_image_preprocess")
+    PROFILE.launches += 2
+    return (out, resized) if return_resized else out
+
+
 def kv_append(qkv: torch.Tensor, kv_cache: torch.Tensor, batch: int, seq: int, hidden: int, heads: int,
               pos0: int = 0) -> None:
     """Packed qkv rows [batch*seq, 3*hidden] -> cache [batch, capacity/32, heads, 32, 256] at tokens

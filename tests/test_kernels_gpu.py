@@ -470,3 +470,28 @@ def test_flash_attention_backward_hd64(causal):
     mine = dqkv.float().view(B * S, 3, H * hd)
     for blk in range(3):
         close(mine[:, blk], g[:, blk], tol=2.0 ** -6)
+
+
+@pytest.mark.parametrize("hw", [(480, 640), (336, 336), (1080, 1920), (100, 57), (37, 336)])
+def test_image_preprocess_is_bit_exact_with_pillow_resize(hw):
+    """merlin_image_preprocess: the uint8 pixels after the bicubic resize equal Pillow's `image.resize((S, S))`
+    bit for bit (and the numpy oracle's), the normalised fp32 output equals the oracle's rescale / normalize
+    exactly, bf16 output is its RNE rounding (base_dataset.py:190-192)."""
+    import numpy as np
+    from oracle import image_oracle as IO
+    rng = np.random.default_rng(hw[0] + hw[1])
+    img = rng.integers(0, 256, size=(hw[0], hw[1], 3), dtype=np.uint8)
+    img[: hw[0] // 3] = 255
+    mean, std = (0.48145466, 0.4578275, 0.40821073), (0.26862954, 0.26130258, 0.27577711)
+    out, resized = ops.image_preprocess(torch.from_numpy(img).cuda(), 336, mean, std, return_resized=True)
+    want_u8 = IO.resize_bicubic_u8(img, 336)
+    assert torch.equal(resized.cpu(), torch.from_numpy(want_u8))
+    try:
+        from PIL import Image
+        assert np.array_equal(resized.cpu().numpy(), np.asarray(Image.fromarray(img).resize((336, 336))))
+    except ImportError:
+        pass
+    want = torch.from_numpy(IO.rescale_normalize(want_u8, mean, std))
+    assert torch.equal(out.cpu(), want)
+    out16 = ops.image_preprocess(torch.from_numpy(img).cuda(), 336, mean, std, dtype=torch.bfloat16)
+    assert torch.equal(out16.cpu(), want.to(torch.bfloat16))
