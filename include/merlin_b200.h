@@ -158,7 +158,8 @@ typedef struct merlin_decoder_weights {
   const float* rope_sin;
 } merlin_decoder_weights;
 
-/* Bytes of scratch merlin_decode_step needs. */
+/* Bytes of scratch merlin_decode_step needs.  The caller zero-fills the workspace ONCE before its first use (it
+ * holds self-resetting arrival counters); no re-zeroing between calls. */
 size_t merlin_decode_workspace_bytes(int hidden, int intermediate, int heads, int n_splits);
 
 /* One decoder pass for the token whose embedding is x[hidden] (bf16, overwritten with the final

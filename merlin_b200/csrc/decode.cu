@@ -499,14 +499,8 @@ int merlin_decode_step(void* stream, const merlin_decoder_weights* w, void* x, c
   float* part_o = reinterpret_cast<float*>(ws + ((static_cast<size_t>(3 * D + FF) * 2 + 255) / 256 * 256));
   float* part_ml = part_o + static_cast<size_t>(H) * n_splits * 128;
   unsigned int* tickets = reinterpret_cast<unsigned int*>(part_ml + static_cast<size_t>(H) * n_splits * 2);
-  {
-    // the per-head arrival counters must start at zero once; they reset themselves afterwards
-    static thread_local void* zeroed_ws = nullptr;
-    if (zeroed_ws != workspace) {
-      MB_CHECK_CUDA(cudaMemsetAsync(tickets, 0, static_cast<size_t>(H) * sizeof(unsigned int), st));
-      zeroed_ws = workspace;
-    }
-  }
+  // `tickets` (per-head arrival counters of the flash-decode merge) must be zero on first use — the caller
+  // zero-fills the workspace once; the last arriver of every head resets its counter for the next layer / token.
   __nv_bfloat16* xb = static_cast<__nv_bfloat16*>(x);
   const float scale_log2e = 1.4426950408889634f / sqrtf(128.f);
   int rc;

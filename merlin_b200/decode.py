@@ -53,7 +53,9 @@ class DecodeRunner:
         L_ = _lib.load()
         nbytes = L_.merlin_decode_workspace_bytes(cfg.hidden_size, cfg.intermediate_size,
                                                   cfg.num_attention_heads, N_SPLITS)
-        self.ws = torch.empty(nbytes, dtype=torch.uint8, device=dev)
+        # zeroed: the per-head arrival tickets of the flash-decode merge must start at 0 (the allocator may hand
+        # back a block that an earlier runner left dirty)
+        self.ws = torch.zeros(nbytes, dtype=torch.uint8, device=dev)
         self.x = torch.empty(cfg.hidden_size, dtype=torch.bfloat16, device=dev)
         self.logits = torch.empty((1, (cfg.vocab_size + 7) // 8 * 8), dtype=torch.bfloat16, device=dev)[:, :cfg.vocab_size]
         self.pos = torch.zeros(1, dtype=torch.int32, device=dev)

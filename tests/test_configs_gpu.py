@@ -94,8 +94,9 @@ def _decode_both(model, ctx, steps=2):
         lb = rb.step_logits(emb).float().clone()
         full = model(input_ids=toks).logits[0, -1].float()
         out.append((la[0], lb[0], full))
-    new_rows = [(x[0, :, :, :].float(), y[0, :, :, :].float()) for x, y in zip(ca.kv, cb.kv)]
-    return out, new_rows
+    t = torch.arange(ctx + steps, device=DEV)            # rows written so far: cache[0, t // 32, :, t % 32]
+    rows = [(x[0, t // 32, :, t % 32].float(), y[0, t // 32, :, t % 32].float()) for x, y in zip(ca.kv, cb.kv)]
+    return out, rows
 
 
 @pytest.mark.parametrize("dims", ["7b", "13b"])
