@@ -44,14 +44,17 @@ static int launch_attn2(cudaStream_t stream, const CUtensorMap& tq, const CUtens
   return MERLIN_OK;
 }
 
-// 1 = one query tile per CTA (attn.cuh), 2 = two query tiles, ping-pong softmax, P in TMEM (attn2.cuh)
-static int attn_version() {
-  static int v = -1;
-  if (v < 0) {
+// 1 = one query tile per CTA (attn.cuh), 2 = two query tiles per CTA, ping-pong softmax, P in TMEM (attn2.cuh,
+// 20 % faster at S = 4096).  Default: v2 for the long causal head_dim-128 sequences of the decoder prefill /
+// training forward (where it was profiled), v1 everywhere else; MERLIN_ATTN_V=1|2 forces one of them.
+static int attn_version(int S, int head_dim, int causal) {
+  static int forced = -1;
+  if (forced < 0) {
     const char* e = getenv("MERLIN_ATTN_V");
-    v = (e && e[0] == '2') ? 2 : 1;
+    forced = (e && (e[0] == '1' || e[0] == '2')) ? (e[0] - '0') : 0;
   }
-  return v;
+  if (forced) return forced;
+  return (head_dim == 128 && causal && S >= 1024) ? 2 : 1;
 }
 
 }  // namespace mb
@@ -95,7 +98,7 @@ extern "C" int merlin_flash_attn_fwd(void* stream, const void* qkv, int64_t ld_q
     if ((rc = make_tmap_bf16(&to, out, 3, dims, str, box)) != MERLIN_OK) return rc;
   }
   cudaStream_t st = static_cast<cudaStream_t>(stream);
-  if (attn_version() == 2) {
+  if (attn_version(S, head_dim, causal) == 2) {
     if (head_dim == 128)
       return causal ? launch_attn2<128, true>(st, tq, to, p) : launch_attn2<128, false>(st, tq, to, p);
     return causal ? launch_attn2<64, true>(st, tq, to, p) : launch_attn2<64, false>(st, tq, to, p);
