@@ -227,9 +227,22 @@ class GraphedGenerator:
         return torch.cat([self.ids, new.view(1, -1)], dim=1)
 
 
+def weight_fingerprint(lm) -> int:
+    """Changes whenever a parameter the captured graphs / the streaming kernel's pointer tables refer to moves
+    (e.g. the trainer re-homes the parameters into its flat arena)."""
+    m = lm.model
+    probes = (m.embed_tokens, lm.lm_head_w, m.norm_w, m.qkv_w[0], m.o_w[0], m.gate_up_w[0], m.down_w[0],
+              m.qkv_w[-1], m.down_w[-1], m.ln1_w[0], m.ln2_w[-1])
+    return hash(tuple(p.data_ptr() for p in probes))
+
+
 def graphed_generate(lm, input_ids, images, max_new_tokens, eos_token_id):
     key = (int(input_ids.shape[1]), tuple(images.shape))
     pool = lm.__dict__.setdefault("_graphed", {})
+    fp = weight_fingerprint(lm)
+    if lm.__dict__.get("_graphed_fp") != fp:      # graphs captured for other weight addresses are stale
+        pool.clear()
+        lm.__dict__["_graphed_fp"] = fp
     gen = pool.get(key)
     need = input_ids.shape[1] + max_new_tokens + 8
     if gen is None or gen.cache.capacity < need:

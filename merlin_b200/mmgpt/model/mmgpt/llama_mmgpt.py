@@ -460,8 +460,10 @@ class MMGPTLlamaForCausalLM(nn.Module, MMGPTMetaForCausalLM):
         return model_inputs
 
     def _get_decoder(self, cache: MerlinKVCache):
-        if self._decoder is None or self._decoder.cache is not cache:
+        fp = _decode.weight_fingerprint(self)
+        if self._decoder is None or self._decoder.cache is not cache or self._decoder.fingerprint != fp:
             self._decoder = _decode.DecodeRunner(self, cache)
+            self._decoder.fingerprint = fp
         return self._decoder
 
     @torch.no_grad()
