@@ -76,21 +76,21 @@ class InterPairWebDataset:
 
     # ------------------------------------------------------------------ image path (base_dataset.py:179-198)
     def _load_image(self, data: bytes) -> torch.Tensor:
-        """'resize' mode: decode -> RGB -> square bicubic resize -> /255 -> CLIP mean / std, on the GPU when one
-        is there (merlin_image_preprocess), else through PIL + the processor exactly like the reference."""
+        """'resize' mode: decode -> RGB -> square bicubic resize -> /255 -> CLIP mean / std.  The decode is PIL's
+        (JPEG entropy decoding is not part of this path); resize + normalise run in merlin_image_preprocess on
+        the GPU — there is no CPU fallback: without a CUDA device / the library this raises."""
+        import numpy as np
         from PIL import Image
+        from .... import ops
+        if not torch.cuda.is_available():
+            raise RuntimeError("InterPairWebDataset: the image path runs on the GPU (merlin_image_preprocess); "
+                               "pass image_loader= to supply pre-processed tensors on a machine without one")
         image = Image.open(io.BytesIO(data)).convert("RGB")
-        if torch.cuda.is_available():
-            from .... import ops
-            import numpy as np
-            proc = self.multimodal_cfg.get("image_processor")
-            mean = getattr(proc, "image_mean", (0.48145466, 0.4578275, 0.40821073))
-            std = getattr(proc, "image_std", (0.26862954, 0.26130258, 0.27577711))
-            pixels = torch.from_numpy(np.asarray(image)).cuda()
-            return ops.image_preprocess(pixels, self.image_size, mean, std).cpu()
-        image = image.resize((self.image_size, self.image_size))
-        proc = self.multimodal_cfg["image_processor"]
-        return proc.preprocess(image, return_tensors="pt", do_resize=False, do_center_crop=False)["pixel_values"][0]
+        proc = self.multimodal_cfg.get("image_processor")
+        mean = getattr(proc, "image_mean", None) or (0.48145466, 0.4578275, 0.40821073)
+        std = getattr(proc, "image_std", None) or (0.26862954, 0.26130258, 0.27577711)
+        pixels = torch.from_numpy(np.asarray(image)).cuda()
+        return ops.image_preprocess(pixels, self.image_size, mean, std).cpu()
 
     # ------------------------------------------------------------------ token grammar (:53-152)
     def add_image_token(self, text):

@@ -495,3 +495,43 @@ def test_image_preprocess_is_bit_exact_with_pillow_resize(hw):
     assert torch.equal(out.cpu(), want)
     out16 = ops.image_preprocess(torch.from_numpy(img).cuda(), 336, mean, std, dtype=torch.bfloat16)
     assert torch.equal(out16.cpu(), want.to(torch.bfloat16))
+
+
+def test_interpair_dataset_image_path_runs_the_gpu_kernel(tmp_path):
+    """InterPairWebDataset over a local tar shard with its default image loader: JPEG bytes -> PIL decode ->
+    merlin_image_preprocess; equals the reference's PIL resize + CLIP processor arithmetic (oracle)."""
+    import io
+    import json
+    import tarfile
+    import types
+    import numpy as np
+    from PIL import Image
+    from oracle import image_oracle as IO
+    from merlin_b200.mmgpt.data.dataset.interpair_webdataset import InterPairWebDataset
+    rng = np.random.default_rng(5)
+    buf = io.BytesIO()
+    Image.fromarray(rng.integers(0, 256, (90, 120, 3), dtype=np.uint8)).save(buf, format="JPEG")
+    jpg = buf.getvalue()
+    shard = tmp_path / "s.tar"
+    with tarfile.open(shard, "w") as tf:
+        for name, data in (("r0.json", json.dumps(dict(prompt="Look <image>", txt="a thing", image_name_list=["v-f0"])).encode()),
+                           ("r0.f0.jpg", jpg)):
+            ti = tarfile.TarInfo(name)
+            ti.size = len(data)
+            tf.addfile(ti, io.BytesIO(data))
+
+    class Tok:
+        eos_token, pad_token_id, model_max_length = "</s>", 0, 128
+
+        def convert_tokens_to_ids(self, toks):
+            return [32000, 32001, 32002]
+
+        def __call__(self, text, padding=None, max_length=None, truncation=False):
+            return types.SimpleNamespace(input_ids=[1] + [5] * min(len(text.split()), 20))
+
+    ds = InterPairWebDataset([str(shard)], Tok(), dict(image_token_len=4, use_im_start_end=True, image_size=56,
+                                                       image_processor=None))
+    sample = ds[0]
+    want = IO.image_preprocess(np.asarray(Image.open(io.BytesIO(jpg)).convert("RGB")), 56,
+                               (0.48145466, 0.4578275, 0.40821073), (0.26862954, 0.26130258, 0.27577711))
+    assert len(sample["image"]) == 1 and torch.equal(sample["image"][0], torch.from_numpy(want))
