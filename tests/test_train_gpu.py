@@ -166,3 +166,92 @@ def test_data_parallel_replicas_stay_bit_identical():
                         os.path.join(root, "scripts", "dp_check.py")], capture_output=True, text=True, timeout=600)
     assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]
     assert "weights identical across ranks: True" in r.stdout
+
+
+def test_local_shards_to_training_step_end_to_end(tmp_path):
+    """N2 <-> a11: tar shards on disk -> build_dataloader (InterPairWebDataset + merlin_image_preprocess on the
+    GPU + DataCollatorForSupervisedDataset) -> MMGPTTrainer.training_step.  The first loss equals the oracle's
+    loss on the same batch (pixels restated by oracle/image_oracle.py), and training reduces it."""
+    import io
+    import json
+    import tarfile
+    import types
+    import numpy as np
+    from PIL import Image
+    from oracle import image_oracle as IO
+    from merlin_b200.mmgpt.data.builder import build_dataloader
+
+    g, cfg = load_golden("tiny_conv")
+    sd = O.init_state_dict(cfg, seed=0)
+    model = build_product_model(cfg, sd)
+
+    class Tok:   # word-level tokenizer inside the tiny vocabulary (ids 3..255), HF call signature
+        eos_token, pad_token_id, model_max_length = "</s>", 0, 96
+        special = {"<im_patch>": cfg.im_patch_token, "<im_start>": cfg.im_start_token, "<im_end>": cfg.im_end_token,
+                   "</s>": 2, "\n": 13}
+
+        def convert_tokens_to_ids(self, toks):
+            return [self.special[t] for t in toks]
+
+        def __call__(self, text, padding=None, max_length=None, truncation=False):
+            ids, i, word = [1], 0, ""
+            flush = lambda w: ids.extend(3 + (sum(map(ord, x)) % 250) for x in w.split())
+            while i < len(text):
+                for sp, tid in self.special.items():
+                    if text.startswith(sp, i):
+                        flush(word)
+                        word = ""
+                        ids.append(tid)
+                        i += len(sp)
+                        break
+                else:
+                    word += text[i]
+                    i += 1
+            flush(word)
+            return types.SimpleNamespace(input_ids=ids[:max_length] if truncation and max_length else ids)
+
+    rng = np.random.default_rng(11)
+    jpgs = {}
+    shard = tmp_path / "interpair-000.tar"
+    with tarfile.open(shard, "w") as tf:
+        def add(name, data):
+            ti = tarfile.TarInfo(name)
+            ti.size = len(data)
+            tf.addfile(ti, io.BytesIO(data))
+        for r in range(4):
+            meta = dict(prompt="Track the object <image> then <image>", txt=f"it moves {['left', 'right', 'up', 'down'][r]} fast",
+                        image_name_list=[f"clip{r}-f0", f"clip{r}-f1"])
+            add(f"rec{r}.json", json.dumps(meta).encode())
+            for j in range(2):
+                buf = io.BytesIO()
+                Image.fromarray(rng.integers(0, 256, (70 + 9 * r, 96, 3), dtype=np.uint8)).save(buf, format="JPEG")
+                jpgs[(r, j)] = buf.getvalue()
+                add(f"rec{r}.f{j}.jpg", buf.getvalue())
+
+    data_args = types.SimpleNamespace(image_token_len=cfg.num_patches, image_aspect_ratio="resize", use_im_start_end=True,
+                                      image_processor=None, box_limit=0, image_size=cfg.image_size,
+                                      interpair_webdatasets=str(tmp_path / "interpair-*.tar"))
+    parts = build_dataloader(Tok(), data_args)
+    ds, collate = parts["train_dataset"], parts["data_collator"]
+    assert len(ds) == 4
+    batch = collate([ds[0], ds[1]])
+    assert batch["input_ids"].shape[0] == 2 and [tuple(i.shape) for i in batch["images"]] == [(2, 3, 56, 56)] * 2
+    assert int((batch["input_ids"] == cfg.im_patch_token).sum()) == 2 * 2 * cfg.num_patches
+
+    # oracle loss on the same batch, pixels restated on the CPU (bit-identical to the GPU image path)
+    mean, std = (0.48145466, 0.4578275, 0.40821073), (0.26862954, 0.26130258, 0.27577711)
+    ref_images = [torch.stack([torch.from_numpy(IO.image_preprocess(
+        np.asarray(Image.open(io.BytesIO(jpgs[(r, j)])).convert("RGB")), cfg.image_size, mean, std)) for j in range(2)])
+        for r in range(2)]
+    assert all(torch.equal(a, b) for a, b in zip(batch["images"], ref_images))
+    ref = O.forward(sd, cfg, batch["input_ids"], batch["attention_mask"], batch["labels"], ref_images)
+
+    for p in model.parameters():
+        p.requires_grad_(True)
+    for p in model.get_model().vision_tower.parameters():
+        p.requires_grad_(False)
+    trainer = MMGPTTrainer(model, TrainingArguments(learning_rate=2e-3, warmup_ratio=0.0, max_steps=20))
+    dev_batch = dict(batch, images=[im.to(DEV) for im in batch["images"]])
+    losses = [trainer.training_step(dev_batch).item() for _ in range(8)]
+    assert abs(losses[0] - ref["loss"].item()) <= 2e-3, (losses[0], ref["loss"].item())
+    assert losses[-1] < losses[0] - 0.5, losses
