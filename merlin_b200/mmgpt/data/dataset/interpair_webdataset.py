@@ -89,7 +89,7 @@ class InterPairWebDataset:
         proc = self.multimodal_cfg.get("image_processor")
         mean = getattr(proc, "image_mean", None) or (0.48145466, 0.4578275, 0.40821073)
         std = getattr(proc, "image_std", None) or (0.26862954, 0.26130258, 0.27577711)
-        pixels = torch.from_numpy(np.asarray(image)).cuda()
+        pixels = torch.from_numpy(np.array(image)).cuda()      # np.array: a writable copy of PIL's buffer
         return ops.image_preprocess(pixels, self.image_size, mean, std).cpu()
 
     # ------------------------------------------------------------------ token grammar (:53-152)
