@@ -28,8 +28,9 @@ def build_dataloader(tokenizer, data_args):
     for kind in ("conversation_datasets", "pair_webdatasets", "pair_token_webdatasets", "interleave_webdatasets"):
         if getattr(data_args, kind, None):
             raise NotImplementedError(f"{kind}: only the interpair datasets are mirrored (SURVEY.md §8f N2)")
-    if multimodal_cfg["image_aspect_ratio"] != "resize":
-        raise NotImplementedError("image_aspect_ratio: only the 'resize' image path runs on the GPU kernel")
+    if multimodal_cfg["image_aspect_ratio"] not in ("resize", "pad"):
+        raise NotImplementedError("image_aspect_ratio: the GPU image path covers 'resize' and 'pad' ('keep' yields "
+                                  "variable-size images that the fixed-resolution CLIP tower cannot take)")
     datasets = []
     for entry in (getattr(data_args, "interpair_webdatasets", None) or "").split("+"):
         if not entry:

@@ -76,7 +76,8 @@ class InterPairWebDataset:
 
     # ------------------------------------------------------------------ image path (base_dataset.py:179-198)
     def _load_image(self, data: bytes) -> torch.Tensor:
-        """'resize' mode: decode -> RGB -> square bicubic resize -> /255 -> CLIP mean / std.  The decode is PIL's
+        """'resize' mode: decode -> RGB -> square bicubic resize -> /255 -> CLIP mean / std ('pad' mode: the image
+        is first expanded to a square on the mean colour, base_dataset.py:186-188).  The decode is PIL's
         (JPEG entropy decoding is not part of this path); resize + normalise run in merlin_image_preprocess on
         the GPU — there is no CPU fallback: without a CUDA device / the library this raises."""
         import numpy as np
@@ -89,8 +90,11 @@ class InterPairWebDataset:
         proc = self.multimodal_cfg.get("image_processor")
         mean = getattr(proc, "image_mean", None) or (0.48145466, 0.4578275, 0.40821073)
         std = getattr(proc, "image_std", None) or (0.26862954, 0.26130258, 0.27577711)
+        mode = self.multimodal_cfg.get("image_aspect_ratio", "resize")
+        if mode not in ("resize", "pad"):
+            raise NotImplementedError(f"image_aspect_ratio={mode!r}: the GPU image path covers 'resize' and 'pad'")
         pixels = torch.from_numpy(np.array(image)).cuda()      # np.array: a writable copy of PIL's buffer
-        return ops.image_preprocess(pixels, self.image_size, mean, std).cpu()
+        return ops.image_preprocess(pixels, self.image_size, mean, std, pad_to_square=(mode == "pad")).cpu()
 
     # ------------------------------------------------------------------ token grammar (:53-152)
     def add_image_token(self, text):

@@ -179,14 +179,23 @@ def gemm_qkv_rope(a: torch.Tensor, w_qkv: torch.Tensor, rope_cos: torch.Tensor, 
 
 
 def image_preprocess(pixels: torch.Tensor, size: int, mean=(0.48145466, 0.4578275, 0.40821073),
-                     std=(0.26862954, 0.26130258, 0.27577711), dtype=torch.float32, return_resized: bool = False):
+                     std=(0.26862954, 0.26130258, 0.27577711), dtype=torch.float32, return_resized: bool = False,
+                     pad_to_square: bool = False):
     """uint8 RGB image [H, W, 3] on the GPU -> [3, size, size]: PIL-exact bicubic resize, /255, CLIP mean / std
-    (merlin_image_preprocess; base_dataset.py:190-192)."""
+    (merlin_image_preprocess; mode 'resize' of base_dataset.py:190-192).  pad_to_square=True is mode 'pad'
+    (base_dataset.py:186-188): the image is first pasted at the top-left corner of a max(H, W) square filled with
+    int(255 * mean) (`expand2square`, mm_utils.py:10-21) — a device-side buffer fill + copy — then resized."""
     import ctypes
     if pixels.dtype != torch.uint8 or pixels.dim() != 3 or pixels.shape[2] != 3 or not pixels.is_cuda:
         raise ValueError("image_preprocess: expected a CUDA uint8 [H, W, 3] tensor")
     if dtype not in (torch.float32, _BF16):
         raise ValueError("image_preprocess: dtype must be float32 or bfloat16")
+    if pad_to_square and pixels.shape[0] != pixels.shape[1]:
+        side = max(pixels.shape[0], pixels.shape[1])
+        canvas = torch.empty((side, side, 3), dtype=torch.uint8, device=pixels.device)
+        canvas[:] = torch.tensor([int(m * 255) for m in mean], dtype=torch.uint8, device=pixels.device)
+        canvas[:pixels.shape[0], :pixels.shape[1]] = pixels
+        pixels = canvas
     pixels = pixels.contiguous()
     H, W, _ = pixels.shape
     L = _lib.load()

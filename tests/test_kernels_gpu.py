@@ -535,3 +535,21 @@ def test_interpair_dataset_image_path_runs_the_gpu_kernel(tmp_path):
     want = IO.image_preprocess(np.asarray(Image.open(io.BytesIO(jpg)).convert("RGB")), 56,
                                (0.48145466, 0.4578275, 0.40821073), (0.26862954, 0.26130258, 0.27577711))
     assert len(sample["image"]) == 1 and torch.equal(sample["image"][0], torch.from_numpy(want))
+
+
+def test_image_preprocess_pad_mode_matches_expand2square_then_pillow():
+    """mode 'pad' (base_dataset.py:186-188): expand2square on int(255 * mean), then the processor's bicubic resize."""
+    import numpy as np
+    from PIL import Image
+    from oracle import image_oracle as IO
+    from merlin_b200.mmgpt.utils.mm_utils import expand2square
+    mean, std = (0.48145466, 0.4578275, 0.40821073), (0.26862954, 0.26130258, 0.27577711)
+    rng = np.random.default_rng(3)
+    for hw in ((200, 321), (400, 150)):
+        img = rng.integers(0, 256, size=(hw[0], hw[1], 3), dtype=np.uint8)
+        sq = expand2square(Image.fromarray(img), tuple(int(x * 255) for x in mean))
+        want_u8 = np.asarray(sq.resize((224, 224), resample=Image.BICUBIC))
+        out, resized = ops.image_preprocess(torch.from_numpy(img).cuda(), 224, mean, std, return_resized=True,
+                                            pad_to_square=True)
+        assert np.array_equal(resized.cpu().numpy(), want_u8)
+        assert torch.equal(out.cpu(), torch.from_numpy(IO.rescale_normalize(want_u8, mean, std)))
