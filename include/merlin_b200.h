@@ -233,6 +233,20 @@ size_t merlin_vit_layer_workspace_bytes(int M, int d, int ff);
 int merlin_vit_layer_forward(void* stream, const merlin_vit_layer_weights* w, void* h, void* workspace, int n_img,
                              int tokens, int d, int heads, int ff, float eps, int cta_group);
 
+/* lm_head + shifted cross-entropy in one call (mmgpt/model/mmgpt/llama_mmgpt.py:86-100): logits[M, V] (row pitch
+ * ldl elements, multiple of 8) = hidden[M, D] . lm_head[V, D]^T, and, when labels != NULL, the shifted fp32 CE of
+ * merlin_cross_entropy_fwd (loss_sum_count[2], optional row_nll[M]).  M = B*S. */
+int merlin_lmhead_ce_forward(void* stream, const void* hidden, int64_t ldh, const void* lm_head_w, void* logits,
+                             int64_t ldl, const int64_t* labels, int B, int S, int D, int V, int64_t ignore_index,
+                             float* row_nll, float* loss_sum_count, int cta_group);
+/* Its backward (autograd of the two lines above): `logits` is overwritten with dlogits (merlin_cross_entropy_bwd
+ * in place, scaled by grad_scale / count), d_lm_head_w[V, D] (NULL to skip) receives dlogits^T . hidden (added to
+ * its contents when accumulate != 0), dhidden[M, D] receives dlogits . lm_head. */
+int merlin_lmhead_ce_backward(void* stream, void* logits, int64_t ldl, const int64_t* labels, int B, int S, int D, int V,
+                              int64_t ignore_index, const float* loss_sum_count, float grad_scale, const void* hidden,
+                              int64_t ldh, const void* lm_head_w, void* d_lm_head_w, int accumulate, void* dhidden,
+                              int64_t lddh, int cta_group);
+
 /* Training forms of the decoder layer.  `saved` (merlin_decoder_layer_saved_bytes) keeps x_in, xn1, qkv, att,
  * x_mid, xn2, gate_up, mid and lse in that order (x_in first: a layer may write its output directly into the
  * next layer's saved block).  backward: dx [B*S, D] holds dL/dx_out on entry and dL/dx_in on return; weight

@@ -202,4 +202,41 @@ int merlin_decoder_layer_backward(void* stream, const merlin_layer_weights* w, c
   return merlin_rmsnorm_bwd(stream, s.x_in, w->ln1_w, dxn, dx_mid, dx, g->ln1_w_f32, M, D, eps);
 }
 
+// ---- lm_head + shifted cross-entropy (llama_mmgpt.py:86-100) as one call each way
+int merlin_lmhead_ce_forward(void* stream, const void* hidden, int64_t ldh, const void* lm_head_w, void* logits,
+                             int64_t ldl, const int64_t* labels, int B, int S, int D, int V, int64_t ignore_index,
+                             float* row_nll, float* loss_sum_count, int cta_group) {
+  MB_CHECK_ARG(hidden && lm_head_w && logits, "lmhead_ce_forward: null argument");
+  MB_CHECK_ARG(labels == nullptr || loss_sum_count != nullptr, "lmhead_ce_forward: labels need loss_sum_count");
+  const int M = B * S;
+  int rc;
+  if ((rc = merlin_gemm_bf16(stream, hidden, ldh, lm_head_w, D, logits, ldl, nullptr, 0, nullptr, M, V, D,
+                             MERLIN_EPI_STORE, cta_group)) != MERLIN_OK)
+    return rc;
+  if (labels == nullptr) return MERLIN_OK;
+  return merlin_cross_entropy_fwd(stream, logits, ldl, labels, B, S, V, ignore_index, row_nll, loss_sum_count);
+}
+
+// logits (in) -> dlogits (in place); d_lm_head (+)= dlogits^T . hidden; dhidden = dlogits . lm_head
+int merlin_lmhead_ce_backward(void* stream, void* logits, int64_t ldl, const int64_t* labels, int B, int S, int D, int V,
+                              int64_t ignore_index, const float* loss_sum_count, float grad_scale, const void* hidden,
+                              int64_t ldh, const void* lm_head_w, void* d_lm_head_w, int accumulate, void* dhidden,
+                              int64_t lddh, int cta_group) {
+  MB_CHECK_ARG(logits && labels && loss_sum_count && hidden && lm_head_w && dhidden, "lmhead_ce_backward: null argument");
+  const int M = B * S;
+  int rc;
+  if ((rc = merlin_cross_entropy_bwd(stream, logits, ldl, labels, B, S, V, ignore_index, loss_sum_count, grad_scale,
+                                     logits, ldl)) != MERLIN_OK)
+    return rc;
+  if (d_lm_head_w != nullptr) {   // wgrad: [V, D] = dlogits[M, V]^T . hidden[M, D]
+    if ((rc = merlin_gemm_bf16_ex(stream, logits, ldl, 1, hidden, ldh, 1, d_lm_head_w, D, accumulate ? d_lm_head_w : nullptr,
+                                  D, nullptr, V, D, M, accumulate ? MERLIN_EPI_RESIDUAL : MERLIN_EPI_STORE,
+                                  cta_group)) != MERLIN_OK)
+      return rc;
+  }
+  // dgrad: [M, D] = dlogits[M, V] . lm_head[V, D]
+  return merlin_gemm_bf16_ex(stream, logits, ldl, 0, lm_head_w, D, 1, dhidden, lddh, nullptr, 0, nullptr, M, D, V,
+                             MERLIN_EPI_STORE, cta_group);
+}
+
 }  // extern "C"

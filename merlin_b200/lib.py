@@ -95,6 +95,10 @@ class LayerGrads(ctypes.Structure):
     _fields_ = [(n, c_void_p) for n in ("qkv_w", "o_w", "gate_up_w", "down_w", "ln1_w_f32", "ln2_w_f32")]
 
 
+_PROTOTYPES["merlin_lmhead_ce_forward"] = [_P, _P, c_int64, _P, _P, c_int64, _P, c_int, c_int, c_int, c_int, c_int64, _P, _P,
+                                          c_int]
+_PROTOTYPES["merlin_lmhead_ce_backward"] = [_P, _P, c_int64, _P, c_int, c_int, c_int, c_int, c_int64, _P, c_float, _P,
+                                           c_int64, _P, _P, c_int, _P, c_int64, c_int]
 _PROTOTYPES["merlin_decoder_layer_forward_train"] = [_P, _P, _P, _P, _P, _P, _P, _P, c_int, c_int, c_int, c_int, c_int,
                                                      c_float, c_int]
 _PROTOTYPES["merlin_decoder_layer_backward"] = [_P, _P, _P, _P, _P, _P, _P, _P, _P, c_int, c_int, c_int, c_int, c_int,

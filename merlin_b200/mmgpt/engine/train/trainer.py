@@ -143,13 +143,13 @@ class MMGPTTrainer:
             ops.decoder_layer_forward_train(self._layer_weights(i), x_src, x_dst, bufs["saved"][i], cos, sin, seqlens,
                                             B, S, D, H, cfg.intermediate_size, cfg.rms_norm_eps)
         hn = ops.rmsnorm(x_final, m.norm_w, cfg.rms_norm_eps)
-        logits = ops.gemm(hn, model.lm_head_w)
+        # lm_head + shifted CE, forward and backward, one library call each (merlin_lmhead_ce_forward / _backward)
+        logits, loss, loss_acc = ops.lmhead_ce_forward(hn, model.lm_head_w, labels_dev, B, S, IGNORE_INDEX)
 
         # ---- backward
-        loss, dlogits = ops.cross_entropy_with_grad(logits, labels_dev, B, S, IGNORE_INDEX, grad_scale)
         acc = accumulate
-        ops.gemm_tn(dlogits, hn, out=g("lm_head.weight"), accumulate=acc)
-        dhn = ops.gemm_nt(dlogits, model.lm_head_w)
+        dhn = ops.lmhead_ce_backward(logits, labels_dev, loss_acc, grad_scale, hn, model.lm_head_w,
+                                     g("lm_head.weight"), acc, B, S, IGNORE_INDEX)
         dx = ops.rmsnorm_bwd(x_final, m.norm_w, dhn, None, self._f32["model.norm.weight"], cfg.rms_norm_eps)
         self._ready_after("model.norm.weight")
         for i in reversed(range(L)):

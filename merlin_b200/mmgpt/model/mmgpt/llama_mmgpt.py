@@ -382,13 +382,9 @@ class MMGPTLlamaForCausalLM(nn.Module, MMGPTMetaForCausalLM):
         if x.dtype != torch.bfloat16:
             x = x.to(torch.bfloat16)
         x = x.contiguous()
-        logits2d, hidden, all_hidden = self._decoder_core(x, B, S, seqlens, cache, bool(output_hidden_states))
+        lab = labels.to(device).contiguous() if labels is not None else None
+        logits2d, hidden, all_hidden, loss = self._decoder_core(x, B, S, seqlens, cache, bool(output_hidden_states), lab)
         logits = logits2d.view(B, S, -1) if logits2d.is_contiguous() else logits2d.unflatten(0, (B, S))
-
-        loss = None
-        if labels is not None:
-            lab = labels.to(device).contiguous()
-            loss, _ = ops.cross_entropy(logits2d, lab, B, S, IGNORE_INDEX)
         hs = None
         if output_hidden_states:
             hs = tuple(h.view(B, S, D) for h in all_hidden[:-1]) + (hidden.view(B, S, D),)
@@ -422,11 +418,12 @@ class MMGPTLlamaForCausalLM(nn.Module, MMGPTMetaForCausalLM):
             out = [(n, p) for n, p in out if p.requires_grad]
         return out
 
-    def _decoder_core(self, x, B, S, seqlens, cache, collect_hidden=False):
-        """Device-only tail of forward: decoder stack + lm_head (kernel launches only, graph-capturable)."""
+    def _decoder_core(self, x, B, S, seqlens, cache, collect_hidden=False, labels=None):
+        """Device-only tail of forward: decoder stack + lm_head (+ shifted CE when labels are given) — kernel
+        launches only, graph-capturable.  lm_head and the loss are ONE library call (merlin_lmhead_ce_forward)."""
         hidden, all_hidden = self.model.forward_layers(x, B, S, seqlens, cache, collect_hidden)
-        logits2d = ops.gemm(hidden, self.lm_head_w)          # [B*S, V] on a 16-byte aligned pitch
-        return logits2d, hidden, all_hidden
+        logits2d, loss, _ = ops.lmhead_ce_forward(hidden, self.lm_head_w, labels, B, S, IGNORE_INDEX)
+        return logits2d, hidden, all_hidden, loss          # logits [B*S, V] on a 16-byte aligned pitch
 
     def _prefill_core(self, ids_dev, images_bf16, feat_offset, feat_limit, cache):
         """Device-only multimodal prefill for one pre-validated batch: ViT -> projector -> splice ->
@@ -443,7 +440,7 @@ class MMGPTLlamaForCausalLM(nn.Module, MMGPTMetaForCausalLM):
             feats = proj([tower.feature_select(hidden, n)])[0]
         feats = feats.reshape(-1, feats.shape[-1])
         x, _ = ops.embed_splice(ids_dev, m.embed_tokens, feats, self.im_patch_token, feat_offset, feat_limit)
-        logits2d, _, _ = self._decoder_core(x, B, S, None, cache)
+        logits2d, _, _, _ = self._decoder_core(x, B, S, None, cache)
         return logits2d
 
     # ------------------------------------------------------------------ generation (llama_mmgpt.py:114-134)

@@ -351,6 +351,48 @@ def cross_entropy(logits: torch.Tensor, labels: torch.Tensor, batch: int, seq: i
     return acc[0] / acc[1], row
 
 
+def lmhead_ce_forward(hidden: torch.Tensor, lm_head_w: torch.Tensor, labels: Optional[torch.Tensor], batch: int,
+                      seq: int, ignore_index: int = -100, cta_group: Optional[int] = None):
+    """logits = hidden @ lm_head_w.T (+ shifted CE when labels are given) in one library call
+    (merlin_lmhead_ce_forward).  Returns (logits [M, V] view on a 16-byte pitch, loss or None, loss_sum_count)."""
+    M, D, ldh = _rows2d(hidden, "hidden")
+    V, Dw, ldw = _rows2d(lm_head_w, "lm_head_w")
+    if D != Dw or ldw != D or M != batch * seq:
+        raise ValueError("lmhead_ce_forward: bad shapes")
+    buf = torch.empty((M, (V + 7) // 8 * 8), dtype=_BF16, device=hidden.device)
+    logits = buf[:, :V]
+    acc = None
+    if labels is not None:
+        if labels.dtype != torch.int64 or not labels.is_contiguous() or labels.numel() != M:
+            raise ValueError("lmhead_ce_forward: labels must be contiguous int64 [batch, seq]")
+        acc = torch.empty((2,), dtype=torch.float32, device=hidden.device)
+    L = _lib.load()
+    check(_gemm_call(L.merlin_lmhead_ce_forward, 2 * M * V * D, _stream(), hidden.data_ptr(), ldh, lm_head_w.data_ptr(),
+                     logits.data_ptr(), buf.stride(0), _ptr(labels), batch, seq, D, V, ignore_index, None, _ptr(acc),
+                     cta_group or DEFAULT_CTA_GROUP), "merlin_lmhead_ce_forward")
+    if labels is not None:
+        PROFILE.launches += 1
+    return logits, (None if acc is None else acc[0] / acc[1]), acc
+
+
+def lmhead_ce_backward(logits: torch.Tensor, labels: torch.Tensor, acc: torch.Tensor, grad_scale: float,
+                       hidden: torch.Tensor, lm_head_w: torch.Tensor, d_lm_head_w: Optional[torch.Tensor],
+                       accumulate: bool, batch: int, seq: int, ignore_index: int = -100,
+                       cta_group: Optional[int] = None) -> torch.Tensor:
+    """Backward of lmhead_ce_forward (merlin_lmhead_ce_backward): logits become dlogits in place, d_lm_head_w gets
+    the weight gradient, returns dhidden [M, D]."""
+    M, V, ldl = _rows2d(logits, "logits")
+    _, D, ldh = _rows2d(hidden, "hidden")
+    dh = torch.empty((M, D), dtype=_BF16, device=hidden.device)
+    L = _lib.load()
+    check(L.merlin_lmhead_ce_backward(_stream(), logits.data_ptr(), ldl, labels.data_ptr(), batch, seq, D, V, ignore_index,
+                                      acc.data_ptr(), float(grad_scale), hidden.data_ptr(), ldh, lm_head_w.data_ptr(),
+                                      _ptr(d_lm_head_w), 1 if accumulate else 0, dh.data_ptr(), D,
+                                      cta_group or DEFAULT_CTA_GROUP), "merlin_lmhead_ce_backward")
+    PROFILE.launches += 3 if d_lm_head_w is not None else 2
+    return dh
+
+
 def argmax(logits: torch.Tensor) -> torch.Tensor:
     M, V, ld = _rows2d(logits, "logits")
     out = torch.empty((M,), dtype=torch.int64, device=logits.device)
