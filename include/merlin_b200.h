@@ -233,6 +233,16 @@ size_t merlin_vit_layer_workspace_bytes(int M, int d, int ff);
 int merlin_vit_layer_forward(void* stream, const merlin_vit_layer_weights* w, void* h, void* workspace, int n_img,
                              int tokens, int d, int heads, int ff, float eps, int cta_group);
 
+/* ConvProjector.forward (mmgpt/model/projector/conv_projector.py:23-39) in one call: the 3x3 / pad 1 / stride-s
+ * convolution of the channel-last patch features as merlin_conv3x3_im2col (into `workspace`,
+ * merlin_projector_workspace_bytes) + merlin_gemm_bf16 with the bias epilogue.  feat addressing as in
+ * merlin_conv3x3_im2col (tok_stride = 577, tok_off = 1 reads hidden_states[-2][:, 1:] in place); weight is
+ * [D_out, 3, 3, C] flattened to [D_out, 9C]; out[n_img * Go * Go, D_out] with row pitch ldo. */
+size_t merlin_projector_workspace_bytes(int n_img, int grid, int C, int stride);
+int merlin_projector_forward(void* stream, const void* feat, const void* weight, const void* bias, void* workspace,
+                             void* out, int64_t ldo, int n_img, int grid, int C, int D_out, int stride, int tok_stride,
+                             int tok_off, int cta_group);
+
 /* lm_head + shifted cross-entropy in one call (mmgpt/model/mmgpt/llama_mmgpt.py:86-100): logits[M, V] (row pitch
  * ldl elements, multiple of 8) = hidden[M, D] . lm_head[V, D]^T, and, when labels != NULL, the shifted fp32 CE of
  * merlin_cross_entropy_fwd (loss_sum_count[2], optional row_nll[M]).  M = B*S. */

@@ -239,4 +239,23 @@ int merlin_lmhead_ce_backward(void* stream, void* logits, int64_t ldl, const int
                              MERLIN_EPI_STORE, cta_group);
 }
 
+// ---- ConvProjector.forward (conv_projector.py:23-39) as one call: im2col of the CLS-dropping slice + GEMM + bias
+size_t merlin_projector_workspace_bytes(int n_img, int grid, int C, int stride) {
+  const int go = (grid + 2 - 3) / stride + 1;
+  return static_cast<size_t>(n_img) * go * go * 9 * C * 2 + 256;
+}
+
+int merlin_projector_forward(void* stream, const void* feat, const void* weight, const void* bias, void* workspace,
+                             void* out, int64_t ldo, int n_img, int grid, int C, int D_out, int stride, int tok_stride,
+                             int tok_off, int cta_group) {
+  MB_CHECK_ARG(feat && weight && workspace && out, "projector_forward: null argument");
+  MB_CHECK_ARG(stride >= 1 && grid >= 1 && C % 8 == 0, "projector_forward: bad geometry");
+  const int go = (grid + 2 - 3) / stride + 1;
+  int rc;
+  if ((rc = merlin_conv3x3_im2col(stream, feat, workspace, n_img, grid, C, stride, tok_stride, tok_off)) != MERLIN_OK)
+    return rc;
+  return merlin_gemm_bf16(stream, workspace, 9 * C, weight, 9 * C, out, ldo, nullptr, 0, bias, n_img * go * go, D_out,
+                          9 * C, MERLIN_EPI_STORE, cta_group);
+}
+
 }  // extern "C"

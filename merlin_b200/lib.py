@@ -95,6 +95,8 @@ class LayerGrads(ctypes.Structure):
     _fields_ = [(n, c_void_p) for n in ("qkv_w", "o_w", "gate_up_w", "down_w", "ln1_w_f32", "ln2_w_f32")]
 
 
+_PROTOTYPES["merlin_projector_forward"] = [_P, _P, _P, _P, _P, _P, c_int64, c_int, c_int, c_int, c_int, c_int, c_int, c_int,
+                                          c_int]
 _PROTOTYPES["merlin_lmhead_ce_forward"] = [_P, _P, c_int64, _P, _P, c_int64, _P, c_int, c_int, c_int, c_int, c_int64, _P, _P,
                                           c_int]
 _PROTOTYPES["merlin_lmhead_ce_backward"] = [_P, _P, c_int64, _P, c_int, c_int, c_int, c_int, c_int64, _P, c_float, _P,
@@ -107,6 +109,7 @@ _SIZE_FNS = {"merlin_decoder_layer_saved_bytes": [c_int, c_int, c_int, c_int, c_
              "merlin_decoder_layer_backward_workspace_bytes": [c_int, c_int, c_int, c_int, c_int, c_int],"merlin_decode_workspace_bytes": [c_int, c_int, c_int, c_int],
              "merlin_decode_stream_workspace_bytes": [c_int, c_int, c_int, c_int],
              "merlin_image_preprocess_workspace_bytes": [c_int, c_int, c_int],
+             "merlin_projector_workspace_bytes": [c_int, c_int, c_int, c_int],
              "merlin_flash_attn_bwd_workspace_bytes": [c_int, c_int, c_int, c_int],
              "merlin_decoder_layer_workspace_bytes": [c_int, c_int, c_int],
              "merlin_vit_layer_workspace_bytes": [c_int, c_int, c_int]}

@@ -52,8 +52,8 @@ class ConvProjector(BaseProjector):
 
     def project(self, feat: torch.Tensor, n_img: int, grid: int, tok_stride: int, tok_off: int) -> torch.Tensor:
         """feat: bf16 buffer whose image i / patch (y,x) row sits at (i*tok_stride + tok_off + y*grid + x)."""
-        col = ops.conv3x3_im2col(feat, n_img, grid, self.in_channels, self.conv_stride, tok_stride, tok_off)
-        return ops.gemm(col, self.weight, bias=self.bias)
+        return ops.projector_forward(feat, self.weight, self.bias, n_img, grid, self.in_channels, self.conv_stride,
+                                     tok_stride, tok_off)
 
     def forward(self, features):
         with torch.set_grad_enabled(False):

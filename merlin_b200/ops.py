@@ -300,6 +300,23 @@ def conv3x3_im2col(feat: torch.Tensor, n_img: int, grid: int, C: int, stride: in
     return col
 
 
+def projector_forward(feat: torch.Tensor, weight: torch.Tensor, bias: Optional[torch.Tensor], n_img: int, grid: int,
+                      C: int, stride: int, tok_stride: int, tok_off: int, cta_group: Optional[int] = None) -> torch.Tensor:
+    """ConvProjector forward in one library call (merlin_projector_forward): [n_img * Go * Go, D_out]."""
+    D_out, K9, ldw = _rows2d(weight, "weight")
+    if K9 != 9 * C or ldw != K9:
+        raise ValueError("projector_forward: weight must be a contiguous [D_out, 9*C] tensor")
+    go = (grid + 2 - 3) // stride + 1
+    L = _lib.load()
+    ws = torch.empty(L.merlin_projector_workspace_bytes(n_img, grid, C, stride), dtype=torch.uint8, device=feat.device)
+    out = torch.empty((n_img * go * go, D_out), dtype=_BF16, device=feat.device)
+    check(_gemm_call(L.merlin_projector_forward, 2 * n_img * go * go * D_out * 9 * C, _stream(), feat.data_ptr(),
+                     weight.data_ptr(), _ptr(bias), ws.data_ptr(), out.data_ptr(), D_out, n_img, grid, C, D_out, stride,
+                     tok_stride, tok_off, cta_group or DEFAULT_CTA_GROUP), "merlin_projector_forward")
+    PROFILE.launches += 1
+    return out
+
+
 def embed_splice(input_ids: torch.Tensor, embed_table: torch.Tensor, image_features: Optional[torch.Tensor],
                  im_patch_token: int, feat_offset: Optional[torch.Tensor] = None,
                  feat_limit: Optional[torch.Tensor] = None, return_rank: bool = False):
