@@ -233,3 +233,34 @@ def test_local_tar_shards_feed_the_dataset_and_the_collator(tmp_path):
     assert int((sample["input_ids"] == 32000).sum()) == 4 * 4                         # 4 images x image_token_len
     batch = DataCollatorForSupervisedDataset(tokenizer=tok)([sample, ds[1]])
     assert batch["input_ids"].shape[0] == 2 and batch["images"][0].shape == (4, 3, 8, 8)
+
+
+def test_build_dataloader_contract(tmp_path):
+    """mmgpt/data/builder.py:12-81 mirror: same return keys; local shard globs with an optional @merge_round;
+    dataset kinds / image modes outside the mirrored slice fail loudly."""
+    from merlin_b200.mmgpt.data.builder import build_dataloader
+    from merlin_b200.mmgpt.data.collator import DataCollatorForSupervisedDataset
+    shard = tmp_path / "a-000.tar"
+    with tarfile.open(shard, "w") as tf:
+        for r in range(5):
+            data = json.dumps(dict(prompt="p <image>", txt="t", image_name_list=[f"x-f{r}"])).encode()
+            ti = tarfile.TarInfo(f"r{r}.json")
+            ti.size = len(data)
+            tf.addfile(ti, io.BytesIO(data))
+    tok = _Tok()
+    base = dict(image_token_len=4, use_im_start_end=True, image_size=8, image_processor=None, image_aspect_ratio="resize")
+    out = build_dataloader(tok, types.SimpleNamespace(interpair_webdatasets=str(tmp_path / "a-*.tar") + "@2", **base))
+    assert set(out) == {"train_dataset", "eval_dataset", "data_collator"} and out["eval_dataset"] is None
+    assert isinstance(out["data_collator"], DataCollatorForSupervisedDataset)
+    assert len(out["train_dataset"]) == 5 // 2 and out["train_dataset"].merge_round == 2
+    two = build_dataloader(tok, types.SimpleNamespace(
+        interpair_webdatasets=str(tmp_path / "a-*.tar") + "+" + str(tmp_path / "a-*.tar") + "@5", **base))
+    assert len(two["train_dataset"]) == 5 + 1
+    with pytest.raises(FileNotFoundError):
+        build_dataloader(tok, types.SimpleNamespace(interpair_webdatasets=str(tmp_path / "none-*.tar"), **base))
+    with pytest.raises(NotImplementedError):
+        build_dataloader(tok, types.SimpleNamespace(interpair_webdatasets=str(shard), conversation_datasets="llava665k", **base))
+    with pytest.raises(NotImplementedError):
+        build_dataloader(tok, types.SimpleNamespace(interpair_webdatasets=str(shard), **dict(base, image_aspect_ratio="keep")))
+    with pytest.raises(ValueError):
+        build_dataloader(tok, types.SimpleNamespace(interpair_webdatasets="", **base))
