@@ -2,16 +2,22 @@
 //
 // The per-kernel decode path (decode.cu) streams every weight once but pays a ramp-up and a tail per
 // kernel: 5 kernels x 32 layers per token leave the HBM pipe idle ~25 % of the time.  Here ONE persistent
-// kernel (one CTA per SM) executes the whole token.  In every CTA a producer warp walks the CTA's share of
-// the weight rows and of the KV-cache tiles of ALL layers in execution order and feeds them through a
-// shared-memory ring with TMA (cp.async.bulk for weight rows, a 3-D tensor map per layer for [32 keys x
-// (k|v) x 128 dims] cache boxes).  Weights and old cache rows do not depend on the activations, so the
-// producer runs ahead across phase and layer boundaries, bounded only by the ring (~200 KB per SM, ~29 MB
-// in flight on the chip): HBM never drains while the 8 consumer warps wait at a grid-wide barrier for the
-// activation they need.  Consumers take one ring stage per warp (no intra-CTA reductions), keep the
-// (RMS-normalised) activation vector in shared memory and apply the same fused epilogues as decode.cu:
-// RoPE + KV-cache append, SwiGLU, residual add.  Attention is split over (head, key-tile range) per warp
-// with an online softmax; the last contributor of a head (ticket counter) merges the partials in a fixed order.
+// kernel (one CTA per SM, cooperative launch) executes the whole token.
+//  * Streaming.  In every CTA a producer thread walks the CTA's share of the weight rows and of the KV-cache
+//    tiles of ALL layers in execution order and feeds them through a shared-memory ring with TMA bulk copies
+//    (cp.async.bulk + mbarrier complete_tx): a weight-row pair, a K-chunk of a down_proj row, or 32 keys of one
+//    head (16 KB contiguous in the tile-major cache).  Units go round-robin over the CTAs, so at any time the
+//    chip reads one dense window of memory.  Weights and old cache rows do not depend on the activations, so the
+//    producer runs ahead across phase and layer boundaries, bounded only by the ring (12 x 16 KB per SM, ~29 MB
+//    in flight on the chip): HBM keeps streaming while the consumers wait at a grid-wide barrier.
+//  * Consuming.  8 consumer warps take one ring stage each (no intra-CTA reductions), keep the (RMS-normalised)
+//    activation vector in shared memory and apply the same fused epilogues as decode.cu: RoPE + KV-cache append,
+//    SwiGLU, residual add.  Five grid barriers per layer (release arrival + polled counter).
+//  * Attention.  Head h owns a group of consecutive ring warps, warp s of the group takes key tiles s, s + WPH,
+//    ...; online softmax per warp, the last contributor of a head (ticket counter) merges the partials in slot
+//    order — deterministic.  The unaligned tail keys and the new token are handled by one warp per head that
+//    reads them straight from global memory.
+// DESIGN.md §7 lists the measured variants (fence-free protocols, other cache layouts, L2 prefetch) that lost.
 #include "host.cuh"
 #include "ptx.cuh"
 
