@@ -1,8 +1,8 @@
 """Pins oracle/merlin_oracle.py against the REAL reference and writes tests/golden/*.pt.
 
 Runs only in the build container (needs /root/reference).  What it does:
-  1. copies /root/reference/mmgpt to a temp dir and restores the one missing ')' at
-     mmgpt/utils/constants.py:72 (the tree as scraped has a SyntaxError at :25);
+  1. builds oracle/_ref (oracle/build_ref.py: a copy of /root/reference/mmgpt with the one missing ')' of
+     mmgpt/utils/constants.py:72 restored — the tree as scraped has a SyntaxError at :25);
   2. imports the reference's own MMGPTLlamaForCausalLM / CLIPVisionTower / ConvProjector /
      MLPProjector (HF transformers 5.5.0 modules underneath, eager attention, fp32 RoPE),
      assembles them exactly like build_vision_tokenizer does (base_mmgpt.py:23-79) and loads the
@@ -18,10 +18,7 @@ from __future__ import annotations
 
 import hashlib
 import os
-import shutil
 import sys
-import tempfile
-import types
 
 import torch
 
@@ -33,56 +30,14 @@ REFERENCE = "/root/reference"
 
 
 def import_reference():
-    tmp = tempfile.mkdtemp(prefix="merlin_ref_")
-    shutil.copytree(os.path.join(REFERENCE, "mmgpt"), os.path.join(tmp, "mmgpt"))
-    os.system(f"chmod -R u+w {tmp}")
-    p = os.path.join(tmp, "mmgpt/utils/constants.py")
-    lines = open(p).read().split("\n")
-    lines.insert(71, ")")
-    open(p, "w").write("\n".join(lines))
-    sys.path.insert(0, tmp)
-    from mmgpt.model.mmgpt.llama_mmgpt import MMGPTConfig, MMGPTLlamaForCausalLM
-    from mmgpt.model.projector.conv_projector import ConvProjector
-    from mmgpt.model.projector.mlp_projector import MLPProjector
-    from mmgpt.model.vision_encoder.clip_encoder import CLIPVisionTower
-    return types.SimpleNamespace(MMGPTConfig=MMGPTConfig, MMGPTLlamaForCausalLM=MMGPTLlamaForCausalLM,
-                                 ConvProjector=ConvProjector, MLPProjector=MLPProjector,
-                                 CLIPVisionTower=CLIPVisionTower)
+    """The real reference classes, from the oracle/_ref copy oracle/build_ref.py makes (one missing ')' restored)."""
+    from oracle import refmodel
+    return refmodel.import_reference()
 
 
 def build_reference_model(ref, cfg: O.OracleConfig, sd):
-    from transformers import CLIPVisionConfig, CLIPVisionModel
-    lcfg = ref.MMGPTConfig(vocab_size=cfg.vocab_size, hidden_size=cfg.hidden_size,
-                           intermediate_size=cfg.intermediate_size, num_hidden_layers=cfg.num_layers,
-                           num_attention_heads=cfg.num_heads, num_key_value_heads=cfg.num_heads,
-                           rms_norm_eps=cfg.rms_norm_eps, rope_theta=cfg.rope_theta,
-                           max_position_embeddings=4096, tie_word_embeddings=False, hidden_act="silu",
-                           attention_bias=False, mlp_bias=False, attn_implementation="eager")
-    model = ref.MMGPTLlamaForCausalLM(lcfg)
-    vt = ref.CLIPVisionTower.__new__(ref.CLIPVisionTower)  # __init__ calls from_pretrained (no weights offline)
-    torch.nn.Module.__init__(vt)
-    vt.select_layer, vt.select_feature = cfg.select_layer, cfg.select_feature
-    vt.freeze_vision_tower, vt.conv_stride = False, (cfg.conv_stride if cfg.projector == "conv" else 1)
-    vt.vision_tower = CLIPVisionModel(CLIPVisionConfig(
-        hidden_size=cfg.vit_hidden, intermediate_size=cfg.vit_intermediate, num_hidden_layers=cfg.vit_layers,
-        num_attention_heads=cfg.vit_heads, image_size=cfg.image_size, patch_size=cfg.patch_size,
-        hidden_act="quick_gelu", layer_norm_eps=cfg.vit_ln_eps, attn_implementation="eager"))
-    args = types.SimpleNamespace(freeze_projector=False, model_name_or_path="/nonexistent")
-    if cfg.projector == "conv":
-        proj = ref.ConvProjector(args, cfg.vit_hidden, cfg.hidden_size, conv_stride=cfg.conv_stride)
-    else:
-        proj = ref.MLPProjector(args, cfg.vit_hidden, cfg.hidden_size)
-    model.get_model().vision_tower = vt
-    model.get_model().projector = proj
-    model.use_im_start_end, model.use_beam_search = True, False
-    model.im_patch_token, model.im_start_token, model.im_end_token = \
-        cfg.im_patch_token, cfg.im_start_token, cfg.im_end_token
-    missing, unexpected = model.load_state_dict(sd, strict=False)
-    # the only keys we do not provide are non-persistent / derived buffers
-    assert not unexpected, unexpected
-    assert all("position_ids" in k or "inv_freq" in k for k in missing), missing
-    model.eval()
-    return model
+    from oracle import refmodel
+    return refmodel.build_reference_model(cfg, sd, device="cpu", dtype=torch.float32, attn="eager", ref=ref)
 
 
 def sha(sd) -> str:

@@ -98,23 +98,31 @@ class OracleConfig:
 
 
 # --------------------------------------------------------------------------- weights
-def init_state_dict(cfg: OracleConfig, seed: int = 0, dtype=torch.float32, round_bf16: bool = True) -> StateDict:
+def init_state_dict(cfg: OracleConfig, seed: int = 0, dtype=torch.float32, round_bf16: bool = True,
+                    device="cpu") -> StateDict:
     """Seeded random-init weights under the reference's state-dict key names.  Draw order is fixed, so
-    the same (cfg, seed) gives identical tensors on every machine with the same torch build.
+    the same (cfg, seed, device type) gives identical tensors on every machine with the same torch build.
     Linear / embedding weights N(0, 0.02) as HF Llama `_init_weights`; CLIP-like scales for the tower.
-    With round_bf16 the values are exactly representable in bf16 (the GPU path stores bf16)."""
-    g = torch.Generator().manual_seed(seed)
+    With round_bf16 the values are exactly representable in bf16 (the GPU path stores bf16).
+    device="cuda" draws on the GPU (a 7B / 13B model in seconds; a different stream than the CPU generator,
+    so the committed CPU goldens are unaffected); each tensor is converted to `dtype` as it is drawn."""
+    g = torch.Generator(device=device).manual_seed(seed)
     sd: StateDict = {}
 
+    def fin(t):
+        if round_bf16:
+            t = t.to(torch.bfloat16)
+        return t.to(dtype)
+
     def normal(name, shape, std):
-        t = torch.empty(shape, dtype=torch.float32).normal_(0.0, std, generator=g)
-        sd[name] = t
+        t = torch.empty(shape, dtype=torch.float32, device=device).normal_(0.0, std, generator=g)
+        sd[name] = fin(t)
 
     def const(name, shape, value, jitter=0.0):
-        t = torch.full(shape, float(value), dtype=torch.float32)
+        t = torch.full(shape, float(value), dtype=torch.float32, device=device)
         if jitter:
-            t += torch.empty(shape, dtype=torch.float32).normal_(0.0, jitter, generator=g)
-        sd[name] = t
+            t += torch.empty(shape, dtype=torch.float32, device=device).normal_(0.0, jitter, generator=g)
+        sd[name] = fin(t)
 
     D, FF, V = cfg.hidden_size, cfg.intermediate_size, cfg.vocab_size
     normal("model.embed_tokens.weight", (V, D), 0.02)
@@ -155,9 +163,7 @@ def init_state_dict(cfg: OracleConfig, seed: int = 0, dtype=torch.float32, round
     else:
         normal(PROJ + "weight", (D, d), d ** -0.5)
     const(PROJ + "bias", (D,), 0.0, 0.02)
-    if round_bf16:
-        sd = {k: v.to(torch.bfloat16).to(torch.float32) for k, v in sd.items()}
-    return {k: v.to(dtype) for k, v in sd.items()}
+    return sd
 
 
 def synthetic_batch(cfg: OracleConfig, batch: int, seq_len: int, images_per_sample: Sequence[int], seed: int = 1234,
@@ -449,14 +455,14 @@ def greedy_generate(sd: StateDict, cfg: OracleConfig, input_ids: torch.Tensor, i
     cache: list = [None] * cfg.num_layers
     feats = encode_images(sd, cfg, images)
     embeds = prepare_inputs_embeds(sd, cfg, ids, feats)
-    h = decoder_forward(sd, cfg, embeds, None, torch.arange(ids.shape[1]), cache)
+    h = decoder_forward(sd, cfg, embeds, None, torch.arange(ids.shape[1], device=ids.device), cache)
     for _ in range(max_new_tokens):
         nxt = F.linear(h[:, -1], sd["lm_head.weight"]).argmax(-1, keepdim=True)
         ids = torch.cat([ids, nxt], dim=1)
         if eos_token_id is not None and int(nxt) == eos_token_id:
             break
         e = F.embedding(nxt, sd["model.embed_tokens.weight"])
-        h = decoder_forward(sd, cfg, e, None, torch.tensor([ids.shape[1] - 1]), cache)
+        h = decoder_forward(sd, cfg, e, None, torch.tensor([ids.shape[1] - 1], device=ids.device), cache)
     return ids
 
 

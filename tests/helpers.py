@@ -24,9 +24,11 @@ def weights_sha(sd):
     return h.hexdigest()
 
 
-def build_product_model(cfg: O.OracleConfig, sd, device="cuda"):
+def build_product_model(cfg: O.OracleConfig, sd, device="cuda", max_position_embeddings=4096):
     """Assemble merlin_b200's MMGPTLlamaForCausalLM for an oracle config and load the oracle's
-    reference-format state dict through the public load_state_dict (strict)."""
+    reference-format state dict through the public load_state_dict (strict).  When the state dict already
+    lives on a GPU (7B / 13B config cases) the model is constructed there directly in bf16."""
+    import contextlib
     from merlin_b200.mmgpt.model.mmgpt.llama_mmgpt import MMGPTConfig, MMGPTLlamaForCausalLM
     from merlin_b200.mmgpt.model.projector.builder import build_projector
     from merlin_b200.mmgpt.model.vision_encoder.builder import build_vision_tower
@@ -34,8 +36,25 @@ def build_product_model(cfg: O.OracleConfig, sd, device="cuda"):
     lcfg = MMGPTConfig(vocab_size=cfg.vocab_size, hidden_size=cfg.hidden_size,
                        intermediate_size=cfg.intermediate_size, num_hidden_layers=cfg.num_layers,
                        num_attention_heads=cfg.num_heads, num_key_value_heads=cfg.num_heads,
-                       rms_norm_eps=cfg.rms_norm_eps, rope_theta=cfg.rope_theta, max_position_embeddings=4096,
-                       tie_word_embeddings=False)
+                       rms_norm_eps=cfg.rms_norm_eps, rope_theta=cfg.rope_theta,
+                       max_position_embeddings=max_position_embeddings, tie_word_embeddings=False)
+    on_gpu = next(iter(sd.values())).is_cuda
+    prev = torch.get_default_dtype()
+    if on_gpu:
+        torch.set_default_dtype(torch.bfloat16)
+    try:
+        with (torch.device(next(iter(sd.values())).device) if on_gpu else contextlib.nullcontext()):
+            model = _assemble(cfg, lcfg, MMGPTLlamaForCausalLM, build_vision_tower, build_projector)
+    finally:
+        torch.set_default_dtype(prev)
+    model.load_state_dict(sd, strict=True)
+    if device is not None:
+        model.to(device=device, dtype=torch.bfloat16)
+    model.eval()
+    return model
+
+
+def _assemble(cfg, lcfg, MMGPTLlamaForCausalLM, build_vision_tower, build_projector):
     model = MMGPTLlamaForCausalLM(lcfg)
     args = SimpleNamespace(vision_tower="clip-synthetic", vision_select_layer=cfg.select_layer,
                            vision_select_feature=cfg.select_feature, freeze_vision_tower=True,
@@ -50,10 +69,6 @@ def build_product_model(cfg: O.OracleConfig, sd, device="cuda"):
     model.im_patch_token, model.im_start_token, model.im_end_token = \
         cfg.im_patch_token, cfg.im_start_token, cfg.im_end_token
     model.use_im_start_end, model.use_beam_search = cfg.use_im_start_end, cfg.use_beam_search
-    model.load_state_dict(sd, strict=True)
-    if device is not None:
-        model.to(device=device, dtype=torch.bfloat16)
-    model.eval()
     return model
 
 
