@@ -306,7 +306,11 @@ def main():
     # recorded between graph nodes), so the same prefill is run eagerly right here, still inside bench.py,
     # with a CUDA event pair around every GEMM launch on the launching stream.
     n_pre = max(2, args.steps // 2)
-    eager_ms, _ = timed(lambda: model(input_ids=ids_d, images=[img_d]), n_pre, profile=True)
+    def eager_prefill():
+        with torch.no_grad():
+            return model(input_ids=ids_d, images=[img_d])
+
+    eager_ms, _ = timed(eager_prefill, n_pre, profile=True)
     gemm_flops, gemm_ms, gemm_n = ops.PROFILE.gemm_summary()
     # prefill alone = one replay of the captured prefill graph (what the timed steps run)
     gen = next(iter(model._graphed.values()))

@@ -361,6 +361,71 @@ int merlin_vit_embed_bwd(void* stream, const void* dhidden, void* dpatch_out, fl
 /* y[n] (bf16) = x[n] (fp32): folds fp32 accumulators (norm-weight / bias gradients) into the arena. */
 int merlin_f32_to_bf16(void* stream, const float* x, void* y, int64_t n);
 
+
+/* ---- whole CLIP tower in one call each way (SURVEY.md §8b minimum set: merlin_vit_forward / merlin_vit_backward).
+ * Replaces CLIPVisionTower.forward (mmgpt/model/vision_encoder/clip_encoder.py:74-82) over HF CLIPVisionModel
+ * (HF:clip/modeling_clip.py:202-218 embeddings, :676-677 pre_layrnorm, :363-384 encoder layers) and its autograd.
+ * `num_layers` is the number of encoder layers to RUN (select_layer already applied: 23 of 24 for -2);
+ * hidden_states[select_layer] comes back as hidden[n_img*tokens, hidden] (CLS row first).  pixels: bf16
+ * [n_img, 3, image_size, image_size].  Biases / norm weights / class + position embeddings accumulate their
+ * gradients in fp32 side buffers (`*_f32`), weight matrices in bf16 (accumulate != 0: added to what is there). */
+typedef struct merlin_vit_weights {
+  int num_layers, hidden, heads, intermediate, image_size, patch_size, k_patch_padded;
+  float ln_eps;
+  const void *class_embedding, *patch_weight, *position_embedding, *pre_ln_w, *pre_ln_b;
+  const merlin_vit_layer_weights* layers; /* [num_layers] */
+} merlin_vit_weights;
+typedef struct merlin_vit_layer_grads {
+  void *qkv_w, *out_w, *fc1_w, *fc2_w;
+  float *qkv_b_f32, *out_b_f32, *ln1_w_f32, *ln1_b_f32, *ln2_w_f32, *ln2_b_f32, *fc1_b_f32, *fc2_b_f32;
+} merlin_vit_layer_grads;
+typedef struct merlin_vit_grads {
+  void* patch_weight;
+  float *position_f32, *class_f32, *pre_ln_w_f32, *pre_ln_b_f32;
+  const merlin_vit_layer_grads* layers; /* [num_layers] */
+} merlin_vit_grads;
+size_t merlin_vit_workspace_bytes(const merlin_vit_weights* w, int n_img);
+int merlin_vit_forward(void* stream, const merlin_vit_weights* w, const void* pixels, int n_img, void* workspace,
+                       void* hidden, int cta_group);
+size_t merlin_vit_saved_bytes(const merlin_vit_weights* w, int n_img);
+int merlin_vit_forward_train(void* stream, const merlin_vit_weights* w, const void* pixels, int n_img, void* saved,
+                             void* hidden, int cta_group);
+size_t merlin_vit_backward_workspace_bytes(const merlin_vit_weights* w, int n_img);
+/* dh [n_img*tokens, hidden]: gradient w.r.t. merlin_vit_forward_train's `hidden`; overwritten. */
+int merlin_vit_backward(void* stream, const merlin_vit_weights* w, const merlin_vit_grads* g, void* saved, void* dh,
+                        void* workspace, int n_img, int accumulate, int cta_group);
+
+/* ---- data-parallel gradient exchange (SURVEY.md §8b minimum set: merlin_dp_init / allreduce_bucket / finalize).
+ * Replaces the FSDP `shard_grad_op auto_wrap` reduce-scatter / all-gather the reference trains with
+ * (playground/merlin/clip-large+conv+vicuna-v15-7b/pretrain.sh:32-33 inside HF Trainer) by plain
+ * data parallelism: one NCCL communicator per rank over NVLink 5 / NVSwitch and an in-place bf16 SUM
+ * all-reduce per contiguous bucket of the flat gradient arena, enqueued on the caller's (side) stream.
+ * The host exchanges the 128-byte unique id (rank 0 creates it) over whatever channel it has
+ * (torch.distributed's store in the Python shim).  max_ctas > 0 bounds the CTAs NCCL may use per collective so
+ * that the exchange co-resides with backward's persistent GEMMs (see merlin_set_sm_budget). */
+#define MERLIN_DP_UNIQUE_ID_BYTES 128
+/* Optional, before any other merlin_dp_* call: resolve NCCL from this shared object (the Python shim passes
+ * the torch-bundled libnccl.so.2 so both use ONE library); default = the libnccl.so.2 already in the process. */
+int merlin_dp_load_nccl(const char* path);
+int merlin_dp_unique_id(void* id_out);
+int merlin_dp_init(const void* unique_id, int rank, int world, int max_ctas, void** comm_out);
+int merlin_dp_allreduce_bucket(void* comm, void* stream, void* grads_bf16, int64_t count);
+/* fp32 SUM (op_max == 0) or MAX all-reduce of a small buffer: loss / timing reductions of the step loop. */
+int merlin_dp_allreduce_f32(void* comm, void* stream, void* buf, int64_t count, int op_max);
+/* Optional: NCCL-owned allocation (ncclMemAlloc) + user-buffer registration of the gradient arena, which lets
+ * NVLS reduce in the switch straight out of the arena (no staging copies, fewer CTAs). */
+int merlin_dp_mem_alloc(void** ptr_out, int64_t bytes);
+int merlin_dp_mem_free(void* ptr);
+int merlin_dp_register(void* comm, void* buf, int64_t bytes, void** handle_out);
+int merlin_dp_deregister(void* comm, void* handle);
+int merlin_dp_finalize(void* comm);
+int merlin_dp_nccl_version(void); /* NCCL_VERSION_CODE of the resolved libnccl, 0 if none */
+
+/* SM budget of the persistent kernels (the tcgen05 GEMM runs one CTA / CTA pair per SM): `sms` > 0 makes their
+ * grids cover at most that many SMs, 0 restores the whole chip; returns the previous value.  Process-wide. */
+int merlin_set_sm_budget(int sms);
+int merlin_sm_count(void);
+
 #ifdef __cplusplus
 }
 #endif

@@ -4,6 +4,8 @@
 #include "attn_bwd.cuh"
 #include "host.cuh"
 
+#include <mutex>
+
 #include <algorithm>
 #include <cmath>
 #include <cstdlib>
@@ -14,12 +16,11 @@ template <int HD, bool kCausal>
 static int launch_attn(cudaStream_t stream, const CUtensorMap& tq, const CUtensorMap& to,
                        const AttnParams& p) {
   using Cfg = AttnCfg<HD>;
-  static bool configured = false;
-  if (!configured) {
-    MB_CHECK_CUDA(cudaFuncSetAttribute(attn_fwd_kernel<HD, kCausal>,
-                                       cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::kSmemBytes));
-    configured = true;
-  }
+  static std::once_flag once;
+  static cudaError_t attr_rc = cudaSuccess;
+  std::call_once(once, [] { attr_rc = cudaFuncSetAttribute(attn_fwd_kernel<HD, kCausal>,
+                                       cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::kSmemBytes); });
+  MB_CHECK_CUDA(attr_rc);
   const int nq = (p.S + kAttnBlock - 1) / kAttnBlock;
   dim3 grid(static_cast<unsigned>(nq), static_cast<unsigned>(p.H), static_cast<unsigned>(p.B));
   attn_fwd_kernel<HD, kCausal><<<grid, kAttnThreads, Cfg::kSmemBytes, stream>>>(tq, to, p);
@@ -31,12 +32,11 @@ template <int HD, bool kCausal>
 static int launch_attn2(cudaStream_t stream, const CUtensorMap& tq, const CUtensorMap& to,
                         const AttnParams& p) {
   using Cfg = Attn2Cfg<HD>;
-  static bool configured = false;
-  if (!configured) {
-    MB_CHECK_CUDA(cudaFuncSetAttribute(attn_fwd2_kernel<HD, kCausal>,
-                                       cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::kSmemBytes));
-    configured = true;
-  }
+  static std::once_flag once;
+  static cudaError_t attr_rc = cudaSuccess;
+  std::call_once(once, [] { attr_rc = cudaFuncSetAttribute(attn_fwd2_kernel<HD, kCausal>,
+                                       cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::kSmemBytes); });
+  MB_CHECK_CUDA(attr_rc);
   const int nq = (p.S + kAttnBlock - 1) / kAttnBlock;
   dim3 grid(static_cast<unsigned>((nq + 1) / 2), static_cast<unsigned>(p.H), static_cast<unsigned>(p.B));
   attn_fwd2_kernel<HD, kCausal><<<grid, kAttn2Threads, Cfg::kSmemBytes, stream>>>(tq, to, p);

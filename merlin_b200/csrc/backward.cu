@@ -306,8 +306,9 @@ __global__ void adamw_kernel(__nv_bfloat16* __restrict__ p, const __nv_bfloat16*
   for (int64_t i = blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x; i < n_vec;
        i += static_cast<int64_t>(gridDim.x) * blockDim.x) {
     const int64_t c = i / chunk_vec;
-    const float lr_c = lr * lr_mult[c];
-    if (lr_c == 0.f) continue;  // frozen segment
+    const float mult = lr_mult[c];
+    if (mult == 0.f) continue;  // frozen segment (lr multiplier 0); lr == 0 alone (warm-up step 0) still updates m, v
+    const float lr_c = lr * mult;
     const float wd_c = wd[c];
     float pf[8], gf[8], mf[8], vf[8];
     unpack8b(reinterpret_cast<const uint4*>(p)[i], pf);

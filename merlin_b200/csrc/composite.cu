@@ -259,3 +259,243 @@ int merlin_projector_forward(void* stream, const void* feat, const void* weight,
 }
 
 }  // extern "C"
+
+// =====================================================================================================
+// Whole CLIP tower as composite entry points (SURVEY.md §8b minimum set: merlin_vit_forward / backward):
+// patch embedding -> CLS / position / pre_layrnorm -> the encoder layers `select_layer` needs, and the
+// explicit backward of the same schedule.  Reference: mmgpt/model/vision_encoder/clip_encoder.py:74-82 over
+// HF CLIPVisionModel (HF:clip/modeling_clip.py:202-218, 363-384, 676-677) and its autograd.
+// =====================================================================================================
+namespace {
+
+struct VitDims {
+  int M, G, d, ff, T, kpp;
+};
+
+VitDims vit_dims(const merlin_vit_weights* w, int n_img) {
+  VitDims v;
+  v.G = w->image_size / w->patch_size;
+  v.T = v.G * v.G + 1;
+  v.M = n_img * v.T;
+  v.d = w->hidden;
+  v.ff = w->intermediate;
+  v.kpp = w->k_patch_padded;
+  return v;
+}
+
+size_t align256(size_t x) { return (x + 255) & ~static_cast<size_t>(255); }
+
+// saved-activation layout of merlin_vit_forward_train
+struct VitSaved {
+  __nv_bfloat16 *col, *emb;
+  struct Layer {
+    __nv_bfloat16 *h, *xn1, *qkv, *att, *h_mid, *xn2, *pre, *mid;
+    float* lse;
+  };
+};
+
+size_t vit_layer_saved_bytes(const VitDims& v, int n_img, int heads) {
+  // h, xn1, att, h_mid, xn2 [M,d]; qkv [M,3d]; pre, mid [M,ff] (bf16); lse [n,heads,T] fp32
+  return align256(static_cast<size_t>(v.M) * (8 * static_cast<size_t>(v.d) + 2 * v.ff) * 2) +
+         align256(static_cast<size_t>(n_img) * heads * v.T * 4);
+}
+
+void vit_layer_layout(uint8_t* base, const VitDims& v, VitSaved::Layer* L) {
+  __nv_bfloat16* p = reinterpret_cast<__nv_bfloat16*>(base);
+  const size_t md = static_cast<size_t>(v.M) * v.d, mf = static_cast<size_t>(v.M) * v.ff;
+  L->h = p;      p += md;
+  L->xn1 = p;    p += md;
+  L->qkv = p;    p += 3 * md;
+  L->att = p;    p += md;
+  L->h_mid = p;  p += md;
+  L->xn2 = p;    p += md;
+  L->pre = p;    p += mf;
+  L->mid = p;    p += mf;
+  L->lse = reinterpret_cast<float*>(base + align256(static_cast<size_t>(v.M) * (8 * static_cast<size_t>(v.d) + 2 * v.ff) * 2));
+}
+
+size_t vit_head_saved_bytes(const VitDims& v, int n_img) {
+  // col [n*G*G, kpp] + emb [M, d]
+  return align256(static_cast<size_t>(n_img) * v.G * v.G * v.kpp * 2) + align256(static_cast<size_t>(v.M) * v.d * 2);
+}
+
+}  // namespace
+
+extern "C" {
+
+size_t merlin_vit_workspace_bytes(const merlin_vit_weights* w, int n_img) {
+  const VitDims v = vit_dims(w, n_img);
+  // col + patch_out + one layer's workspace
+  return align256(static_cast<size_t>(n_img) * v.G * v.G * v.kpp * 2) +
+         align256(static_cast<size_t>(n_img) * v.G * v.G * v.d * 2) + merlin_vit_layer_workspace_bytes(v.M, v.d, v.ff);
+}
+
+int merlin_vit_forward(void* stream, const merlin_vit_weights* w, const void* pixels, int n_img, void* workspace,
+                       void* hidden, int cta_group) {
+  MB_CHECK_ARG(w && pixels && workspace && hidden && n_img > 0, "vit_forward: null argument");
+  MB_CHECK_ARG(w->layers && w->num_layers >= 0 && w->hidden == w->heads * 64, "vit_forward: bad weights (head_dim 64)");
+  const VitDims v = vit_dims(w, n_img);
+  uint8_t* ws = static_cast<uint8_t*>(workspace);
+  void* col = ws;
+  void* patch_out = ws + align256(static_cast<size_t>(n_img) * v.G * v.G * v.kpp * 2);
+  void* layer_ws = static_cast<uint8_t*>(patch_out) + align256(static_cast<size_t>(n_img) * v.G * v.G * v.d * 2);
+  int rc;
+  // HF:clip/modeling_clip.py:202-218 (conv k=P, s=P, no bias as im2col + GEMM), :676-677 (pre_layrnorm)
+  if ((rc = merlin_patch_im2col(stream, pixels, col, n_img, w->image_size, w->patch_size, v.kpp)) != MERLIN_OK) return rc;
+  if ((rc = merlin_gemm_bf16(stream, col, v.kpp, w->patch_weight, v.kpp, patch_out, v.d, nullptr, 0, nullptr,
+                             n_img * v.G * v.G, v.d, v.kpp, MERLIN_EPI_STORE, cta_group)) != MERLIN_OK)
+    return rc;
+  if ((rc = merlin_vit_embed_ln(stream, patch_out, w->class_embedding, w->position_embedding, w->pre_ln_w, w->pre_ln_b,
+                                hidden, n_img, v.T, v.d, w->ln_eps)) != MERLIN_OK)
+    return rc;
+  for (int j = 0; j < w->num_layers; ++j)
+    if ((rc = merlin_vit_layer_forward(stream, &w->layers[j], hidden, layer_ws, n_img, v.T, v.d, w->heads, v.ff,
+                                       w->ln_eps, cta_group)) != MERLIN_OK)
+      return rc;
+  return MERLIN_OK;
+}
+
+size_t merlin_vit_saved_bytes(const merlin_vit_weights* w, int n_img) {
+  const VitDims v = vit_dims(w, n_img);
+  return vit_head_saved_bytes(v, n_img) + static_cast<size_t>(w->num_layers) * vit_layer_saved_bytes(v, n_img, w->heads) +
+         align256(static_cast<size_t>(n_img) * v.G * v.G * v.d * 2);   // + patch_out scratch
+}
+
+int merlin_vit_forward_train(void* stream, const merlin_vit_weights* w, const void* pixels, int n_img, void* saved,
+                             void* hidden, int cta_group) {
+  MB_CHECK_ARG(w && pixels && saved && hidden && n_img > 0, "vit_forward_train: null argument");
+  MB_CHECK_ARG(w->layers && w->hidden == w->heads * 64, "vit_forward_train: bad weights (head_dim 64)");
+  const VitDims v = vit_dims(w, n_img);
+  uint8_t* sv = static_cast<uint8_t*>(saved);
+  void* col = sv;
+  void* emb = sv + align256(static_cast<size_t>(n_img) * v.G * v.G * v.kpp * 2);
+  uint8_t* layers = sv + vit_head_saved_bytes(v, n_img);
+  const size_t per_layer = vit_layer_saved_bytes(v, n_img, w->heads);
+  void* patch_out = layers + static_cast<size_t>(w->num_layers) * per_layer;
+  const int M = v.M, d = v.d, ff = v.ff;
+  int rc;
+  if ((rc = merlin_patch_im2col(stream, pixels, col, n_img, w->image_size, w->patch_size, v.kpp)) != MERLIN_OK) return rc;
+  if ((rc = merlin_gemm_bf16(stream, col, v.kpp, w->patch_weight, v.kpp, patch_out, d, nullptr, 0, nullptr,
+                             n_img * v.G * v.G, d, v.kpp, MERLIN_EPI_STORE, cta_group)) != MERLIN_OK)
+    return rc;
+  if ((rc = merlin_vit_embed(stream, patch_out, w->class_embedding, w->position_embedding, emb, n_img, v.T, d)) != MERLIN_OK)
+    return rc;
+  VitSaved::Layer L, Lnext;
+  if (w->num_layers > 0) vit_layer_layout(layers, v, &L);
+  void* h0 = w->num_layers > 0 ? static_cast<void*>(L.h) : hidden;
+  if ((rc = merlin_layernorm(stream, emb, d, w->pre_ln_w, w->pre_ln_b, h0, d, M, d, w->ln_eps)) != MERLIN_OK) return rc;
+  for (int j = 0; j < w->num_layers; ++j) {
+    const merlin_vit_layer_weights* lw = &w->layers[j];
+    vit_layer_layout(layers + j * per_layer, v, &L);
+    void* h_out = hidden;
+    if (j + 1 < w->num_layers) {
+      vit_layer_layout(layers + (j + 1) * per_layer, v, &Lnext);
+      h_out = Lnext.h;                      // layer j writes its output straight into layer j+1's input slot
+    }
+    if ((rc = merlin_layernorm(stream, L.h, d, lw->ln1_w, lw->ln1_b, L.xn1, d, M, d, w->ln_eps)) != MERLIN_OK) return rc;
+    if ((rc = merlin_gemm_bf16(stream, L.xn1, d, lw->qkv_w, d, L.qkv, 3 * d, nullptr, 0, lw->qkv_b, M, 3 * d, d,
+                               MERLIN_EPI_STORE, cta_group)) != MERLIN_OK)
+      return rc;
+    if ((rc = merlin_flash_attn_fwd(stream, L.qkv, 3 * d, L.att, d, L.lse, nullptr, n_img, v.T, w->heads, 64, 0, 0.f)) !=
+        MERLIN_OK)
+      return rc;
+    if ((rc = merlin_gemm_bf16(stream, L.att, d, lw->out_w, d, L.h_mid, d, L.h, d, lw->out_b, M, d, d,
+                               MERLIN_EPI_RESIDUAL, cta_group)) != MERLIN_OK)
+      return rc;
+    if ((rc = merlin_layernorm(stream, L.h_mid, d, lw->ln2_w, lw->ln2_b, L.xn2, d, M, d, w->ln_eps)) != MERLIN_OK) return rc;
+    if ((rc = merlin_gemm_bf16(stream, L.xn2, d, lw->fc1_w, d, L.pre, ff, nullptr, 0, lw->fc1_b, M, ff, d,
+                               MERLIN_EPI_STORE, cta_group)) != MERLIN_OK)
+      return rc;
+    if ((rc = merlin_quick_gelu(stream, L.pre, nullptr, L.mid, static_cast<int64_t>(M) * ff)) != MERLIN_OK) return rc;
+    if ((rc = merlin_gemm_bf16(stream, L.mid, ff, lw->fc2_w, ff, h_out, d, L.h_mid, d, lw->fc2_b, M, d, ff,
+                               MERLIN_EPI_RESIDUAL, cta_group)) != MERLIN_OK)
+      return rc;
+  }
+  return MERLIN_OK;
+}
+
+size_t merlin_vit_backward_workspace_bytes(const merlin_vit_weights* w, int n_img) {
+  const VitDims v = vit_dims(w, n_img);
+  // dmid [M,ff] + dxn, dh_mid, datt [M,d] + dqkv [M,3d] + demb [M,d] + dpatch [n*G*G,d] + attention-backward scratch
+  return align256(static_cast<size_t>(v.M) * (static_cast<size_t>(v.ff) + 8 * v.d) * 2) +
+         align256(merlin_flash_attn_bwd_workspace_bytes(n_img, v.T, w->heads, 64)) + 1024;
+}
+
+int merlin_vit_backward(void* stream, const merlin_vit_weights* w, const merlin_vit_grads* g, void* saved, void* dh,
+                        void* workspace, int n_img, int accumulate, int cta_group) {
+  MB_CHECK_ARG(w && g && saved && dh && workspace && n_img > 0, "vit_backward: null argument");
+  MB_CHECK_ARG(w->layers && g->layers, "vit_backward: null layer tables");
+  const VitDims v = vit_dims(w, n_img);
+  const int M = v.M, d = v.d, ff = v.ff;
+  uint8_t* sv = static_cast<uint8_t*>(saved);
+  void* col = sv;
+  void* emb = sv + align256(static_cast<size_t>(n_img) * v.G * v.G * v.kpp * 2);
+  uint8_t* layers = sv + vit_head_saved_bytes(v, n_img);
+  const size_t per_layer = vit_layer_saved_bytes(v, n_img, w->heads);
+  __nv_bfloat16* dmid = static_cast<__nv_bfloat16*>(workspace);
+  __nv_bfloat16* dxn = dmid + static_cast<size_t>(M) * ff;
+  __nv_bfloat16* dh_mid = dxn + static_cast<size_t>(M) * d;
+  __nv_bfloat16* datt = dh_mid + static_cast<size_t>(M) * d;
+  __nv_bfloat16* dqkv = datt + static_cast<size_t>(M) * d;
+  __nv_bfloat16* demb = dqkv + static_cast<size_t>(M) * 3 * d;
+  __nv_bfloat16* dpatch = demb + static_cast<size_t>(M) * d;
+  void* attn_ws = static_cast<uint8_t*>(workspace) + align256(static_cast<size_t>(M) * (static_cast<size_t>(ff) + 8 * d) * 2);
+  const int epi = accumulate ? MERLIN_EPI_RESIDUAL : MERLIN_EPI_STORE;
+  int rc;
+  VitSaved::Layer L;
+  for (int j = w->num_layers - 1; j >= 0; --j) {
+    const merlin_vit_layer_weights* lw = &w->layers[j];
+    const merlin_vit_layer_grads* lg = &g->layers[j];
+    vit_layer_layout(layers + j * per_layer, v, &L);
+    // ---- MLP: h_out = h_mid + fc2(quick_gelu(fc1(LN2(h_mid))))
+    if ((rc = merlin_gemm_bf16_ex(stream, dh, d, 0, lw->fc2_w, ff, 1, dmid, ff, nullptr, 0, nullptr, M, ff, d,
+                                  MERLIN_EPI_STORE, cta_group)) != MERLIN_OK)
+      return rc;
+    if ((rc = merlin_gemm_bf16_ex(stream, dh, d, 1, L.mid, ff, 1, lg->fc2_w, ff, lg->fc2_w, ff, nullptr, d, ff, M, epi,
+                                  cta_group)) != MERLIN_OK)
+      return rc;
+    if ((rc = merlin_colsum(stream, dh, d, lg->fc2_b_f32, M, d)) != MERLIN_OK) return rc;
+    if ((rc = merlin_quick_gelu(stream, L.pre, dmid, dmid, static_cast<int64_t>(M) * ff)) != MERLIN_OK) return rc;  // dpre
+    if ((rc = merlin_gemm_bf16_ex(stream, dmid, ff, 1, L.xn2, d, 1, lg->fc1_w, d, lg->fc1_w, d, nullptr, ff, d, M, epi,
+                                  cta_group)) != MERLIN_OK)
+      return rc;
+    if ((rc = merlin_colsum(stream, dmid, ff, lg->fc1_b_f32, M, ff)) != MERLIN_OK) return rc;
+    if ((rc = merlin_gemm_bf16_ex(stream, dmid, ff, 0, lw->fc1_w, d, 1, dxn, d, nullptr, 0, nullptr, M, d, ff,
+                                  MERLIN_EPI_STORE, cta_group)) != MERLIN_OK)
+      return rc;
+    if ((rc = merlin_layernorm_bwd(stream, L.h_mid, lw->ln2_w, dxn, dh, dh_mid, lg->ln2_w_f32, lg->ln2_b_f32, M, d,
+                                   w->ln_eps)) != MERLIN_OK)
+      return rc;
+    // ---- attention: h_mid = h + out_proj(attn(qkv(LN1(h))))
+    if ((rc = merlin_gemm_bf16_ex(stream, dh_mid, d, 0, lw->out_w, d, 1, datt, d, nullptr, 0, nullptr, M, d, d,
+                                  MERLIN_EPI_STORE, cta_group)) != MERLIN_OK)
+      return rc;
+    if ((rc = merlin_gemm_bf16_ex(stream, dh_mid, d, 1, L.att, d, 1, lg->out_w, d, lg->out_w, d, nullptr, d, d, M, epi,
+                                  cta_group)) != MERLIN_OK)
+      return rc;
+    if ((rc = merlin_colsum(stream, dh_mid, d, lg->out_b_f32, M, d)) != MERLIN_OK) return rc;
+    if ((rc = merlin_flash_attn_bwd(stream, L.qkv, 3 * d, L.att, datt, d, L.lse, nullptr, dqkv, 3 * d, attn_ws, n_img, v.T,
+                                    w->heads, 64, 0, 0.f)) != MERLIN_OK)
+      return rc;
+    if ((rc = merlin_gemm_bf16_ex(stream, dqkv, 3 * d, 1, L.xn1, d, 1, lg->qkv_w, d, lg->qkv_w, d, nullptr, 3 * d, d, M,
+                                  epi, cta_group)) != MERLIN_OK)
+      return rc;
+    if ((rc = merlin_colsum(stream, dqkv, 3 * d, lg->qkv_b_f32, M, 3 * d)) != MERLIN_OK) return rc;
+    if ((rc = merlin_gemm_bf16_ex(stream, dqkv, 3 * d, 0, lw->qkv_w, d, 1, dxn, d, nullptr, 0, nullptr, M, d, 3 * d,
+                                  MERLIN_EPI_STORE, cta_group)) != MERLIN_OK)
+      return rc;
+    if ((rc = merlin_layernorm_bwd(stream, L.h, lw->ln1_w, dxn, dh_mid, dh, lg->ln1_w_f32, lg->ln1_b_f32, M, d,
+                                   w->ln_eps)) != MERLIN_OK)
+      return rc;
+  }
+  // ---- pre_layrnorm, CLS / position embeddings, patch convolution
+  if ((rc = merlin_layernorm_bwd(stream, emb, w->pre_ln_w, dh, nullptr, demb, g->pre_ln_w_f32, g->pre_ln_b_f32, M, d,
+                                 w->ln_eps)) != MERLIN_OK)
+    return rc;
+  if ((rc = merlin_vit_embed_bwd(stream, demb, dpatch, g->position_f32, g->class_f32, n_img, v.T, d)) != MERLIN_OK)
+    return rc;
+  return merlin_gemm_bf16_ex(stream, dpatch, d, 1, col, v.kpp, 1, g->patch_weight, v.kpp, g->patch_weight, v.kpp, nullptr,
+                             d, v.kpp, n_img * v.G * v.G, epi, cta_group);
+}
+
+}  // extern "C"

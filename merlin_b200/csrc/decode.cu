@@ -7,6 +7,8 @@
 // Every kernel reads the current position from device memory, so a whole step (and the greedy loop
 // around it) can be captured once in a CUDA graph and replayed.
 #include "host.cuh"
+
+#include <mutex>
 #include "ptx.cuh"
 
 #include <algorithm>
@@ -448,12 +450,11 @@ template <int kMode>
 static int launch_gemv(cudaStream_t st, GemvParams p, int tasks, int ksplit) {
   p.ksplit = ksplit;
   const size_t smem = static_cast<size_t>(p.K) * 2;
-  static bool configured = false;
-  if (!configured) {
-    MB_CHECK_CUDA(cudaFuncSetAttribute(gemv_pair_kernel<kMode>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                       96 * 1024));
-    configured = true;
-  }
+  static std::once_flag once;
+  static cudaError_t attr_rc = cudaSuccess;
+  std::call_once(once, [] { attr_rc = cudaFuncSetAttribute(gemv_pair_kernel<kMode>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                       96 * 1024); });
+  MB_CHECK_CUDA(attr_rc);
   MB_CHECK_ARG(smem <= 96 * 1024 && p.K % 8 == 0, "gemv: K=%d unsupported", p.K);
   const int blocks = (tasks * p.ksplit + kGemvWarps - 1) / kGemvWarps;
   cudaLaunchConfig_t cfg = pdl_config(dim3(blocks), dim3(kGemvThreads), smem, st);

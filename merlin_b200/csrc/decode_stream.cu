@@ -19,6 +19,8 @@
 //    reads them straight from global memory.
 // DESIGN.md §7 lists the measured variants (fence-free protocols, other cache layouts, L2 prefetch) that lost.
 #include "host.cuh"
+
+#include <mutex>
 #include "ptx.cuh"
 
 #include <cstdlib>
@@ -867,11 +869,10 @@ int merlin_decode_stream_step(void* stream, const merlin_decoder_weights* w, con
                w->intermediate);
   const int G = sm_count();
   MB_CHECK_ARG(G > (w->heads + kSC - 1) / kSC, "decode_stream_step: %d SMs are too few for %d heads", G, w->heads);
-  static bool configured = false;
-  if (!configured) {
-    MB_CHECK_CUDA(cudaFuncSetAttribute(decode_stream_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
-    configured = true;
-  }
+  static std::once_flag once;
+  static cudaError_t attr_rc = cudaSuccess;
+  std::call_once(once, [] { attr_rc = cudaFuncSetAttribute(decode_stream_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024); });
+  MB_CHECK_CUDA(attr_rc);
   const StreamLayout lay = stream_layout(w->num_layers, w->hidden, w->heads, w->intermediate);
   uint8_t* ws = static_cast<uint8_t*>(workspace);
   StreamParams p = {};

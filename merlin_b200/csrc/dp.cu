@@ -4,11 +4,15 @@
 // whole SMs (see merlin_set_sm_budget in gemm.cu).  Replaces the FSDP reduce-scatter / all-gather of the
 // reference's launch line (playground/merlin/clip-large+conv+vicuna-v15-7b/pretrain.sh:32-33).
 //
-// libnccl is resolved at run time: the process has normally loaded the torch-bundled libnccl.so.2 already
-// (RTLD_NOLOAD finds it); otherwise the loader's search path is used.  Only prototypes from <nccl.h> are
-// needed at build time.
+// libnccl is resolved at run time, in this order: the path given to merlin_dp_load_nccl() / $MERLIN_NCCL_LIB;
+// the libnccl.so.2 the process has already loaded (RTLD_NOLOAD — under PyTorch that is the torch-bundled one;
+// loading a second, different libnccl.so.2 by bare name BEFORE torch would make the loader hand torch the
+// wrong SONAME match); finally the loader's search path (plain C/C++ hosts).  Only prototypes from <nccl.h>
+// are needed at build time.
 #include "host.cuh"
 
+#include <cstdlib>
+#include <cstring>
 #include <dlfcn.h>
 #include <mutex>
 #include <nccl.h>
@@ -33,18 +37,24 @@ struct NcclApi {
   bool ok = false;
 };
 
+char g_nccl_path[1024] = "";
+
 NcclApi& api() {
   static NcclApi a;
   static std::once_flag once;
   std::call_once(once, [] {
     const char* names[] = {"libnccl.so.2", "libnccl.so"};
-    for (const char* n : names) {
-      a.handle = dlopen(n, RTLD_NOW | RTLD_NOLOAD | RTLD_GLOBAL);
-      if (a.handle) break;
-    }
+    const char* env = getenv("MERLIN_NCCL_LIB");
+    if (g_nccl_path[0]) a.handle = dlopen(g_nccl_path, RTLD_NOW | RTLD_LOCAL);
+    if (!a.handle && env && env[0]) a.handle = dlopen(env, RTLD_NOW | RTLD_LOCAL);
     if (!a.handle)
       for (const char* n : names) {
-        a.handle = dlopen(n, RTLD_NOW | RTLD_GLOBAL);
+        a.handle = dlopen(n, RTLD_NOW | RTLD_NOLOAD | RTLD_LOCAL);
+        if (a.handle) break;
+      }
+    if (!a.handle)
+      for (const char* n : names) {
+        a.handle = dlopen(n, RTLD_NOW | RTLD_LOCAL);
         if (a.handle) break;
       }
     if (!a.handle) return;
@@ -92,6 +102,12 @@ struct DpComm {
   } while (0)
 
 extern "C" {
+
+int merlin_dp_load_nccl(const char* path) {
+  if (path && path[0]) snprintf(mb::g_nccl_path, sizeof(mb::g_nccl_path), "%s", path);
+  MB_NEED_NCCL();
+  return MERLIN_OK;
+}
 
 int merlin_dp_unique_id(void* id_out) {
   MB_NEED_NCCL();

@@ -2,8 +2,10 @@
 #include "gemm.cuh"
 #include "host.cuh"
 
+#include <atomic>
 #include <cstring>
 #include <mutex>
+#include <unordered_map>
 
 namespace mb {
 
@@ -46,8 +48,57 @@ int make_tmap_f32(CUtensorMap* out, const void* base, int rank, const uint64_t* 
   return make_tmap_typed(out, base, rank, dims, strides_bytes, box, CU_TENSOR_MAP_DATA_TYPE_FLOAT32);
 }
 
+// Encoded tensor maps are cached per thread, keyed on everything that goes into the encoding (base pointer,
+// dims, strides, box, dtype): a training step re-issues the same ~30 GEMM shapes over the same buffers for
+// every layer and every step, and cuTensorMapEncodeTiled costs a driver call each time.  thread_local keeps
+// the library re-entrant without a lock (SURVEY.md §8b threading).
+struct TmapKey {
+  uint64_t base;
+  uint64_t dims[5];
+  uint64_t strides[4];
+  uint32_t box[5];
+  uint32_t rank_dtype;
+  bool operator==(const TmapKey& o) const { return memcmp(this, &o, sizeof(TmapKey)) == 0; }
+};
+struct TmapKeyHash {
+  size_t operator()(const TmapKey& k) const {
+    const uint64_t* w = reinterpret_cast<const uint64_t*>(&k);
+    uint64_t h = 1469598103934665603ull;
+    for (size_t i = 0; i < sizeof(TmapKey) / 8; ++i) h = (h ^ w[i]) * 1099511628211ull;
+    return static_cast<size_t>(h);
+  }
+};
+static_assert(sizeof(TmapKey) % 8 == 0, "TmapKey is hashed as 64-bit words");
+
+static int make_tmap_encode(CUtensorMap* out, const void* base, int rank, const uint64_t* dims,
+                            const uint64_t* strides_bytes, const uint32_t* box, CUtensorMapDataType dtype);
+
 static int make_tmap_typed(CUtensorMap* out, const void* base, int rank, const uint64_t* dims,
                            const uint64_t* strides_bytes, const uint32_t* box, CUtensorMapDataType dtype) {
+  static thread_local std::unordered_map<TmapKey, CUtensorMap, TmapKeyHash> cache;
+  TmapKey k;
+  memset(&k, 0, sizeof(k));
+  k.base = reinterpret_cast<uint64_t>(base);
+  for (int i = 0; i < rank; ++i) {
+    k.dims[i] = dims[i];
+    k.box[i] = box[i];
+    if (i + 1 < rank) k.strides[i] = strides_bytes[i];
+  }
+  k.rank_dtype = (static_cast<uint32_t>(rank) << 16) | static_cast<uint32_t>(dtype);
+  auto it = cache.find(k);
+  if (it != cache.end()) {
+    *out = it->second;
+    return MERLIN_OK;
+  }
+  int rc = make_tmap_encode(out, base, rank, dims, strides_bytes, box, dtype);
+  if (rc != MERLIN_OK) return rc;
+  if (cache.size() >= 8192) cache.clear();
+  cache.emplace(k, *out);
+  return MERLIN_OK;
+}
+
+static int make_tmap_encode(CUtensorMap* out, const void* base, int rank, const uint64_t* dims,
+                            const uint64_t* strides_bytes, const uint32_t* box, CUtensorMapDataType dtype) {
   EncodeTiledFn fn = encode_fn();
   if (!fn) {
     set_error("cuTensorMapEncodeTiled entry point unavailable (no CUDA driver?)");
@@ -88,27 +139,40 @@ static int make_tmap_typed(CUtensorMap* out, const void* base, int rank, const u
 
 int sm_count() {
   static int n = 0;
-  if (n == 0) {
+  static std::once_flag once;
+  std::call_once(once, [] {
     int dev = 0;
     cudaGetDevice(&dev);
     cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev);
-  }
+  });
   return n;
+}
+
+// SM budget of the persistent kernels (merlin_set_sm_budget): 0 = the whole chip.  The data-parallel step loop
+// lowers it while gradient all-reduces are in flight, so the static tile schedule of the GEMM is laid over the
+// SMs the collective's CTAs leave free instead of queueing CTAs behind them.
+static std::atomic<int> g_sm_budget{0};
+
+int sm_budget() {
+  const int n = sm_count();
+  const int b = g_sm_budget.load(std::memory_order_relaxed);
+  return (b > 0 && b < n) ? b : n;
 }
 
 template <int kCtaGroup, bool kAMN, bool kBMN>
 static int launch_gemm(cudaStream_t stream, const CUtensorMap& ta, const CUtensorMap& tb,
                        const CUtensorMap& tc, const CUtensorMap& tr, const GemmParams& p) {
   using Cfg = GemmCfg<kCtaGroup>;
-  static bool configured = false;
-  if (!configured) {
-    MB_CHECK_CUDA(cudaFuncSetAttribute(gemm_bf16_kernel<kCtaGroup, kAMN, kBMN>,
-                                       cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::kSmemBytes));
-    configured = true;
-  }
+  static std::once_flag once;
+  static cudaError_t attr_rc = cudaSuccess;
+  std::call_once(once, [] {
+    attr_rc = cudaFuncSetAttribute(gemm_bf16_kernel<kCtaGroup, kAMN, kBMN>,
+                                   cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::kSmemBytes);
+  });
+  MB_CHECK_CUDA(attr_rc);
   const int rows_per_tile = kBlockM * kCtaGroup;
   const int tiles = ((p.M + rows_per_tile - 1) / rows_per_tile) * ((p.N + kBlockN - 1) / kBlockN);
-  int workers = sm_count() / kCtaGroup;
+  int workers = sm_budget() / kCtaGroup;
   if (tiles < workers) workers = tiles;
   cudaLaunchConfig_t cfg = {};
   cfg.gridDim = dim3(static_cast<unsigned>(workers * kCtaGroup));
@@ -185,6 +249,13 @@ int gemm_dispatch(cudaStream_t stream, const void* A, int64_t lda, const void* B
 extern "C" {
 
 const char* merlin_last_error(void) { return mb::g_error; }
+
+int merlin_set_sm_budget(int sms) {
+  const int prev = mb::g_sm_budget.exchange(sms < 0 ? 0 : sms, std::memory_order_relaxed);
+  return prev;
+}
+
+int merlin_sm_count(void) { return mb::sm_count(); }
 
 int merlin_gemm_bf16(void* stream, const void* A, int64_t lda, const void* B, int64_t ldb, void* C,
                      int64_t ldc, const void* R, int64_t ldr, const void* bias, int M, int N, int K,

@@ -40,5 +40,7 @@ int make_tmap_f32(CUtensorMap* out, const void* base, int rank, const uint64_t* 
                   const uint64_t* strides_bytes, const uint32_t* box);
 
 int sm_count();
+// SMs the persistent kernels may occupy right now (merlin_set_sm_budget; defaults to sm_count()).
+int sm_budget();
 
 }  // namespace mb

@@ -122,7 +122,7 @@ class DecodeRunner:
         self._greedy_body()  # warm-up outside capture (one-time kernel attributes)
         torch.cuda.synchronize()
         g = torch.cuda.CUDAGraph()
-        with torch.cuda.graph(g):
+        with torch.cuda.graph(g, capture_error_mode="thread_local"):
             self._greedy_body()
         self.graph = g
 
@@ -162,20 +162,31 @@ class DecodeRunner:
         return self.out_ids[base:base + done].clone()
 
 
-class GraphedGenerator:
-    """Whole generate() step from CUDA graphs for one (sequence length, image batch) shape: static
-    input buffers, one graph for the multimodal prefill (ViT -> projector -> splice -> 32 layers ->
-    lm_head -> argmax of the last row), then DecodeRunner's per-token graph."""
+class DecodeState:
+    """KV cache + DecodeRunner (+ its per-token CUDA graph) for one capacity bucket.  The decode graph reads the
+    position from device memory, so ONE state serves every prompt length that fits the bucket."""
 
-    def __init__(self, lm, S: int, image_shape, capacity: int):
+    def __init__(self, lm, capacity: int):
         from .mmgpt.model.mmgpt.llama_mmgpt import MerlinKVCache
         cfg = lm.config
+        self.capacity = capacity
+        self.cache = MerlinKVCache(cfg.num_hidden_layers, 1, capacity, cfg.hidden_size, lm.device)
+        self.runner = DecodeRunner(lm, self.cache)
+        self.runner.ensure_graph()
+
+
+class GraphedGenerator:
+    """Multimodal prefill for one (sequence length, image batch) shape: ViT -> projector -> splice -> decoder
+    layers -> lm_head -> argmax of the last row, into the KV cache of a shared DecodeState.  The first call for a
+    shape runs the launches eagerly; a shape that comes back is captured into a CUDA graph (static input buffers)
+    and replayed from then on — evaluation prompts rarely repeat a length, benchmark / serving shapes do."""
+
+    def __init__(self, lm, S: int, image_shape, state: DecodeState):
         dev = lm.device
-        self.lm, self.S = lm, S
+        self.lm, self.S, self.state = lm, S, state
+        self.cache, self.runner = state.cache, state.runner
         self.ids = torch.zeros((1, S), dtype=torch.int64, device=dev)
         self.img = torch.zeros(tuple(image_shape), dtype=torch.bfloat16, device=dev)
-        self.cache = MerlinKVCache(cfg.num_hidden_layers, 1, capacity, cfg.hidden_size, dev)
-        self.runner = DecodeRunner(lm, self.cache)
         tower = lm.get_model().vision_tower
         rows = image_shape[0] * tower.num_patches
         self.feat_offset = torch.zeros(1, dtype=torch.int32, device=dev)
@@ -183,12 +194,14 @@ class GraphedGenerator:
         self.scratch_pos = torch.zeros(1, dtype=torch.int32, device=dev)
         self.per_image = tower.num_patches
         self.launches = 0
-        self.cache.seq_len = S
-        self.runner.ensure_graph()
+        self.graph = None
+        self.calls = 0
+
+    def capture(self):
         self._body()                       # warm-up outside capture
         torch.cuda.synchronize()
         g = torch.cuda.CUDAGraph()
-        with torch.cuda.graph(g):
+        with torch.cuda.graph(g, capture_error_mode="thread_local"):
             self._body()
         self.graph = g
 
@@ -208,13 +221,20 @@ class GraphedGenerator:
         self.launches = _ops.PROFILE.launches - before + 2
         self.logits2d = logits2d
 
-    def generate(self, input_ids: torch.Tensor, images: torch.Tensor, max_new_tokens: int, eos_token_id=None):
+    def generate(self, input_ids: torch.Tensor, images: torch.Tensor, max_new_tokens: int, eos_token_id=None,
+                 capture_after: int = 1):
         ids_host = input_ids if not input_ids.is_cuda else input_ids.cpu()
         self.lm._validate_image_grammar(ids_host, [images], self.per_image)
         self.ids.copy_(input_ids, non_blocking=True)
         self.img.copy_(images, non_blocking=True)
-        self.graph.replay()
-        _ops.PROFILE.launches += self.launches
+        self.calls += 1
+        if self.graph is None and self.calls > capture_after:
+            self.capture()
+        if self.graph is not None:
+            self.graph.replay()
+            _ops.PROFILE.launches += self.launches
+        else:
+            self._body()
         self.cache.seq_len = self.S
         new = None
         if max_new_tokens > 1:
@@ -236,18 +256,41 @@ def weight_fingerprint(lm) -> int:
     return hash(tuple(p.data_ptr() for p in probes))
 
 
-def graphed_generate(lm, input_ids, images, max_new_tokens, eos_token_id):
-    key = (int(input_ids.shape[1]), tuple(images.shape))
+CAPACITY_BUCKET = 1024      # KV-cache capacities are rounded up to a multiple of this
+MAX_DECODE_STATES = 2       # capacity buckets kept alive (each holds a full KV cache)
+MAX_PREFILL_SHAPES = 8      # (length, image shape) entries kept (static input buffers; a graph once a shape repeats)
+
+
+def graphed_generate(lm, input_ids, images, max_new_tokens, eos_token_id, capture_after: int = 1):
+    """Greedy generate() from device-resident state.  ONE KV cache + decode runner + per-token graph per capacity
+    bucket serves every prompt length (evaluation prompts almost never repeat a length); the prefill of a shape
+    is captured into a CUDA graph only once that shape has been seen `capture_after` times."""
     pool = lm.__dict__.setdefault("_graphed", {})
+    states = lm.__dict__.setdefault("_decode_states", {})
     fp = weight_fingerprint(lm)
     if lm.__dict__.get("_graphed_fp") != fp:      # graphs captured for other weight addresses are stale
         pool.clear()
+        states.clear()
         lm.__dict__["_graphed_fp"] = fp
-    gen = pool.get(key)
     need = input_ids.shape[1] + max_new_tokens + 8
-    if gen is None or gen.cache.capacity < need:
-        if len(pool) >= 4:
+    cap = (need + CAPACITY_BUCKET - 1) // CAPACITY_BUCKET * CAPACITY_BUCKET
+    state = states.get(cap)
+    if state is None:
+        bigger = [c for c in states if c >= cap]
+        if bigger:                                 # a larger bucket already exists: use it
+            cap = min(bigger)
+            state = states[cap]
+        else:
+            while len(states) >= MAX_DECODE_STATES:
+                old = next(iter(states))
+                states.pop(old)
+                for k in [k for k in pool if k[2] == old]:
+                    pool.pop(k)
+            state = states[cap] = DecodeState(lm, cap)
+    key = (int(input_ids.shape[1]), tuple(images.shape), cap)
+    gen = pool.get(key)
+    if gen is None:
+        while len(pool) >= MAX_PREFILL_SHAPES:
             pool.pop(next(iter(pool)))
-        gen = GraphedGenerator(lm, int(input_ids.shape[1]), images.shape, need)
-        pool[key] = gen
-    return gen.generate(input_ids, images, max_new_tokens, eos_token_id)
+        gen = pool[key] = GraphedGenerator(lm, int(input_ids.shape[1]), images.shape, state)
+    return gen.generate(input_ids, images, max_new_tokens, eos_token_id, capture_after)

@@ -61,6 +61,19 @@ _PROTOTYPES = {
     "merlin_image_preprocess": [_P, _P, c_int64, c_int, c_int, c_int, _P, _P, _P, _P, c_int, _P],
     "merlin_kv_append": [_P, _P, c_int64, _P, c_int64, c_int, c_int, c_int, c_int, c_int],
     "merlin_record_advance": [_P, _P, _P, _P, _P, c_int],
+    "merlin_dp_load_nccl": [c_char_p],
+    "merlin_dp_unique_id": [_P],
+    "merlin_dp_init": [_P, c_int, c_int, c_int, ctypes.POINTER(c_void_p)],
+    "merlin_dp_allreduce_bucket": [_P, _P, _P, c_int64],
+    "merlin_dp_allreduce_f32": [_P, _P, _P, c_int64, c_int],
+    "merlin_dp_mem_alloc": [ctypes.POINTER(c_void_p), c_int64],
+    "merlin_dp_mem_free": [_P],
+    "merlin_dp_register": [_P, _P, c_int64, ctypes.POINTER(c_void_p)],
+    "merlin_dp_deregister": [_P, _P],
+    "merlin_dp_finalize": [_P],
+    "merlin_dp_nccl_version": [],
+    "merlin_set_sm_budget": [c_int],
+    "merlin_sm_count": [],
 }
 
 
@@ -87,6 +100,29 @@ class VitLayerWeights(ctypes.Structure):
                                         "fc1_w", "fc1_b", "fc2_w", "fc2_b")]
 
 
+class VitWeights(ctypes.Structure):
+    """struct merlin_vit_weights."""
+    _fields_ = [(n, c_int) for n in ("num_layers", "hidden", "heads", "intermediate", "image_size", "patch_size",
+                                     "k_patch_padded")] + [("ln_eps", c_float)] + \
+               [(n, c_void_p) for n in ("class_embedding", "patch_weight", "position_embedding", "pre_ln_w", "pre_ln_b")] + \
+               [("layers", ctypes.POINTER(VitLayerWeights))]
+
+
+class VitLayerGrads(ctypes.Structure):
+    """struct merlin_vit_layer_grads."""
+    _fields_ = [(n, c_void_p) for n in ("qkv_w", "out_w", "fc1_w", "fc2_w", "qkv_b_f32", "out_b_f32", "ln1_w_f32",
+                                        "ln1_b_f32", "ln2_w_f32", "ln2_b_f32", "fc1_b_f32", "fc2_b_f32")]
+
+
+class VitGrads(ctypes.Structure):
+    """struct merlin_vit_grads."""
+    _fields_ = [(n, c_void_p) for n in ("patch_weight", "position_f32", "class_f32", "pre_ln_w_f32", "pre_ln_b_f32")] + \
+               [("layers", ctypes.POINTER(VitLayerGrads))]
+
+
+_PROTOTYPES["merlin_vit_forward"] = [_P, _P, _P, c_int, _P, _P, c_int]
+_PROTOTYPES["merlin_vit_forward_train"] = [_P, _P, _P, c_int, _P, _P, c_int]
+_PROTOTYPES["merlin_vit_backward"] = [_P, _P, _P, _P, _P, _P, c_int, c_int, c_int]
 _PROTOTYPES["merlin_decoder_layer_forward"] = [_P, _P, _P, _P, _P, _P, _P, _P, c_int64, c_int, c_int, c_int, c_int,
                                                c_int, c_float, c_int]
 _PROTOTYPES["merlin_vit_layer_forward"] = [_P, _P, _P, _P, c_int, c_int, c_int, c_int, c_int, c_float, c_int]
@@ -112,7 +148,10 @@ _SIZE_FNS = {"merlin_decoder_layer_saved_bytes": [c_int, c_int, c_int, c_int, c_
              "merlin_projector_workspace_bytes": [c_int, c_int, c_int, c_int],
              "merlin_flash_attn_bwd_workspace_bytes": [c_int, c_int, c_int, c_int],
              "merlin_decoder_layer_workspace_bytes": [c_int, c_int, c_int],
-             "merlin_vit_layer_workspace_bytes": [c_int, c_int, c_int]}
+             "merlin_vit_layer_workspace_bytes": [c_int, c_int, c_int],
+             "merlin_vit_workspace_bytes": [_P, c_int],
+             "merlin_vit_saved_bytes": [_P, c_int],
+             "merlin_vit_backward_workspace_bytes": [_P, c_int]}
 
 
 def declared_symbols(header: str = _HEADER) -> list[str]:

@@ -4,14 +4,21 @@ What is kept: the token grammar (`add_image_token`, :53-61), the prompt / text t
 and every image token masked out of the labels (`token_processor`, :63-152), the merge of `merge_round` records
 into one interleaved training sample (`__getitem__`, :157-185) and the zero-image fallback (:143-144).  What is
 replaced: the webdataset / megfile / S3 pipeline (:30-41) by a plain `tarfile` reader over local shards with the
-same record format (one `<key>.json` with `prompt`, `txt`, `image_name_list`, plus `<suffix>.jpg` members), and
+same record format (one `<key>.json` with `prompt`, `txt`, `image_name_list`, plus `<suffix>.jpg` members) that
+keeps the pipeline's data-parallel semantics — an infinite, per-epoch reshuffled shard list (seed 3407), a
+shard-level shuffle buffer of world_size, `split_by_node` (rank r takes every world_size-th shard),
+`split_by_worker` (DataLoader worker w every num_workers-th of those) and a 1000-sample shuffle buffer (seed 42) —
+so ranks and workers read DISJOINT shards instead of identical samples; and
 the PIL + CLIPImageProcessor image path (`base_dataset.py:179-198`, mode 'resize') by the GPU preprocessing
 kernel (`ops.image_preprocess`: bit-exact PIL bicubic resize on the uint8 pixels + CLIP mean / std normalise).
 """
 from __future__ import annotations
 
 import io
+import itertools
 import json
+import os
+import random
 import tarfile
 from typing import Dict, Iterator, List, Optional, Sequence
 
@@ -45,11 +52,43 @@ def iter_tar_records(shards: Sequence[str]) -> Iterator[dict]:
                 yield cur
 
 
+def shuffle_buffer(src: Iterator, bufsize: int, rng: random.Random) -> Iterator:
+    """webdataset's `shuffle(bufsize, rng=...)` (the `_shuffle` filter): keep `bufsize` items, swap each incoming
+    item with a random slot and emit what was there; drain the buffer at the end of a finite stream."""
+    if bufsize <= 1:
+        yield from src
+        return
+    buf = []
+    for item in src:
+        if len(buf) < bufsize:
+            buf.append(item)
+            continue
+        k = rng.randint(0, bufsize - 1)
+        item, buf[k] = buf[k], item
+        yield item
+    rng.shuffle(buf)
+    yield from buf
+
+
+def rank_and_world():
+    """(rank, world_size) of this process: torch.distributed when initialised, else torchrun's environment."""
+    try:
+        import torch.distributed as dist
+        if dist.is_available() and dist.is_initialized():
+            return dist.get_rank(), dist.get_world_size()
+    except Exception:
+        pass
+    return int(os.environ.get("RANK", "0")), int(os.environ.get("WORLD_SIZE", "1"))
+
+
 class InterPairWebDataset:
     """Interleave-format dataset for stage-1 pre-training (reference docstring, :17)."""
 
+    SHARD_SEED, SHUFFLE_SEED, SAMPLE_BUFFER = 3407, 42, 1000      # interpair_webdataset.py:32-37
+
     def __init__(self, shards: Sequence[str], tokenizer, multimodal_cfg: dict, merge_round: int = 1,
-                 data_size: Optional[int] = None, image_loader=None):
+                 data_size: Optional[int] = None, image_loader=None, rank: Optional[int] = None,
+                 world_size: Optional[int] = None, shuffle: bool = True):
         self.tokenizer = tokenizer
         self.multimodal_cfg = multimodal_cfg
         self.image_size = multimodal_cfg["image_size"]
@@ -61,18 +100,56 @@ class InterPairWebDataset:
         if self.use_im_start_end:
             self.replace_token = DEFAULT_IM_START_TOKEN + self.replace_token + DEFAULT_IM_END_TOKEN
         self.shards = list(shards)
-        self.inner_iter = self._infinite()
+        if not self.shards:
+            raise RuntimeError("InterPairWebDataset: no shards given")
+        self.rank, self.world_size, self.shuffle = rank, world_size, shuffle
+        self._inner_iter = None           # built on first use, i.e. inside the DataLoader worker that consumes it
         self.data_size = data_size if data_size is not None else sum(1 for _ in iter_tar_records(self.shards))
         self.image_loader = image_loader or self._load_image
 
-    def _infinite(self):
-        while True:                       # wds.InfiniteShardList (:32)
-            yielded = False
-            for rec in iter_tar_records(self.shards):
-                yielded = True
-                yield rec
-            if not yielded:
-                raise RuntimeError("InterPairWebDataset: no records in the given shards")
+    # ------------------------------------------------------------------ the data pipeline (:30-41)
+    def _shard_stream(self) -> Iterator[str]:
+        """wds.InfiniteShardList(shards, seed=3407): every epoch walks the shard list in a freshly seeded order."""
+        epoch = 0
+        while True:
+            order = list(self.shards)
+            if self.shuffle:
+                random.Random(self.SHARD_SEED + epoch).shuffle(order)
+            yield from order
+            epoch += 1
+
+    def _pipeline(self) -> Iterator[dict]:
+        rank, world = rank_and_world()
+        rank = self.rank if self.rank is not None else rank
+        world = self.world_size if self.world_size is not None else world
+        info = torch.utils.data.get_worker_info()
+        wid, nworkers = (info.id, info.num_workers) if info is not None else (0, 1)
+        stream = self._shard_stream()
+        if self.shuffle:
+            stream = shuffle_buffer(stream, world, random.Random(self.SHUFFLE_SEED))     # wds.shuffle(world_size)
+        stream = itertools.islice(stream, rank, None, world)                             # wds.split_by_node
+        stream = itertools.islice(stream, wid, None, nworkers)                           # wds.split_by_worker
+
+        def records():
+            empty_in_a_row = 0
+            for shard in stream:
+                n = 0
+                for rec in iter_tar_records([shard]):
+                    n += 1
+                    yield rec
+                empty_in_a_row = 0 if n else empty_in_a_row + 1
+                if empty_in_a_row > len(self.shards):
+                    raise RuntimeError("InterPairWebDataset: no records in the given shards")
+
+        if self.shuffle:
+            return shuffle_buffer(records(), self.SAMPLE_BUFFER, random.Random(self.SHUFFLE_SEED))  # wds.shuffle(1000)
+        return records()
+
+    @property
+    def inner_iter(self):
+        if self._inner_iter is None:
+            self._inner_iter = self._pipeline()
+        return self._inner_iter
 
     # ------------------------------------------------------------------ image path (base_dataset.py:179-198)
     def _load_image(self, data: bytes) -> torch.Tensor:

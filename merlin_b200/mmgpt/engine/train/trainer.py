@@ -245,8 +245,10 @@ class MMGPTTrainer:
 
     def optimizer_step(self):
         a, ar = self.args, self.arena
-        self.global_step += 1
+        # HF Trainer steps the scheduler AFTER optimizer.step(): update k (1-based) runs at lr(k - 1), so the first
+        # update of a warm-up schedule has lr 0 (it still moves the AdamW moments, as torch.optim.AdamW does)
         lr = cosine_lr(self.global_step, a.learning_rate, a.max_steps, a.warmup_ratio)
+        self.global_step += 1
         ops.grad_sumsq(ar.grads, self._sumsq)
         ops.adamw_step(ar.params, ar.grads, ar.exp_avg, ar.exp_avg_sq, ar.lr_mult, ar.weight_decay, ar.chunk, lr,
                        a.adam_beta1, a.adam_beta2, a.adam_epsilon, self.global_step, 1.0, a.max_grad_norm, self._sumsq)

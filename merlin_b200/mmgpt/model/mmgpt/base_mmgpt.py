@@ -103,6 +103,7 @@ class MMGPTMetaForCausalLM(ABC):
                 raise ValueError(f"The number of image start tokens ({n_start}) and image end tokens "
                                  f"({n_end}) should be the same.")
             starts = torch.where(row == self.im_start_token)[0].tolist()
+            blocks = 0
             for pos, _ in zip(starts, range(images[b].shape[0])):
                 end = pos + per_image + 1
                 if end >= row.shape[0] or int(row[end]) != self.im_end_token:
@@ -110,6 +111,15 @@ class MMGPTMetaForCausalLM(ABC):
                 if not bool((row[pos + 1:end] == self.im_patch_token).all()):
                     raise ValueError("The image patch tokens between <im_start> and <im_end> must be "
                                      "<im_patch> placeholders.")
+                blocks += 1
+            # The splice kernel places feature row r at the r-th <im_patch> of the sample.  The reference replaces
+            # the span after each of the first n <im_start> tokens and leaves any other <im_patch> as a plain
+            # embedding (base_mmgpt.py:119-135): a stray placeholder outside the validated blocks would shift every
+            # later feature row by one here, so it is an error instead of a silent misalignment.
+            n_patch = int((row == self.im_patch_token).sum())
+            if n_patch != blocks * per_image:
+                raise ValueError(f"{n_patch} <im_patch> tokens for {blocks} image block(s) of {per_image}: "
+                                 "<im_patch> may only appear between <im_start> and <im_end>")
 
     def prepare_inputs_labels_for_multimodal(self, input_ids, attention_mask, past_key_values, labels, images):
         model = self.get_model()

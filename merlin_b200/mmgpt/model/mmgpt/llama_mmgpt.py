@@ -19,7 +19,6 @@ from __future__ import annotations
 import json
 import os
 from collections import OrderedDict
-from dataclasses import dataclass
 from typing import List, Optional
 
 import torch
@@ -31,31 +30,13 @@ from ....lib import EPI_RESIDUAL, EPI_SWIGLU
 from ...utils.constants import IGNORE_INDEX
 from .base_mmgpt import MMGPTMetaForCausalLM
 
-try:  # keep the HF config class when transformers is importable (it is in this image)
-    from transformers import LlamaConfig
-    from transformers.modeling_outputs import CausalLMOutputWithPast
+from transformers import AutoConfig, AutoModelForCausalLM, GenerationMixin, LlamaConfig, PreTrainedModel
+from transformers.modeling_outputs import CausalLMOutputWithPast
 
-    class MMGPTConfig(LlamaConfig):
-        model_type = "mmgpt"
-except Exception:  # pragma: no cover
-    LlamaConfig = None
 
-    @dataclass
-    class CausalLMOutputWithPast:  # type: ignore
-        loss: Optional[torch.Tensor] = None
-        logits: Optional[torch.Tensor] = None
-        past_key_values: Optional[object] = None
-        hidden_states: Optional[tuple] = None
-        attentions: Optional[tuple] = None
-
-    class MMGPTConfig:  # type: ignore
-        model_type = "mmgpt"
-
-        def __init__(self, **kw):
-            self.__dict__.update(dict(vocab_size=32000, hidden_size=4096, intermediate_size=11008,
-                                      num_hidden_layers=32, num_attention_heads=32, rms_norm_eps=1e-5,
-                                      rope_theta=10000.0, max_position_embeddings=4096))
-            self.__dict__.update(kw)
+class MMGPTConfig(LlamaConfig):
+    """llama_mmgpt.py:27-28."""
+    model_type = "mmgpt"
 
 
 def vicuna_7b_config(**kw) -> "MMGPTConfig":
@@ -139,6 +120,7 @@ class MMGPTLlamaModel(nn.Module):
         self.ln2_w = nn.ParameterList([nn.Parameter(torch.ones(D)) for _ in range(L)])
         self.norm_w = nn.Parameter(torch.ones(D))
         self._rope = None  # (cos, sin) fp32 tables, built lazily on the parameter device
+        self.gradient_checkpointing = False  # set by gradient_checkpointing_enable(): per-layer activation recompute
 
     def rope_tables(self, need: int):
         if self._rope is None or self._rope[0].shape[0] < need or self._rope[0].device != self.embed_tokens.device:
@@ -184,12 +166,26 @@ class MMGPTLlamaModel(nn.Module):
         return out, hidden
 
 
-class MMGPTLlamaForCausalLM(nn.Module, MMGPTMetaForCausalLM):
+class MMGPTLlamaForCausalLM(PreTrainedModel, GenerationMixin, MMGPTMetaForCausalLM):
+    """HF `PreTrainedModel` + `GenerationMixin` subclass registered as model_type "mmgpt", like the reference's
+    `MMGPTLlamaForCausalLM(LlamaForCausalLM, MMGPTMetaForCausalLM)` (llama_mmgpt.py:38,137-138): `AutoConfig` /
+    `AutoModelForCausalLM` resolve it, `Trainer`-style `model(**batch).loss.backward()` trains it (autograd
+    Functions over the library's backward entry points, merlin_b200/autograd.py) and `generate(**hf_kwargs)`
+    accepts the HF generation arguments.  The decoder itself is not HF's LlamaModel: weights live packed in
+    `MMGPTLlamaModel` and every FLOP runs in libmerlin_b200.so."""
     config_class = MMGPTConfig
+    base_model_prefix = "model"
+    main_input_name = "input_ids"
+    supports_gradient_checkpointing = True
+    _supports_flash_attn = True
+    _supports_sdpa = True
+    _supports_flex_attn = True
+    _supports_attention_backend = True
+    _no_split_modules = []
+    _tied_weights_keys = None
 
     def __init__(self, config):
-        super().__init__()
-        self.config = config
+        super().__init__(config)
         self.model = MMGPTLlamaModel(config)
         std = getattr(config, "initializer_range", 0.02)
         self.lm_head_w = nn.Parameter(torch.empty(config.vocab_size, config.hidden_size).normal_(0.0, std))
@@ -198,6 +194,15 @@ class MMGPTLlamaForCausalLM(nn.Module, MMGPTMetaForCausalLM):
         self.im_patch_token, self.im_start_token, self.im_end_token = 32000, 32001, 32002
         self.num_new_tokens = 0
         self._decoder = None
+        self.post_init()
+
+    def _init_weights(self, module):
+        """Parameters are initialised by the constructors above (N(0, initializer_range), norm weights 1)."""
+        return
+
+    def tie_weights(self, *args, **kwargs):
+        """lm_head and embed_tokens are never tied (Vicuna: tie_word_embeddings=False)."""
+        return
 
     # ------------------------------------------------------------------ HF-style accessors
     def get_model(self):
@@ -291,12 +296,26 @@ class MMGPTLlamaForCausalLM(nn.Module, MMGPTMetaForCausalLM):
                     dst.copy_(src)
         return torch.nn.modules.module._IncompatibleKeys(missing, unexpected)
 
-    def save_pretrained(self, save_directory: str):
+    def save_pretrained(self, save_directory: str, state_dict=None, safe_serialization: bool = False, **kwargs):
+        """Writes `pytorch_model.bin` (reference key names) + `config.json` — the files the reference's own
+        loaders read back (clip_encoder.py:26-62, base_projector.py:12-48, from_pretrained).  `state_dict`
+        (HF Trainer._save passes the CPU copy made by trainer.py:29-43) overrides the live weights;
+        safe_serialization=True writes `model.safetensors` instead."""
         os.makedirs(save_directory, exist_ok=True)
-        sd = {k: v.detach().cpu().contiguous() for k, v in self.state_dict().items()}
-        torch.save(sd, os.path.join(save_directory, "pytorch_model.bin"))
-        cfg = self.config.to_dict() if hasattr(self.config, "to_dict") else dict(self.config.__dict__)
-        json.dump(cfg, open(os.path.join(save_directory, "config.json"), "w"), indent=2, default=str)
+        sd = state_dict if state_dict is not None else self.state_dict()
+        sd = {k: v.detach().cpu().contiguous() for k, v in sd.items()}
+        if safe_serialization:
+            from safetensors.torch import save_file
+            save_file({k: v.clone() for k, v in sd.items()}, os.path.join(save_directory, "model.safetensors"),
+                      metadata={"format": "pt"})
+        else:
+            torch.save(sd, os.path.join(save_directory, "pytorch_model.bin"))
+        self.config.save_pretrained(save_directory)
+        if getattr(self, "generation_config", None) is not None:
+            try:
+                self.generation_config.save_pretrained(save_directory)
+            except Exception:  # an invalid user-edited generation config must not lose the weights
+                pass
 
     @staticmethod
     def _read_checkpoint(path: str):
@@ -318,7 +337,12 @@ class MMGPTLlamaForCausalLM(nn.Module, MMGPTMetaForCausalLM):
         return sd
 
     @classmethod
-    def from_pretrained(cls, path: str, config=None, **_):
+    def from_pretrained(cls, pretrained_model_name_or_path: str, *model_args, config=None, torch_dtype=None, dtype=None,
+                        **_):
+        """Local-directory loader with the call shape of builder.py:70 (`from_pretrained(path, cache_dir=...)`):
+        config.json + pytorch_model.bin[.index.json] / *.safetensors in reference key names (a plain Vicuna
+        checkpoint or a saved mmgpt model)."""
+        path = pretrained_model_name_or_path
         if config is None:
             raw = json.load(open(os.path.join(path, "config.json")))
             raw = {k: v for k, v in raw.items() if k not in ("model_type", "architectures", "transformers_version")}
@@ -331,6 +355,9 @@ class MMGPTLlamaForCausalLM(nn.Module, MMGPTMetaForCausalLM):
             if vocab != config.vocab_size:           # checkpoint saved after the image tokens were added
                 model.resize_token_embeddings(vocab)
             model.load_state_dict(llm, strict=False)
+        want = dtype if dtype is not None else torch_dtype
+        if isinstance(want, torch.dtype):
+            model.to(want)
         return model
 
     # ------------------------------------------------------------------ forward (llama_mmgpt.py:53-112)
@@ -346,7 +373,16 @@ class MMGPTLlamaForCausalLM(nn.Module, MMGPTMetaForCausalLM):
                                "model.to(dtype=torch.bfloat16, device='cuda') first (builder.py:163)")
         return_dict = True if return_dict is None else return_dict
         if past_key_values is not None and not isinstance(past_key_values, MerlinKVCache):
-            raise TypeError("past_key_values must be the MerlinKVCache returned by a previous forward")
+            # HF generate() pre-allocates an EMPTY DynamicCache: that is "no past, please
+            # cache" — the MerlinKVCache of this forward's output replaces it in HF's model_kwargs
+            if hasattr(past_key_values, "get_seq_length") and past_key_values.get_seq_length() == 0:
+                past_key_values, use_cache = None, True
+            else:
+                raise TypeError("past_key_values must be the MerlinKVCache returned by a previous forward")
+        if (torch.is_grad_enabled() and past_key_values is None and not use_cache
+                and self._wants_grad(inputs_embeds)):
+            return self._forward_autograd(input_ids, attention_mask, inputs_embeds, labels, images,
+                                          bool(output_hidden_states), return_dict)
         if past_key_values is not None and not past_key_values:
             past_key_values_in, past_for_mm = past_key_values, None
         else:
@@ -392,6 +428,93 @@ class MMGPTLlamaForCausalLM(nn.Module, MMGPTMetaForCausalLM):
             out = (logits, cache)
             return (loss,) + out if loss is not None else out
         return CausalLMOutputWithPast(loss=loss, logits=logits, past_key_values=cache, hidden_states=hs,
+                                      attentions=None)
+
+    # ------------------------------------------------------------------ training forward (autograd)
+    def _wants_grad(self, inputs_embeds) -> bool:
+        if inputs_embeds is not None and inputs_embeds.requires_grad:
+            return True
+        return any(p.requires_grad for p in self.parameters())
+
+    def _forward_autograd(self, input_ids, attention_mask, inputs_embeds, labels, images, output_hidden_states,
+                          return_dict):
+        """forward() with gradients: the same kernels as the inference path, sequenced through the
+        torch.autograd.Functions of merlin_b200/autograd.py (one Function per decoder layer, per tower, per
+        projector, for the splice and for lm_head + CE), so `out.loss.backward()` fills `param.grad` — the contract
+        of HF Trainer.training_step over the reference model (mmgpt/engine/train/train.py:49-59).  With
+        `gradient_checkpointing_enable()` every decoder layer keeps only its input and is re-run in backward
+        (the reference trains with --gradient_checkpointing True, pretrain.sh:35)."""
+        from .... import autograd as A
+        m, cfg = self.model, self.config
+        device = self.device
+        D, H, FF = cfg.hidden_size, cfg.num_attention_heads, cfg.intermediate_size
+        tower, proj = getattr(m, "vision_tower", None), getattr(m, "projector", None)
+        if inputs_embeds is None:
+            ids_dev = input_ids.to(device).contiguous()
+            B, S = ids_dev.shape
+            feats = feat_offset = feat_limit = None
+            if tower is not None and images is not None and S != 1:
+                if len(images) < B:
+                    raise ValueError(f"images has {len(images)} entries for a batch of {B} samples")
+                concat = torch.cat([im for im in images], dim=0)
+                n_img = concat.shape[0]
+                tower_params = [p for _, p in tower.named_parameters_reference()]
+                if tower_params:
+                    hidden_v = A.VisionTowerFn.apply(tower, concat, *tower_params)
+                else:
+                    with torch.no_grad():
+                        hidden_v = tower.encode(concat)
+                grid = tower.config.image_size // tower.config.patch_size
+                if hasattr(proj, "project") and tower.select_feature == "patch":
+                    feats = A.ConvProjectorFn.apply(hidden_v, proj.weight, proj.bias, n_img, grid, proj.in_channels,
+                                                    proj.conv_stride, tower.tokens, 1)
+                else:
+                    rows = tower.feature_select(hidden_v, n_img).reshape(-1, hidden_v.shape[-1])
+                    feats = A.LinearFn.apply(rows, proj.weight, proj.bias)
+                feats = feats.reshape(-1, feats.shape[-1])
+                per_image = feats.shape[0] // n_img
+                ids_host = input_ids if not input_ids.is_cuda else input_ids.cpu()
+                self._validate_image_grammar(ids_host, images, per_image)
+                rows_per_sample = [im.shape[0] * per_image for im in images][:B]
+                offs = [sum(rows_per_sample[:b]) for b in range(B)]
+                feat_offset = torch.tensor(offs, dtype=torch.int32).to(device)
+                feat_limit = torch.tensor(rows_per_sample, dtype=torch.int32).to(device)
+                if not feats.is_contiguous():
+                    feats = feats.contiguous()
+            x = A.EmbedSpliceFn.apply(m.embed_tokens, feats, ids_dev, self.im_patch_token if feats is not None else -1,
+                                      feat_offset, feat_limit)
+        else:
+            B, S, _ = inputs_embeds.shape
+            x = inputs_embeds.reshape(B * S, D).to(torch.bfloat16)
+        if getattr(self, "use_beam_search", False):
+            raise NotImplementedError("use_beam_search is a generation-time flag (base_mmgpt.py:162-163)")
+        seqlens = None
+        if attention_mask is not None:
+            lens = attention_mask.sum(dim=-1)
+            if bool((lens != S).any()):
+                seqlens = lens.to(device=device, dtype=torch.int32)
+        cos, sin = m.rope_tables(S)
+        recompute = bool(m.gradient_checkpointing and self.training)
+        hs = [x] if output_hidden_states else None
+        for i in range(cfg.num_hidden_layers):
+            x = A.DecoderLayerFn.apply(x, m.qkv_w[i], m.o_w[i], m.gate_up_w[i], m.down_w[i], m.ln1_w[i], m.ln2_w[i],
+                                       cos, sin, seqlens, B, S, H, FF, cfg.rms_norm_eps, recompute)
+            if output_hidden_states:
+                hs.append(x)
+        hn = A.RMSNormFn.apply(x, m.norm_w, cfg.rms_norm_eps)
+        loss = None
+        if labels is not None:
+            lab = labels.to(device).contiguous()
+            logits2d, loss = A.LMHeadCEFn.apply(hn, self.lm_head_w, lab, B, S, IGNORE_INDEX)
+        else:
+            logits2d = A.LinearFn.apply(hn, self.lm_head_w, None)
+        logits = logits2d.view(B, S, -1) if logits2d.is_contiguous() else logits2d.unflatten(0, (B, S))
+        hidden_states = None
+        if output_hidden_states:
+            hidden_states = tuple(h.view(B, S, D) for h in hs[:-1]) + (hn.view(B, S, D),)
+        if not return_dict:
+            return (loss, logits, None) if loss is not None else (logits, None)
+        return CausalLMOutputWithPast(loss=loss, logits=logits, past_key_values=None, hidden_states=hidden_states,
                                       attentions=None)
 
     def named_parameters_reference(self, trainable_only: bool = True):
@@ -446,9 +569,13 @@ class MMGPTLlamaForCausalLM(nn.Module, MMGPTMetaForCausalLM):
     # ------------------------------------------------------------------ generation (llama_mmgpt.py:114-134)
     def prepare_inputs_for_generation(self, input_ids, past_key_values=None, attention_mask=None,
                                       inputs_embeds=None, **kwargs):
-        if past_key_values:
+        # "is there a past" by LENGTH: an empty HF DynamicCache is truthy (SURVEY.md §0 fact 9 — the reference's
+        # `if past_key_values:` at llama_mmgpt.py:117 slices the PROMPT to one token under transformers 5.x)
+        has_past = past_key_values is not None and (
+            past_key_values.get_seq_length() > 0 if hasattr(past_key_values, "get_seq_length") else bool(past_key_values))
+        if has_past:
             input_ids = input_ids[:, -1:]
-        if inputs_embeds is not None and not past_key_values:
+        if inputs_embeds is not None and not has_past:
             model_inputs = {"inputs_embeds": inputs_embeds}
         else:
             model_inputs = {"input_ids": input_ids}
@@ -515,38 +642,114 @@ class MMGPTLlamaForCausalLM(nn.Module, MMGPTMetaForCausalLM):
             res = bs.step(logits)
         return bs.finalize().to(device)
 
+    # generation keywords understood natively (HF names); anything else must go through use_hf_loop=True
+    _GEN_KEYS = ("max_new_tokens", "max_length", "min_new_tokens", "do_sample", "temperature", "top_p", "top_k",
+                 "num_beams", "eos_token_id", "pad_token_id", "bos_token_id", "length_penalty", "early_stopping",
+                 "repetition_penalty", "num_return_sequences", "return_dict_in_generate", "output_scores", "use_cache")
+
+    def _generation_settings(self, generation_config, kwargs):
+        """HF semantics: self.generation_config, overridden by a passed GenerationConfig, overridden by keywords."""
+        import copy
+        gc = copy.deepcopy(generation_config if generation_config is not None else self.generation_config)
+        explicit = {k: kwargs.pop(k) for k in list(kwargs) if k in self._GEN_KEYS}
+        for k, v in explicit.items():
+            setattr(gc, k, v)
+        return gc, explicit
+
     @torch.no_grad()
-    def generate(self, input_ids: torch.LongTensor, images: Optional[List[torch.Tensor]] = None,
-                 max_new_tokens: int = 1024, do_sample: bool = False, temperature: float = 1.0,
-                 top_p: float = 1.0, num_beams: int = 1, eos_token_id: Optional[int] = 2,
-                 stopping_criteria=None, attention_mask=None, use_cache: bool = True, streamer=None,
-                 generator: Optional[torch.Generator] = None, **kw):
-        """Greedy decoding, temperature / top-p sampling or beam search (num_beams > 1; extra keywords
-        length_penalty, early_stopping as in HF) with a KV cache.  Step 0 is the full multimodal prefill,
-        later steps feed one token and skip the vision path.  Returns [1, S + new] ids."""
+    def generate(self, inputs: Optional[torch.LongTensor] = None, generation_config=None, logits_processor=None,
+                 stopping_criteria=None, *, images: Optional[List[torch.Tensor]] = None, input_ids=None,
+                 attention_mask=None, streamer=None, generator: Optional[torch.Generator] = None,
+                 use_hf_loop: bool = False, **kwargs):
+        """`generate(input_ids, images=[...], **hf_generation_kwargs)` — the call of eval_mmvet.py:101-120,
+        eval_box.py:245-264, model_worker.py:169-180.  Greedy decoding, temperature / top-k / top-p sampling with
+        repetition penalty and custom logits processors, and beam search (num_beams > 1, length_penalty,
+        early_stopping) run on the library's KV-cache decode kernels: step 0 is the full multimodal prefill, later
+        steps feed one token and skip the vision path.  Returns [1, S + new] ids, or a
+        GenerateDecoderOnlyOutput with return_dict_in_generate=True.  Unknown keywords raise (nothing is silently
+        swallowed); `use_hf_loop=True` runs HF's own GenerationMixin loop over this model's forward instead
+        (every HF decoding mode at batch 1, without the CUDA-graph decode loop).  Calls are serialised per model
+        by a lock: the serve worker runs generate() from background threads (model_worker.py:169-180)."""
+        if inputs is None:
+            inputs = input_ids
+        if inputs is None:
+            raise ValueError("generate() needs input_ids")
+        if use_hf_loop:
+            extra = {k: v for k, v in (("attention_mask", attention_mask), ("streamer", streamer)) if v is not None}
+            with self._generate_lock():
+                return GenerationMixin.generate(self, inputs, generation_config=generation_config,
+                                                logits_processor=logits_processor, stopping_criteria=stopping_criteria,
+                                                images=images, **extra, **kwargs)
+        length_norm = kwargs.pop("length_norm", "total")
+        gc, explicit = self._generation_settings(generation_config, kwargs)
+        if kwargs:
+            raise ValueError(f"generate(): unsupported keyword arguments {sorted(kwargs)}; pass use_hf_loop=True to run "
+                             "HF's GenerationMixin loop over this model")
+        input_ids = inputs
         if input_ids.shape[0] != 1:
             raise NotImplementedError("generate() handles one sequence at a time (reference eval scripts)")
+        if (gc.num_return_sequences or 1) != 1:
+            raise NotImplementedError("num_return_sequences > 1: use use_hf_loop=True")
+        S = input_ids.shape[1]
+        if "max_new_tokens" in explicit or gc.max_new_tokens is not None:
+            max_new_tokens = int(gc.max_new_tokens)
+        elif "max_length" in explicit:
+            max_new_tokens = max(int(gc.max_length) - S, 0)
+        else:
+            max_new_tokens = 1024                     # the reference's eval / serve default
+        eos = gc.eos_token_id if "eos_token_id" in explicit or gc.eos_token_id is not None else 2
+        eos_token_id = eos[0] if isinstance(eos, (list, tuple)) and len(eos) == 1 else eos
+        if isinstance(eos_token_id, (list, tuple)):
+            raise NotImplementedError("several eos ids: use use_hf_loop=True")
+        do_sample, temperature = bool(gc.do_sample), float(gc.temperature if gc.temperature is not None else 1.0)
+        top_p = float(gc.top_p if gc.top_p is not None else 1.0)
+        top_k = int(gc.top_k or 0)
+        rep = float(gc.repetition_penalty or 1.0)
+        min_new = int(gc.min_new_tokens or 0)
+        num_beams = int(gc.num_beams or 1)
+        if attention_mask is not None and not bool(attention_mask.bool().all()):
+            raise NotImplementedError("generate() takes an unpadded prompt (attention_mask of ones)")
+        with self._generate_lock():
+            ids = self._generate_locked(input_ids, images, max_new_tokens, do_sample, temperature, top_p, top_k, rep,
+                                        min_new, num_beams, eos_token_id, stopping_criteria, logits_processor, streamer,
+                                        generator, gc, length_norm)
+        if gc.return_dict_in_generate:
+            from transformers.generation.utils import GenerateDecoderOnlyOutput
+            return GenerateDecoderOnlyOutput(sequences=ids)
+        return ids
+
+    def _generate_lock(self):
+        import threading
+        lock = self.__dict__.get("_gen_lock")
+        if lock is None:
+            lock = self.__dict__.setdefault("_gen_lock", threading.RLock())
+        return lock
+
+    def _generate_locked(self, input_ids, images, max_new_tokens, do_sample, temperature, top_p, top_k, rep, min_new,
+                         num_beams, eos_token_id, stopping_criteria, logits_processor, streamer, generator, gc,
+                         length_norm):
         device = self.device
         if num_beams != 1:
             if do_sample or streamer is not None:
                 raise NotImplementedError("beam search runs without sampling and without a streamer")
             return self._generate_beam(input_ids, images, num_beams, max_new_tokens, eos_token_id,
-                                       stopping_criteria, float(kw.get("length_penalty", 1.0)),
-                                       kw.get("early_stopping", False), kw.get("length_norm", "generated"))
-        fast = (not do_sample and stopping_criteria is None and streamer is None and max_new_tokens > 0
-                and attention_mask is None and images is not None and len(images) == 1
+                                       stopping_criteria, float(gc.length_penalty if gc.length_penalty is not None else 1.0),
+                                       gc.early_stopping or False, length_norm)
+        plain = (not do_sample and not stopping_criteria and not logits_processor and streamer is None
+                 and rep == 1.0 and min_new == 0 and max_new_tokens > 0)
+        fast = (plain and images is not None and len(images) == 1
                 and getattr(self, "use_cuda_graphs", True) and not getattr(self, "use_beam_search", False)
                 and getattr(self.model, "vision_tower", None) is not None)
         if fast:
-            # whole step from CUDA graphs: 1 replay for the multimodal prefill, 1 per decoded token
+            # device-resident loop: prefill launches (a CUDA graph once the shape repeats) + 1 graph replay per token
             return _decode.graphed_generate(self, input_ids, images[0], max_new_tokens, eos_token_id)
         ids = input_ids.to(device)
         self._cache_capacity = ids.shape[1] + max_new_tokens + 8
-        inputs = self.prepare_inputs_for_generation(ids, None, attention_mask, use_cache=True, images=images)
+        inputs = self.prepare_inputs_for_generation(ids, None, None, use_cache=True, images=images)
         out = self.forward(**inputs)
         cache = out.past_key_values
         last = out.logits[:, -1, :]
-        if not do_sample and stopping_criteria is None and streamer is None and max_new_tokens > 0:
+        if plain:
             # device-resident greedy loop: one CUDA-graph replay per token, no host round trips
             first = ops.argmax(last).view(1, 1)
             ids = torch.cat([ids, first], dim=1)
@@ -554,20 +757,28 @@ class MMGPTLlamaForCausalLM(nn.Module, MMGPTMetaForCausalLM):
                 more = self._get_decoder(cache).greedy(first, max_new_tokens - 1, eos_token_id)
                 ids = torch.cat([ids, more.view(1, -1)], dim=1)
             return ids
-        new_tokens = []
         for step in range(max_new_tokens):
+            scores = last.float()
+            if rep != 1.0:                                   # HF RepetitionPenaltyLogitsProcessor
+                seen = scores.gather(1, ids)
+                scores = scores.scatter(1, ids, torch.where(seen < 0, seen * rep, seen / rep))
+            if min_new and step < min_new and eos_token_id is not None:   # MinNewTokensLengthLogitsProcessor
+                scores[:, eos_token_id] = float("-inf")
+            for proc in (logits_processor or ()):
+                scores = proc(ids, scores)
             if do_sample and temperature > 0:
-                probs = sampling_distribution(last, temperature, top_p)
+                probs = sampling_distribution(scores, temperature, top_p, top_k)
                 nxt = torch.multinomial(probs, 1, generator=generator)
-            else:
+            elif scores is last or not (rep != 1.0 or min_new or logits_processor):
                 nxt = ops.argmax(last).view(1, 1)
-            new_tokens.append(nxt)
+            else:
+                nxt = scores.argmax(dim=-1, keepdim=True)
             ids = torch.cat([ids, nxt], dim=1)
             if streamer is not None:
                 streamer.put(nxt.cpu())
             if eos_token_id is not None and int(nxt) == eos_token_id:
                 break
-            if stopping_criteria is not None and any(c(ids, last) for c in stopping_criteria):
+            if stopping_criteria is not None and any(bool(torch.as_tensor(c(ids, last)).all()) for c in stopping_criteria):
                 break
             if step + 1 == max_new_tokens:
                 break
@@ -579,12 +790,16 @@ class MMGPTLlamaForCausalLM(nn.Module, MMGPTMetaForCausalLM):
         return ids
 
 
-def sampling_distribution(logits: torch.Tensor, temperature: float = 1.0, top_p: float = 1.0) -> torch.Tensor:
+def sampling_distribution(logits: torch.Tensor, temperature: float = 1.0, top_p: float = 1.0,
+                          top_k: int = 0) -> torch.Tensor:
     """Next-token distribution of HF sampling (`generate(do_sample=True, temperature, top_p)`, the call of
-    model_worker.py:169-176 / eval_box.py:256-263): logits / temperature (TemperatureLogitsWarper), then nucleus
-    filtering — sort ascending, drop every token whose cumulative probability is <= 1 - top_p, always keep the
-    most likely one (TopPLogitsWarper, min_tokens_to_keep=1) — then softmax."""
+    model_worker.py:169-176 / eval_box.py:256-263): logits / temperature (TemperatureLogitsWarper), top-k
+    (TopKLogitsWarper), then nucleus filtering — sort ascending, drop every token whose cumulative probability is
+    <= 1 - top_p, always keep the most likely one (TopPLogitsWarper, min_tokens_to_keep=1) — then softmax."""
     scores = logits.float() / temperature
+    if top_k and top_k < scores.shape[-1]:
+        kth = scores.topk(top_k, dim=-1).values[..., -1:]
+        scores = scores.masked_fill(scores < kth, float("-inf"))
     if top_p < 1.0:
         sorted_logits, sorted_idx = torch.sort(scores, descending=False, dim=-1)
         cum = sorted_logits.softmax(dim=-1).cumsum(dim=-1)
@@ -595,3 +810,8 @@ def sampling_distribution(logits: torch.Tensor, temperature: float = 1.0, top_p:
 
 
 MerlinForCausalLM = MMGPTLlamaForCausalLM  # the name BASELINE.json's north_star uses
+
+# llama_mmgpt.py:137-138.  exist_ok: the reference's own module registers the same model_type when both are
+# imported into one process (the parity tests do that).
+AutoConfig.register("mmgpt", MMGPTConfig, exist_ok=True)
+AutoModelForCausalLM.register(MMGPTConfig, MMGPTLlamaForCausalLM, exist_ok=True)

@@ -89,9 +89,21 @@ class CLIPVisionTower(nn.Module):
         self.fc1_b = nn.ParameterList([P(ff) for _ in range(L)])
         self.fc2_w = nn.ParameterList([P(d, ff) for _ in range(L)])
         self.fc2_b = nn.ParameterList([P(d) for _ in range(L)])
+        # clip_encoder.py:21-24: CLIPVisionModel.from_pretrained(args.vision_tower) FIRST, then the
+        # `model.vision_tower.*` slice of the mmgpt checkpoint overlays it.  The parameters above start at zero, so
+        # a tower that found neither source is useless (constant features, zero gradients): say so loudly.
+        self.weight_sources: List[str] = []
+        if self._load_clip_checkpoint(self.vision_tower_name):
+            self.weight_sources.append(f"clip:{self.vision_tower_name}")
         model_path = getattr(args, "model_name_or_path", None)
-        if model_path:
-            self.load_weights(model_path)
+        if model_path and self.load_weights(model_path):
+            self.weight_sources.append(f"mmgpt:{model_path}")
+        if not self.weight_sources:
+            import warnings
+            warnings.warn(f"CLIPVisionTower: no pretrained weights found (vision_tower={self.vision_tower_name!r} is not "
+                          f"a local CLIP checkpoint directory and model_name_or_path={model_path!r} holds no "
+                          "'model.vision_tower.*' keys): every tower parameter is ZERO until load_state_dict() is "
+                          "called", RuntimeWarning, stacklevel=2)
 
     # ------------------------------------------------------------------ reference-format state dict
     def _build_image_processor(self):
@@ -181,6 +193,44 @@ class CLIPVisionTower(nn.Module):
             weights = {k[len(prefix):]: v for k, v in ckpt.items() if "vision_tower" in k}
         if weights:
             self.load_state_dict(weights, strict=True)
+        return bool(weights)
+
+    def _load_clip_checkpoint(self, name_or_path) -> bool:
+        """`CLIPVisionModel.from_pretrained(vision_tower)` (clip_encoder.py:22) for a LOCAL checkpoint directory
+        (there is no hub access): reads pytorch_model.bin / model.safetensors (sharded or not) of a CLIPVisionModel
+        or a full CLIPModel, keeps the `vision_model.*` keys and loads them (q/k/v fused into qkv_w, the patch
+        convolution flattened into patch_weight by load_state_dict's reference-layout views).  A position table of
+        another resolution is interpolated (interpolate_model.py:11-28)."""
+        if not name_or_path or not os.path.isdir(str(name_or_path)):
+            return False
+        path = str(name_or_path)
+        sd = {}
+        files = sorted(os.listdir(path))
+        for idx in ("pytorch_model.bin.index.json", "model.safetensors.index.json"):
+            if idx in files:
+                files = sorted(set(json.load(open(os.path.join(path, idx)))["weight_map"].values()))
+                break
+        for f in files:
+            full = os.path.join(path, f)
+            if f.endswith(".safetensors"):
+                from safetensors.torch import load_file
+                sd.update(load_file(full))
+            elif f.endswith(".bin") and f.startswith("pytorch_model"):
+                sd.update(torch.load(full, map_location="cpu"))
+        own = self.state_dict(keep_vars=True)
+        picked = {}
+        for k, v in sd.items():
+            if k.startswith("vision_model."):
+                k = "vision_tower." + k
+            if k in own:
+                picked[k] = v
+        if not picked:
+            return False
+        missing = [k for k in own if k not in picked]
+        if missing:
+            raise RuntimeError(f"CLIP checkpoint {path} lacks {len(missing)} tower tensors, e.g. {missing[:3]}")
+        self.load_state_dict(picked, strict=True, interpolate=True)
+        return True
 
     # ------------------------------------------------------------------------------ forward
     def feature_select(self, hidden: torch.Tensor, n_img: int) -> torch.Tensor:
@@ -196,21 +246,53 @@ class CLIPVisionTower(nn.Module):
         L = self._config.num_hidden_layers
         return L + 1 + self.select_layer if self.select_layer < 0 else self.select_layer
 
+    def _c_weights(self):
+        """struct merlin_vit_weights for the layers `select_layer` needs (rebuilt when a parameter moved)."""
+        import ctypes
+        from .... import lib as _lib
+        c = self._config
+        n_run = self.num_layers_to_run()
+        key = tuple(p.data_ptr() for p in (self.class_embedding, self.patch_weight, self.position_embedding,
+                                           self.qkv_w[0], self.fc2_w[n_run - 1] if n_run else self.pre_ln_w)) + (n_run,)
+        cached = self.__dict__.get("_cw")
+        if cached is not None and cached[0] == key:
+            return cached[1]
+        layers = (_lib.VitLayerWeights * max(n_run, 1))()
+        for j in range(n_run):
+            layers[j] = _lib.VitLayerWeights(*[t.data_ptr() for t in (
+                self.qkv_w[j], self.qkv_b[j], self.out_w[j], self.out_b[j], self.ln1_w[j], self.ln1_b[j],
+                self.ln2_w[j], self.ln2_b[j], self.fc1_w[j], self.fc1_b[j], self.fc2_w[j], self.fc2_b[j])])
+        w = _lib.VitWeights(n_run, c.hidden_size, c.num_attention_heads, c.intermediate_size, c.image_size,
+                            c.patch_size, self.k_patch_padded, float(c.layer_norm_eps),
+                            self.class_embedding.data_ptr(), self.patch_weight.data_ptr(),
+                            self.position_embedding.data_ptr(), self.pre_ln_w.data_ptr(), self.pre_ln_b.data_ptr(),
+                            ctypes.cast(layers, ctypes.POINTER(_lib.VitLayerWeights)))
+        self.__dict__["_cw"] = (key, w, layers)
+        return w
+
     def encode(self, pixel_values: torch.Tensor) -> torch.Tensor:
-        """[n,3,H,W] -> selected hidden state [n*T, d] (row-major tokens, CLS first)."""
+        """[n,3,H,W] -> selected hidden state [n*T, d] (row-major tokens, CLS first): ONE library call
+        (merlin_vit_forward) for patch embedding, CLS / position / pre-LN and every encoder layer."""
+        import ctypes
+        from .... import lib as _lib
         c = self._config
         n = pixel_values.shape[0]
         d, H = c.hidden_size, c.num_attention_heads
         px = pixel_values.to(device=self.device, dtype=torch.bfloat16).contiguous()
+        if not ops.PROFILE.enabled:
+            L_ = _lib.load()
+            w = self._c_weights()
+            ws = torch.empty(L_.merlin_vit_workspace_bytes(ctypes.byref(w), n), dtype=torch.uint8, device=px.device)
+            h = torch.empty((n * self.tokens, d), dtype=torch.bfloat16, device=px.device)
+            ops.check(L_.merlin_vit_forward(torch.cuda.current_stream().cuda_stream, ctypes.byref(w), px.data_ptr(), n,
+                                            ws.data_ptr(), h.data_ptr(), ops.DEFAULT_CTA_GROUP), "merlin_vit_forward",
+                      3 + 7 * self.num_layers_to_run())
+            return h
+        # roofline leg of bench.py: per-op launches with a CUDA-event pair around every GEMM
         col = ops.patch_im2col(px, c.patch_size, self.k_patch_padded)
         patch_out = ops.gemm(col, self.patch_weight)
         h = ops.vit_embed_ln(patch_out, self.class_embedding, self.position_embedding, self.pre_ln_w,
                              self.pre_ln_b, n, c.layer_norm_eps)
-        if not ops.PROFILE.enabled:
-            ws = ops.vit_layer_workspace(h.shape[0], d, c.intermediate_size, h.device)
-            for j in range(self.num_layers_to_run()):
-                ops.vit_layer_forward(h, ws, self, j, n)      # merlin_vit_layer_forward: 7 kernels, one call
-            return h
         xn = torch.empty_like(h)
         for j in range(self.num_layers_to_run()):
             ops.layernorm(h, self.ln1_w[j], self.ln1_b[j], c.layer_norm_eps, out=xn)
@@ -245,62 +327,54 @@ class CLIPVisionTower(nn.Module):
         return [(n, p) for n, p in out if p.requires_grad]
 
     def encode_train(self, pixel_values: torch.Tensor):
-        """encode() that keeps what backward needs.  Returns (hidden [n*T, d], saved)."""
-        c = self._config
-        n, H = pixel_values.shape[0], c.num_attention_heads
+        """encode() that keeps what backward needs (merlin_vit_forward_train).  Returns (hidden [n*T, d], saved)."""
+        import ctypes
+        from .... import lib as _lib
+        n = pixel_values.shape[0]
         px = pixel_values.to(device=self.device, dtype=torch.bfloat16).contiguous()
-        col = ops.patch_im2col(px, c.patch_size, self.k_patch_padded)
-        patch_out = ops.gemm(col, self.patch_weight)
-        emb = ops.vit_embed(patch_out, self.class_embedding, self.position_embedding, n)
-        h = ops.layernorm(emb, self.pre_ln_w, self.pre_ln_b, c.layer_norm_eps)
-        layers = []
-        for j in range(self.num_layers_to_run()):
-            xn1 = ops.layernorm(h, self.ln1_w[j], self.ln1_b[j], c.layer_norm_eps)
-            qkv = ops.gemm(xn1, self.qkv_w[j], bias=self.qkv_b[j])
-            att, lse = ops.flash_attn(qkv, n, self.tokens, H, 64, causal=False, return_lse=True)
-            h_mid = ops.gemm(att, self.out_w[j], bias=self.out_b[j], residual=h, epilogue=EPI_RESIDUAL)
-            xn2 = ops.layernorm(h_mid, self.ln2_w[j], self.ln2_b[j], c.layer_norm_eps)
-            pre = ops.gemm(xn2, self.fc1_w[j], bias=self.fc1_b[j])
-            mid = ops.quick_gelu(pre)
-            h_out = ops.gemm(mid, self.fc2_w[j], bias=self.fc2_b[j], residual=h_mid, epilogue=EPI_RESIDUAL)
-            layers.append((h, xn1, qkv, att, lse, h_mid, xn2, pre, mid))
-            h = h_out
-        return h, dict(n=n, col=col, emb=emb, layers=layers)
+        L_ = _lib.load()
+        w = self._c_weights()
+        saved = torch.empty(L_.merlin_vit_saved_bytes(ctypes.byref(w), n), dtype=torch.uint8, device=px.device)
+        h = torch.empty((n * self.tokens, self._config.hidden_size), dtype=torch.bfloat16, device=px.device)
+        ops.check(L_.merlin_vit_forward_train(torch.cuda.current_stream().cuda_stream, ctypes.byref(w), px.data_ptr(), n,
+                                              saved.data_ptr(), h.data_ptr(), ops.DEFAULT_CTA_GROUP),
+                  "merlin_vit_forward_train", 4 + 9 * self.num_layers_to_run())
+        return h, dict(n=n, saved=saved)
 
     def backward(self, dh: torch.Tensor, saved, grad, f32, accumulate: bool, done=None):
-        """dh: gradient w.r.t. encode_train()'s hidden.  grad(name) -> bf16 arena view for weight matrices,
-        f32[name] -> fp32 accumulator for biases / norm weights / position + class embeddings."""
-        c = self._config
-        n, H, eps = saved["n"], c.num_attention_heads, c.layer_norm_eps
-        for j in reversed(range(self.num_layers_to_run())):
-            h, xn1, qkv, att, lse, h_mid, xn2, pre, mid = saved["layers"][j]
+        """dh: gradient w.r.t. encode_train()'s hidden (overwritten).  grad(name) -> bf16 gradient tensor of a
+        weight matrix, f32[name] -> fp32 accumulator for biases / norm weights / position + class embeddings.
+        ONE library call (merlin_vit_backward) walks the layers last-to-first."""
+        import ctypes
+        from .... import lib as _lib
+        n, n_run = saved["n"], self.num_layers_to_run()
+        L_ = _lib.load()
+        w = self._c_weights()
+        lg = (_lib.VitLayerGrads * max(n_run, 1))()
+        for j in range(n_run):
             p = self.VM + f"encoder.layers.{j}."
-            dmid = ops.gemm_nt(dh, self.fc2_w[j])
-            ops.gemm_tn(dh, mid, out=grad(p + "mlp.fc2.weight"), accumulate=accumulate)
-            ops.colsum_accumulate(dh, f32[p + "mlp.fc2.bias"])
-            dpre = ops.quick_gelu(pre, dy=dmid.contiguous())
-            ops.gemm_tn(dpre, xn2, out=grad(p + "mlp.fc1.weight"), accumulate=accumulate)
-            ops.colsum_accumulate(dpre, f32[p + "mlp.fc1.bias"])
-            dxn2 = ops.gemm_nt(dpre, self.fc1_w[j])
-            dh_mid = ops.layernorm_bwd(h_mid, self.ln2_w[j], dxn2, dh, f32[p + "layer_norm2.weight"],
-                                       f32[p + "layer_norm2.bias"], eps)
-            datt = ops.gemm_nt(dh_mid, self.out_w[j])
-            ops.gemm_tn(dh_mid, att, out=grad(p + "self_attn.out_proj.weight"), accumulate=accumulate)
-            ops.colsum_accumulate(dh_mid, f32[p + "self_attn.out_proj.bias"])
-            dqkv = ops.flash_attn_bwd(qkv, att, datt, lse, n, self.tokens, H, 64, causal=False)
-            ops.gemm_tn(dqkv, xn1, out=grad(p + "self_attn.qkv_proj.weight"), accumulate=accumulate)
-            ops.colsum_accumulate(dqkv, f32[p + "self_attn.qkv_proj.bias"])
-            dxn1 = ops.gemm_nt(dqkv, self.qkv_w[j])
-            dh = ops.layernorm_bwd(h, self.ln1_w[j], dxn1, dh_mid, f32[p + "layer_norm1.weight"],
-                                   f32[p + "layer_norm1.bias"], eps)
-            saved["layers"][j] = None
-            if done is not None:
-                done(p + "layer_norm1.bias")
-        demb = ops.layernorm_bwd(saved["emb"], self.pre_ln_w, dh, None, f32[self.VM + "pre_layrnorm.weight"],
-                                 f32[self.VM + "pre_layrnorm.bias"], eps)
-        dpatch = ops.vit_embed_bwd(demb, f32[self.VM + "embeddings.position_embedding.weight"].view(self.tokens, -1),
-                                   f32[self.VM + "embeddings.class_embedding"], n)
-        ops.gemm_tn(dpatch, saved["col"], out=grad(self.VM + "embeddings.patch_embedding.weight"), accumulate=accumulate)
+            lg[j] = _lib.VitLayerGrads(
+                grad(p + "self_attn.qkv_proj.weight").data_ptr(), grad(p + "self_attn.out_proj.weight").data_ptr(),
+                grad(p + "mlp.fc1.weight").data_ptr(), grad(p + "mlp.fc2.weight").data_ptr(),
+                f32[p + "self_attn.qkv_proj.bias"].data_ptr(), f32[p + "self_attn.out_proj.bias"].data_ptr(),
+                f32[p + "layer_norm1.weight"].data_ptr(), f32[p + "layer_norm1.bias"].data_ptr(),
+                f32[p + "layer_norm2.weight"].data_ptr(), f32[p + "layer_norm2.bias"].data_ptr(),
+                f32[p + "mlp.fc1.bias"].data_ptr(), f32[p + "mlp.fc2.bias"].data_ptr())
+        g = _lib.VitGrads(grad(self.VM + "embeddings.patch_embedding.weight").data_ptr(),
+                          f32[self.VM + "embeddings.position_embedding.weight"].data_ptr(),
+                          f32[self.VM + "embeddings.class_embedding"].data_ptr(),
+                          f32[self.VM + "pre_layrnorm.weight"].data_ptr(), f32[self.VM + "pre_layrnorm.bias"].data_ptr(),
+                          ctypes.cast(lg, ctypes.POINTER(_lib.VitLayerGrads)))
+        ws = torch.empty(L_.merlin_vit_backward_workspace_bytes(ctypes.byref(w), n), dtype=torch.uint8, device=dh.device)
+        if not dh.is_contiguous():
+            raise ValueError("CLIPVisionTower.backward: dh must be contiguous")
+        ops.check(L_.merlin_vit_backward(torch.cuda.current_stream().cuda_stream, ctypes.byref(w), ctypes.byref(g),
+                                         saved["saved"].data_ptr(), dh.data_ptr(), ws.data_ptr(), n,
+                                         int(bool(accumulate)), ops.DEFAULT_CTA_GROUP), "merlin_vit_backward",
+                  3 + 20 * n_run)
+        saved["saved"] = None
+        if done is not None:
+            done(self.VM + "embeddings.patch_embedding.weight")
 
     def forward(self, images: List[torch.Tensor]):
         with torch.set_grad_enabled(False):  # forward-only kernels; training path: see engine/train

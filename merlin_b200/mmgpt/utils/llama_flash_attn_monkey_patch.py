@@ -38,8 +38,15 @@ def merlin_attention_forward(module, query: torch.Tensor, key: torch.Tensor, val
         seqlens = attention_mask.sum(-1).to(torch.int32)
     # pack to the [B*S, 3*H*hd] layout the kernel reads through one TMA tensor map
     qkv = torch.stack((query, key, value), dim=1).permute(0, 3, 1, 2, 4).reshape(B * S, 3 * H * hd)
-    out = ops.flash_attn(qkv.contiguous(), B, S, H, hd, causal=True, seqlens=seqlens,
-                         softmax_scale=float(scaling) if scaling else 0.0)
+    scale = float(scaling) if scaling else 0.0
+    if torch.is_grad_enabled() and qkv.requires_grad:
+        # training through the seam (train_flash_attn.py:6-8 exists to TRAIN with the patched attention):
+        # merlin_flash_attn_fwd saves the log-sum-exp, merlin_flash_attn_bwd returns the packed dq|dk|dv and
+        # autograd carries it back through the stack / permute into HF's q, k, v projections
+        from ...autograd import FlashAttnFn
+        out = FlashAttnFn.apply(qkv, seqlens, B, S, H, hd, True, scale)
+    else:
+        out = ops.flash_attn(qkv.contiguous(), B, S, H, hd, causal=True, seqlens=seqlens, softmax_scale=scale)
     return out.view(B, S, H, hd), None
 
 

@@ -51,6 +51,9 @@ def build_product_model(cfg: O.OracleConfig, sd, device="cuda", max_position_emb
     if device is not None:
         model.to(device=device, dtype=torch.bfloat16)
     model.eval()
+    # inference by default: with trainable parameters and grad mode on, forward() takes the autograd path (like any
+    # HF model); the training tests switch requires_grad on for what they train
+    model.requires_grad_(False)
     return model
 
 

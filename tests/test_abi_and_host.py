@@ -99,6 +99,10 @@ def test_grammar_validation_matches_reference_errors():
     bad[0, -2] = cfg.im_start_token                             # unmatched <im_start>
     with pytest.raises(ValueError):
         model._validate_image_grammar(bad, g["images"], P)
+    bad = ids.clone()
+    bad[0, -3] = cfg.im_patch_token                             # stray <im_patch> outside any image block
+    with pytest.raises(ValueError, match="may only appear between"):
+        model._validate_image_grammar(bad, g["images"], P)
     model.use_im_start_end = False
     with pytest.raises(NotImplementedError):
         model._validate_image_grammar(ids, g["images"], P)
@@ -173,3 +177,47 @@ def test_build_model_tokenizer_from_checkpoint(tmp_path):
     assert torch.allclose(e[-1], e[:-2].mean(0), atol=1e-2)
     with pytest.raises(NotImplementedError):
         build_model_tokenizer(SimpleNamespace(**{**margs.__dict__, "model_name_or_path": "x/baichuan-7b"}), dargs, targs)
+
+
+def test_clip_tower_loads_pretrained_clip_then_overlays_the_mmgpt_slice(tmp_path):
+    """clip_encoder.py:21-24: CLIPVisionModel.from_pretrained(args.vision_tower) first, then the
+    `model.vision_tower.*` keys of model_name_or_path on top; a tower with neither source warns (its parameters are
+    all zero)."""
+    import json
+    from types import SimpleNamespace
+    from transformers import CLIPVisionConfig, CLIPVisionModel
+    from merlin_b200.mmgpt.model.vision_encoder.clip_encoder import CLIPVisionTower
+    vcfg = CLIPVisionConfig(hidden_size=128, intermediate_size=256, num_hidden_layers=3, num_attention_heads=2,
+                            image_size=56, patch_size=14, hidden_act="quick_gelu")
+    torch.manual_seed(0)
+    hf = CLIPVisionModel(vcfg)
+    clip_dir = tmp_path / "clip-vit-tiny"
+    hf.save_pretrained(str(clip_dir))
+    assert ((clip_dir / "model.safetensors").exists() or (clip_dir / "pytorch_model.bin").exists()) \
+        and (clip_dir / "config.json").exists()
+    args = SimpleNamespace(vision_tower=str(clip_dir), vision_select_layer=-2, vision_select_feature="patch",
+                           freeze_vision_tower=True, conv_stride=2, model_name_or_path=None)
+    tower = CLIPVisionTower(args)
+    assert tower.weight_sources == [f"clip:{clip_dir}"] and tower.config.hidden_size == 128
+    want = {"vision_tower." + k: v for k, v in hf.state_dict().items() if "position_ids" not in k}
+    got = tower.state_dict()
+    assert set(got) == set(want) and all(torch.equal(got[k], want[k]) for k in want)
+    assert float(tower.qkv_w[0].abs().sum()) > 0 and float(tower.ln1_w[0].abs().sum()) > 0
+    # overlay: an mmgpt checkpoint whose tower slice differs wins over the CLIP weights
+    ck = tmp_path / "mmgpt-ckpt"
+    ck.mkdir()
+    over = {"model.vision_tower." + k: v + 1.0 for k, v in want.items()}
+    over["model.layers.0.mlp.down_proj.weight"] = torch.zeros(2, 2)
+    torch.save(over, ck / "pytorch_model.bin")
+    args.model_name_or_path = str(ck)
+    tower2 = CLIPVisionTower(args)
+    assert tower2.weight_sources == [f"clip:{clip_dir}", f"mmgpt:{ck}"]
+    assert all(torch.equal(tower2.state_dict()[k], want[k] + 1.0) for k in want)
+    # neither source: loud warning, zero parameters
+    args2 = SimpleNamespace(vision_tower="clip-does-not-exist", vision_select_layer=-2, vision_select_feature="patch",
+                            freeze_vision_tower=True, conv_stride=2, model_name_or_path=None)
+    with pytest.warns(RuntimeWarning, match="no pretrained weights"):
+        empty = CLIPVisionTower(args2, config=SimpleNamespace(
+            hidden_size=128, intermediate_size=256, num_hidden_layers=3, num_attention_heads=2, image_size=56,
+            patch_size=14, hidden_act="quick_gelu", layer_norm_eps=1e-5, num_channels=3))
+    assert empty.weight_sources == [] and float(empty.qkv_w[0].abs().sum()) == 0

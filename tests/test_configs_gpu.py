@@ -18,7 +18,7 @@ DEV = "cuda"
 def _decoder_only(cfg_fn, **kw):
     from merlin_b200.mmgpt.model.mmgpt.llama_mmgpt import MMGPTLlamaForCausalLM
     torch.manual_seed(0)
-    return MMGPTLlamaForCausalLM(cfg_fn(**kw)).to(device=DEV, dtype=torch.bfloat16)
+    return MMGPTLlamaForCausalLM(cfg_fn(**kw)).to(device=DEV, dtype=torch.bfloat16).requires_grad_(False)
 
 
 def _fp32_logits(model, ids, ocfg):

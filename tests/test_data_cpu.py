@@ -264,3 +264,61 @@ def test_build_dataloader_contract(tmp_path):
         build_dataloader(tok, types.SimpleNamespace(interpair_webdatasets=str(shard), **dict(base, image_aspect_ratio="keep")))
     with pytest.raises(ValueError):
         build_dataloader(tok, types.SimpleNamespace(interpair_webdatasets="", **base))
+
+
+def _write_text_shards(tmp_path, n_shards=8, per_shard=5):
+    paths = []
+    for s in range(n_shards):
+        p = tmp_path / f"s-{s:03d}.tar"
+        with tarfile.open(p, "w") as tf:
+            for r in range(per_shard):
+                data = json.dumps(dict(prompt=None, txt=f"rec {s} {r}", image_name_list=[], uid=s * 100 + r)).encode()
+                ti = tarfile.TarInfo(f"r{s}_{r}.json")
+                ti.size = len(data)
+                tf.addfile(ti, io.BytesIO(data))
+        paths.append(str(p))
+    return paths
+
+
+def test_interpair_dataset_shards_by_rank_and_worker_and_shuffles_with_fixed_seeds(tmp_path, monkeypatch):
+    """The reference pipeline (interpair_webdataset.py:30-41): InfiniteShardList(seed 3407) -> shuffle(world_size) ->
+    split_by_node -> split_by_worker -> tarfile_to_samples -> shuffle(1000, seed 42).  Under data parallelism every
+    rank (and every DataLoader worker) must read DIFFERENT shards; same seeds -> same order on every run."""
+    from merlin_b200.mmgpt.data.dataset.interpair_webdataset import InterPairWebDataset, shuffle_buffer
+    import random
+    shards = _write_text_shards(tmp_path)
+    cfg = dict(image_token_len=4, use_im_start_end=True, image_size=8, image_processor=None)
+
+    def first_uids(n, **kw):
+        ds = InterPairWebDataset(shards, _Tok(), cfg, data_size=40, **kw)
+        it = ds.inner_iter
+        return [next(it)["json"]["uid"] for _ in range(n)]
+
+    # one epoch = 40 records over 8 shards; with 2 ranks each rank owns 4 shards per epoch
+    r0 = first_uids(20, rank=0, world_size=2, shuffle=False)
+    r1 = first_uids(20, rank=1, world_size=2, shuffle=False)
+    assert not set(r0) & set(r1) and len(set(r0) | set(r1)) == 40          # disjoint, together the whole epoch
+    assert {u // 100 for u in r0} == {0, 2, 4, 6} and {u // 100 for u in r1} == {1, 3, 5, 7}
+    # torchrun environment is picked up when rank / world_size are not given
+    monkeypatch.setenv("RANK", "1")
+    monkeypatch.setenv("WORLD_SIZE", "2")
+    assert first_uids(20, shuffle=False) == r1
+    monkeypatch.delenv("RANK")
+    monkeypatch.delenv("WORLD_SIZE")
+    # DataLoader workers split the rank's shards again (split_by_worker)
+    import torch.utils.data as tud
+    seen = {}
+    for wid in range(2):
+        monkeypatch.setattr(tud, "get_worker_info", lambda wid=wid: types.SimpleNamespace(id=wid, num_workers=2))
+        seen[wid] = first_uids(10, rank=0, world_size=2, shuffle=False)
+    monkeypatch.undo()
+    assert not set(seen[0]) & set(seen[1]) and set(seen[0]) | set(seen[1]) == set(r0)
+    # shuffled: deterministic across runs, a permutation that differs from file order, ranks still disjoint per epoch
+    a, b = first_uids(60, rank=0, world_size=1), first_uids(60, rank=0, world_size=1)
+    assert a == b and a[:40] != sorted(a[:40])
+    s0 = {u // 100 for u in first_uids(2000, rank=0, world_size=2)}
+    assert len(s0) == 8                                                     # over several epochs a rank sees every shard
+    # the shuffle filter itself: a permutation of a finite stream, bounded look-ahead
+    out = list(shuffle_buffer(iter(range(50)), 8, random.Random(42)))
+    assert sorted(out) == list(range(50)) and out != list(range(50))
+    assert all(x <= i + 8 for i, x in enumerate(out))

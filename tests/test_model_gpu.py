@@ -130,6 +130,7 @@ def test_full_width_single_layer_properties():
     from merlin_b200.mmgpt.model.mmgpt.llama_mmgpt import MMGPTLlamaForCausalLM, vicuna_7b_config
     torch.manual_seed(0)
     model = MMGPTLlamaForCausalLM(vicuna_7b_config(num_hidden_layers=1, vocab_size=2048)).to(device=DEV, dtype=torch.bfloat16)
+    model.requires_grad_(False)
     ids = torch.randint(3, 2000, (1, 2048), device=DEV)
     a = model(input_ids=ids).logits
     b = model(input_ids=ids).logits
