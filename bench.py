@@ -94,7 +94,115 @@ class ClockSampler:
 
 
 # ----------------------------------------------------------------------------- reference / CPU arm
-def cpu_reference_sample(threads=None):
+REF_SLICE_LAYERS = 4      # decoder layers of the bounded reference sample (of 32)
+REF_DECODE_STEPS = 2      # cached decode steps timed per sample
+
+
+class ReferenceCpuArm:
+    """The REAL reference on the host cores: `MMGPTLlamaForCausalLM` + `CLIPVisionTower` + `ConvProjector` imported
+    from oracle/_ref (oracle/build_ref.py; HF transformers modules underneath), bf16 like the reference's training
+    cast (builder.py:163), eager attention, every host thread.  One sample = the SAME workload with the decoder cut
+    to REF_SLICE_LAYERS of its 32 layers: full 5-frame 24-layer CLIP tower + projector + splice + 4 decoder layers
+    at S=4096 + full-sequence lm_head through the reference's own forward(use_cache=True), then REF_DECODE_STEPS
+    cached decode steps through the HF path generate() drives.  A second, 2-layer model separates the per-layer
+    cost from the fixed cost (tower, projector, lm_head), so the whole-step time is `fixed + 32 * per_layer` for the
+    prefill and `fixed_d + 32 * per_layer_d` per decode token — both measured here, on this box."""
+
+    def __init__(self, threads=None):
+        from oracle import merlin_oracle as O
+        from oracle import refmodel
+        self.threads = threads or os.cpu_count()
+        torch.set_num_threads(self.threads)
+        self.kind = "reference" if refmodel.available() else "port"
+        self.O, self.refmodel = O, refmodel
+        g = torch.Generator().manual_seed(1234)
+        self.batch = O.synthetic_batch(O.OracleConfig(), 1, SEQ_LEN, [N_FRAMES], seed=1234)
+        self.models = {}
+        if self.kind == "reference":
+            for L in (2, REF_SLICE_LAYERS):
+                cfg = O.OracleConfig(num_layers=L)
+                with torch.no_grad():
+                    self.models[L] = (cfg, refmodel.build_reference_model(cfg, None, device="cpu", dtype=torch.bfloat16,
+                                                                          attn="eager"))
+        self.per_layer = self.fixed = None
+
+    @torch.no_grad()
+    def _run(self, L, decode_steps):
+        cfg, m = self.models[L]
+        ids, imgs = self.batch["input_ids"], [self.batch["images"][0].to(torch.bfloat16)]
+        t0 = time.perf_counter()
+        out = m(input_ids=ids, attention_mask=torch.ones_like(ids, dtype=torch.bool), images=imgs, use_cache=True)
+        t_pre = time.perf_counter() - t0
+        cache, tok = out.past_key_values, out.logits[0, -1].argmax().view(1, 1)
+        t0 = time.perf_counter()
+        for t in range(decode_steps):
+            o = m.model(input_ids=tok, past_key_values=cache, use_cache=True,
+                        position_ids=torch.tensor([[SEQ_LEN + t]]))
+            tok = m.lm_head(o.last_hidden_state[0, -1]).argmax().view(1, 1)
+        t_dec = (time.perf_counter() - t0) / max(decode_steps, 1)
+        return t_pre, t_dec
+
+    def sample(self):
+        """One bounded sample; returns (tokens/s of the whole workload, measured sample seconds, description)."""
+        if self.kind != "reference":
+            v, total, text, _ = cpu_port_sample(self.threads)
+            return v, total, text
+        t0 = time.perf_counter()
+        if self.per_layer is None:          # calibrate fixed vs per-layer cost once with the 2-layer model
+            p2, d2 = self._run(2, REF_DECODE_STEPS)
+            self._two = (p2, d2)
+        pL, dL = self._run(REF_SLICE_LAYERS, REF_DECODE_STEPS)
+        p2, d2 = self._two
+        per_p, per_d = (pL - p2) / (REF_SLICE_LAYERS - 2), (dL - d2) / (REF_SLICE_LAYERS - 2)
+        fix_p, fix_d = pL - REF_SLICE_LAYERS * per_p, dL - REF_SLICE_LAYERS * per_d
+        self.per_layer = per_p
+        prefill = fix_p + 32 * per_p
+        decode = DECODE_TOKENS * (fix_d + 32 * per_d)
+        elapsed = time.perf_counter() - t0
+        text = (f"real reference (oracle/_ref MMGPTLlamaForCausalLM.forward, bf16, eager, {self.threads} threads): full 5-frame "
+                f"CLIP tower + projector + {REF_SLICE_LAYERS} of 32 decoder layers at S={SEQ_LEN} + lm_head = {pL:.2f}s "
+                f"(2-layer model {p2:.2f}s -> {per_p:.2f}s per layer, {fix_p:.2f}s fixed), cached decode step "
+                f"{dL * 1e3:.0f}ms ({per_d * 1e3:.1f}ms per layer); whole step = {fix_p:.2f} + 32x{per_p:.2f} + "
+                f"{DECODE_TOKENS}x({fix_d * 1e3:.0f}+32x{per_d * 1e3:.1f})ms = {prefill + decode:.1f}s")
+        return (SEQ_LEN + DECODE_TOKENS) / (prefill + decode), elapsed, text
+
+    @torch.no_grad()
+    def c1_full(self):
+        """BASELINE configs[0] in FULL: one 336 px image + 32-token caption through all 32 decoder layers of the real
+        reference on the host (bf16).  Weights are a tiled random block (timing only: a 7B normal_() draw on the host
+        takes minutes); norm weights are 1."""
+        if self.kind != "reference":
+            return None
+        O, refmodel = self.O, self.refmodel
+        cfg = O.OracleConfig()
+        t0 = time.perf_counter()
+        blk = torch.empty(1 << 22, dtype=torch.float32).normal_(0, 0.02).to(torch.bfloat16)
+        shapes = {k: v.shape for k, v in O.init_state_dict(O.OracleConfig(num_layers=1), seed=0).items()}
+        full = {}
+        for k, shp in shapes.items():
+            per_layer = k.startswith("model.layers.0.")
+            for n in ([k.replace("model.layers.0.", f"model.layers.{i}.") for i in range(32)] if per_layer else [k]):
+                numel = int(torch.Size(shp).numel())
+                t = blk.repeat((numel + blk.numel() - 1) // blk.numel())[:numel].view(shp).clone()
+                if len(shp) == 1 and n.endswith("weight"):
+                    t.fill_(1.0)
+                full[n] = t
+        m = refmodel.build_reference_model(cfg, full, device="cpu", dtype=torch.bfloat16, attn="eager")
+        del full
+        build_s = time.perf_counter() - t0
+        b = O.synthetic_batch(cfg, 1, 1 + 148 + 32, [1], seed=1234)
+        args = dict(input_ids=b["input_ids"], attention_mask=torch.ones_like(b["input_ids"], dtype=torch.bool),
+                    labels=b["labels"], images=[b["images"][0].to(torch.bfloat16)])
+        m(**args)
+        t0 = time.perf_counter()
+        out = m(**args)
+        fwd = time.perf_counter() - t0
+        return {"config": "C1: 1x336px image + 32-token caption, S=181, Vicuna-7B 32 layers, batch 1, bf16, host CPU",
+                "forward_s": fwd, "tokens_per_s": b["input_ids"].numel() / fwd, "loss": float(out.loss),
+                "build_s": build_s, "threads": self.threads}
+
+
+def cpu_port_sample(threads=None):
     """Oracle port of the reference CPU path, bounded sample of the SAME workload: one CLIP layer on the
     5 frames, one Vicuna-7B decoder layer at S=4096, the lm_head on 256 rows, and one cached decode layer
     step at context 4096 — bf16 weights/activations like the reference's training cast (builder.py:163),
@@ -150,22 +258,33 @@ def cpu_reference_sample(threads=None):
 
 
 def run_reference_arm(args, rank):
+    """`--impl reference`: the reference's own CPU implementation of the path on the box's host cores.  Every step is
+    one bounded sample (see ReferenceCpuArm); `ms_per_step` is the measured wall time of a sample, `value` the
+    whole-workload tokens/s its per-layer timings give.  Rank 0 only."""
     if rank != 0:
         return
+    arm = ReferenceCpuArm()
     vals = []
     for i in range(args.warmup + args.steps):
-        v, total, sample, threads = cpu_reference_sample()
+        v, elapsed, sample = arm.sample()
         if i >= args.warmup:
-            vals.append((v, total))
+            vals.append((v, elapsed))
     v = statistics.mean(x[0] for x in vals)
     ms = statistics.mean(x[1] for x in vals) * 1e3
     line = {"impl": "reference", "metric": "tokens/sec (prefill+decode) Merlin-7B 5-frame interpair", "value": v,
             "unit": "tokens/s", "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms,
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
-            "config": {"workload": WORKLOAD, "timing": "host wall clock, extrapolated from a bounded per-layer sample"},
-            "cpu_baseline": {"value": v, "unit": "tokens/s", "cores": threads, "kind": "port", "sample": sample},
+            "config": {"workload": WORKLOAD,
+                       "timing": "host wall clock; ms_per_step = one bounded sample (4 of 32 decoder layers, everything else "
+                                 "in full), value = whole-workload tokens/s from the measured fixed + per-layer times"},
+            "cpu_baseline": {"value": v, "unit": "tokens/s", "cores": arm.threads, "kind": arm.kind, "sample": sample},
             "e2e": {"value": v, "unit": "tokens/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "gpu_launches": 0}
+    if os.environ.get("MERLIN_BENCH_C1", "1") == "1":
+        try:
+            line["c1_full"] = arm.c1_full()
+        except Exception as e:  # the extra must never break the line
+            line["c1_full"] = {"error": str(e)}
     print(json.dumps(line), flush=True)
 
 
@@ -214,29 +333,105 @@ def make_inputs(rank):
     return input_ids, images
 
 
+def torch_gpu_detail(device, steps=2):
+    """Context (the honest same-box bar): the SAME C3 step through the REAL reference model
+    (oracle/_ref `MMGPTLlamaForCausalLM` over HF transformers' LlamaModel + CLIPVisionModel) on this GPU in bf16 —
+    cuBLAS GEMMs, torch SDPA attention, HF DynamicCache decode — prefill through the reference's own forward, then
+    32 cached single-token steps through the HF path its generate() drives (the reference's generate() itself does
+    not run under transformers 5.x).  Same dims, random weights, batch 1.  Not a target."""
+    from oracle import merlin_oracle as O
+    from oracle import refmodel
+    if not refmodel.available():
+        return {"unavailable": "oracle/_ref not built"}
+    cfg = O.OracleConfig()
+    prev = torch.get_default_dtype()
+    torch.set_default_dtype(torch.bfloat16)
+    try:
+        with torch.no_grad():
+            m = refmodel.build_reference_model(cfg, None, device=device, dtype=torch.bfloat16, attn="sdpa",
+                                               max_position_embeddings=SEQ_LEN + 64)
+    finally:
+        torch.set_default_dtype(prev)
+    b = O.synthetic_batch(cfg, 1, SEQ_LEN, [N_FRAMES], seed=1234)
+    ids = b["input_ids"].to(device)
+    imgs = [b["images"][0].to(device=device, dtype=torch.bfloat16)]
+    mask = torch.ones_like(ids, dtype=torch.bool)
+
+    @torch.no_grad()
+    def step():
+        e = [torch.cuda.Event(enable_timing=True) for _ in range(3)]
+        e[0].record()
+        out = m(input_ids=ids, attention_mask=mask, images=imgs, use_cache=True)
+        cache, tok = out.past_key_values, out.logits[0, -1].argmax().view(1, 1)
+        e[1].record()
+        for t in range(DECODE_TOKENS):
+            o = m.model(input_ids=tok, past_key_values=cache, use_cache=True,
+                        position_ids=torch.tensor([[SEQ_LEN + t]], device=device))
+            tok = m.lm_head(o.last_hidden_state[0, -1]).argmax().view(1, 1)
+        e[2].record()
+        torch.cuda.synchronize()
+        return e[0].elapsed_time(e[1]), e[1].elapsed_time(e[2])
+
+    step()
+    runs = [step() for _ in range(steps)]
+    pre = statistics.mean(r[0] for r in runs)
+    dec = statistics.mean(r[1] for r in runs)
+    del m
+    torch.cuda.empty_cache()
+    return {"what": "real reference model (oracle/_ref) on HF transformers %s, bf16, cuBLAS + SDPA, eager launches, DynamicCache"
+                    % __import__("transformers").__version__,
+            "prefill_ms": pre, "decode_ms_per_token": dec / DECODE_TOKENS, "ms_per_step": pre + dec,
+            "tokens_per_s": (SEQ_LEN + DECODE_TOKENS) / ((pre + dec) / 1e3)}
+
+
 def train_detail(model, input_ids_h, img_d, world, device, timed, steps=3):
     """Data-parallel training step on the same sample shape (extra information, not the headline):
-    forward + backward + bucketed NCCL all-reduce of the bf16 gradients (overlapped with backward) +
-    fused AdamW.  LLM + lm_head + embeddings + projector train, vision tower frozen."""
+    forward + backward + bucketed NCCL all-reduce of the bf16 gradients (merlin_dp_*, overlapped with backward) +
+    fused AdamW.  LLM + lm_head + embeddings + projector train, vision tower frozen.  At N > 1 the step is also
+    timed with the exchange switched off on the same box (`exposed_comm_ms` = the difference) and the replicas'
+    parameters are compared bit for bit after the steps (every rank trains on its own sample)."""
+    import torch.distributed as dist
     from merlin_b200.mmgpt.engine.train.trainer import MMGPTTrainer, TrainingArguments
     for p in model.parameters():
         p.requires_grad_(True)
     for p in model.get_model().vision_tower.parameters():
         p.requires_grad_(False)
-    model._graphed = {}  # graphs captured above hold the old weight addresses
+    model._graphed, model._decode_states = {}, {}  # graphs captured above hold the old weight addresses
     torch.cuda.empty_cache()
     trainer = MMGPTTrainer(model, TrainingArguments(learning_rate=1e-5, max_steps=1000))
     labels = input_ids_h.clone()
     labels[:, : SEQ_LEN // 2] = -100
     batch = {"input_ids": input_ids_h, "labels": labels, "attention_mask": None, "images": [img_d]}
     trainer.training_step(batch)
+    trainer.training_step(batch)
+    bytes0 = trainer.reducer.bytes_reduced
     ms, _ = timed(lambda: trainer.training_step(batch), steps)
     ms /= steps
+    per_step_bytes = (trainer.reducer.bytes_reduced - bytes0) // max(1, steps)
     n_params = trainer.arena.numel
     fl = 3 * algorithmic_flops_prefill(SEQ_LEN, 0) + algorithmic_flops_prefill(0, N_FRAMES)  # tower is forward-only
-    return {"ms_per_step": ms, "tokens_per_s": world * SEQ_LEN / (ms / 1e3), "trainable_params": n_params,
-            "model_tflops_per_gpu": fl / (ms / 1e3) / 1e12, "allreduce_bytes_per_step": trainer.reducer.bytes_reduced // max(1, steps + 1),
-            "note": "fwd+bwd+grad all-reduce+AdamW, bf16 weights/grads/state, no activation recompute"}
+    out = {"ms_per_step": ms, "tokens_per_s": world * SEQ_LEN / (ms / 1e3), "trainable_params": n_params,
+           "model_tflops_per_gpu": fl / (ms / 1e3) / 1e12, "allreduce_bytes_per_step": per_step_bytes,
+           "note": "fwd+bwd+grad all-reduce+AdamW, bf16 weights/grads/state, no activation recompute"}
+    if world > 1:
+        # replicas must hold bit-identical parameters: same initial weights, same all-reduced gradients, same
+        # fixed-point clip factor (each rank trained on a DIFFERENT sample)
+        bits = trainer.arena.params.view(torch.int32)        # pairs of bf16 as int32: exact bitwise comparison
+        hi, lo = bits.clone(), bits.clone()
+        dist.all_reduce(hi, op=dist.ReduceOp.MAX)
+        dist.all_reduce(lo, op=dist.ReduceOp.MIN)
+        out["replicas_bit_identical"] = bool(torch.equal(hi, lo))
+        del hi, lo
+        r = trainer.reducer
+        out["exchange"] = {"backend": r.backend, "nccl_max_ctas": r.max_ctas, "sm_reserve": r.sm_reserve,
+                           "buckets": len(r.buckets)}
+        r.exchange_enabled = False          # compute-only step on the same box (gradients stay local)
+        trainer.training_step(batch)
+        ms0, _ = timed(lambda: trainer.training_step(batch), steps)
+        r.exchange_enabled = True
+        out["ms_per_step_without_exchange"] = ms0 / steps
+        out["exposed_comm_ms"] = ms - ms0 / steps
+    return out
 
 
 def main():
@@ -343,6 +538,12 @@ def main():
         dec_kernel_ms = [k0.elapsed_time(k1) for k0, k1 in pairs[2:]]
     step_host()
     e2e_ms, _ = timed(step_host, args.steps)
+    torch_gpu = None
+    if rank == 0 and world == 1 and os.environ.get("MERLIN_BENCH_TORCH_GPU", "1") == "1":
+        try:
+            torch_gpu = torch_gpu_detail(device)
+        except Exception as e:  # context only: never break the bench line
+            torch_gpu = {"error": str(e)[:300]}
     train = train_detail(model, input_ids_h, img_d, world, device, timed) if os.environ.get("MERLIN_BENCH_TRAIN", "1") == "1" else None
 
     tokens = SEQ_LEN + DECODE_TOKENS
@@ -355,12 +556,15 @@ def main():
     fl = algorithmic_flops_prefill(SEQ_LEN, N_FRAMES)
     # algorithmic bytes of one decode launch: every decoder + lm_head weight once, the cached
     # keys/values of the context once (average context of the timed tokens)
-    dec_bytes = 13.48e9 + 0.524e6 * (SEQ_LEN + DECODE_TOKENS / 2)
+    # weights the decode kernel streams: 32 layers x 202.38 M parameters + lm_head [32003, 4096], bf16 = 13.21 GB
+    # (embed_tokens is NOT streamed: one row is gathered); KV read 0.524 MB per context token
+    dec_weight_bytes = 2.0 * (32 * (4 * 4096 * 4096 + 3 * 4096 * 11008 + 2 * 4096) + 4096 + 32003 * 4096)
+    dec_bytes = dec_weight_bytes + 0.524e6 * (SEQ_LEN + DECODE_TOKENS / 2)
     if dec_kernel_ms:
         dk_ms = statistics.mean(dec_kernel_ms)
         roof_hbm = {"bound": "hbm", "achieved": dec_bytes / (dk_ms / 1e3) / 1e9, "peak": peaks["hbm"], "unit": "GB/s",
                     "frac": dec_bytes / (dk_ms / 1e3) / 1e9 / peaks["hbm"], "traffic": 15.38e9,
-                    "traffic_note": "dram__bytes_read+write of ONE launch from profiles/r1_decode_stream_metrics.csv (algorithmic 15.63 GB)",
+                    "traffic_note": "dram__bytes_read+write of ONE launch from profiles/r1_decode_stream_metrics.csv (algorithmic %.2f GB)" % (dec_bytes / 1e9),
                     "kernel": "decode_stream_kernel (whole decode step: 1 persistent launch per token, TMA weight/KV ring)",
                     "launches_timed": len(dec_kernel_ms), "avg_launch_ms": dk_ms,
                     "share_of_step": DECODE_TOKENS * dk_ms / ms_per_step,
@@ -390,14 +594,17 @@ def main():
                    "prefill_model_tflops": fl / (pre_ms / 1e3) / 1e12,
                    "prefill_frac_of_sustained_peak": fl / (pre_ms / 1e3) / 1e12 / peaks["tflops"],
                    "decode_ms_per_token": dec_ms / DECODE_TOKENS, "decode_tokens_per_s": DECODE_TOKENS / (dec_ms / 1e3),
-                   "decode_hbm_frac": (13.48e9 + 0.524e6 * SEQ_LEN) / (dec_ms / DECODE_TOKENS / 1e3) / 1e9 / peaks["hbm"]},
+                   "decode_hbm_frac": (dec_weight_bytes + 0.524e6 * SEQ_LEN) / (dec_ms / DECODE_TOKENS / 1e3) / 1e9 / peaks["hbm"]},
     }
     if train is not None:
         line["detail"]["train"] = train
+    if torch_gpu is not None:
+        line["detail"]["torch_gpu"] = torch_gpu
     if rank == 0 and world == 1 and os.environ.get("MERLIN_BENCH_CPU", "1") == "1":
         try:
-            v, total, sample, threads = cpu_reference_sample()
-            line["cpu_baseline"] = {"value": v, "unit": "tokens/s", "cores": threads, "kind": "port", "sample": sample}
+            arm = ReferenceCpuArm()
+            v, _, sample = arm.sample()
+            line["cpu_baseline"] = {"value": v, "unit": "tokens/s", "cores": arm.threads, "kind": arm.kind, "sample": sample}
         except Exception as e:  # the checker must never break the bench line
             line["cpu_baseline"] = {"value": None, "unit": "tokens/s", "cores": os.cpu_count(), "kind": "port",
                                     "sample": f"failed: {e}"}

@@ -1,21 +1,34 @@
-// merlin_b200 — flash-attention backward for sm_100a (tcgen05 + TMEM + TMA), head_dim 128.
+// merlin_b200 — flash-attention backward for sm_100a (tcgen05 + TMEM + TMA), head_dim 64 / 128.
 //
 // One CTA owns a 128-key tile j of one head and walks the query tiles i that attend to it
 // (i >= j when causal).  Per (i, j):
 //     S  = Q_i K_jᵀ            dP = dO_i V_jᵀ                      (tcgen05 -> TMEM, fp32)
-//     P  = exp2(S·c − lse_i)    dS = P ∘ (dP − δ_i) · scale         (128 threads, one query row each)
+//     P  = exp2(S·c − lse_i)    dS = P ∘ (dP − δ_i) · scale         (256 threads: query row x column half)
 //     dV += Pᵀ dO_i            dK += dSᵀ Q_i            dQ_i = dS K_j
 // dK / dV accumulate in TMEM across the whole walk and are written once; dQ_i is reduced into an fp32
-// global buffer with red.global.add (the cross-CTA reduction over key tiles).  P and dS are written
+// global buffer with TMA reduce-add (the cross-CTA reduction over key tiles).  P and dS are written
 // once to 128B-swizzled shared tiles and consumed both K-major (dQ) and MN-major (dV, dK: the same
 // bytes, described with the M and K roles swapped), as are the Q / dO / K / V row-major TMA tiles.
-// TMEM: S|dQ [0,128)  dP [128,256)  dV [256,384)  dK [384,512).
+// TMEM: S|dQ [0,128)  dP [128,256)  dV [256,384)  dK [384,512)  — all 512 columns, so S / dP cannot be
+// double-buffered, and shared memory (K, V, Q, dO, P, dS = 192 KB) has no room for a second Q / dO stage.
+// The overlap therefore happens INSIDE a step: the tensor pipe and the softmax warps alternate on halves of it
+//
+//   tensor pipe :  S ─────►  dP ─────────►  dV ─────────►  dK ──►  dQ ──►            (S of step s+1 ...)
+//   softmax     :            P = f(S) ───►  dS = g(P, dP) ►                 drain dQ, TMA reduce-add
+//   TMA loads   :                                           dO(s+1) ◄── after dV    Q(s+1) ◄── after dK
+//
+// i.e. P is computed while dP is being multiplied, dS while dV is, and the next step's operands arrive under
+// dK / dQ and the dQ drain.  Round 1 ran these phases back to back with 4 softmax warps and measured 18 % tensor
+// pipe activity (profiles/r2_train_kernels_ncu.txt); two warps per TMEM lane quarter halve the softmax time and
+// keep the per-thread state at 64 columns (no local-memory spills).
 #pragma once
 #include "ptx.cuh"
 
 namespace mb {
 
-constexpr int kBwdThreads = 256;
+constexpr int kBwdSoftmaxWarps = 8;
+constexpr int kBwdSoftmaxThreads = kBwdSoftmaxWarps * 32;
+constexpr int kBwdThreads = 128 + kBwdSoftmaxThreads;   // warps 0-3: TMA, MMA, TMEM alloc, spare
 constexpr int kBwdBlock = 128;
 
 struct AttnBwdParams {
@@ -36,15 +49,9 @@ struct AttnBwdCfg {
   static constexpr int kTileBytes = kBwdBlock * HD * 2;         // [128 rows x HD] bf16: K, V, Q, dO
   static constexpr int kPBytes = kBwdBlock * kBwdBlock * 2;     // [128 x 128] bf16: P, dS
   static constexpr int kSmemTiles = kTileBytes * 4 + kPBytes * 2;
-  static constexpr int kNumBars = 8;
+  static constexpr int kNumBars = 12;
   static constexpr int kSmemBytes = kSmemTiles + kNumBars * 8 + 16 + 1024;
 };
-
-// 16-byte vector reduction (sm_90+): one L2 atomic transaction per four floats
-__device__ __forceinline__ void red_add_f32x4(float* addr, float a, float b, float c, float d) {
-  asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(addr), "f"(a), "f"(b), "f"(c), "f"(d)
-               : "memory");
-}
 
 template <int HD, bool kCausal>
 __global__ void __launch_bounds__(kBwdThreads, 1)
@@ -65,12 +72,16 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid_constan
   uint8_t* sds = sp + Cfg::kPBytes;
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + Cfg::kSmemTiles);
   uint64_t* kv_full = bars;        // K_j, V_j landed (once)
-  uint64_t* qdo_full = bars + 1;   // Q_i, dO_i landed
-  uint64_t* qdo_empty = bars + 2;  // MMAs of step i no longer read Q_i / dO_i / P / dS
-  uint64_t* sdp_full = bars + 3;   // S and dP in TMEM
-  uint64_t* pds_full = bars + 4;   // P and dS in shared memory (128 arrivals)
-  uint64_t* dq_full = bars + 5;    // dV, dK, dQ MMAs of step i complete
-  uint64_t* dq_read = bars + 6;    // dQ drained from TMEM (128 arrivals): S region reusable
+  uint64_t* q_full = bars + 1;     // Q_i landed
+  uint64_t* do_full = bars + 2;    // dO_i landed
+  uint64_t* q_empty = bars + 3;    // S and dK MMAs of step i done: Q_i reusable
+  uint64_t* do_empty = bars + 4;   // dP and dV MMAs of step i done: dO_i reusable
+  uint64_t* s_full = bars + 5;     // S in TMEM
+  uint64_t* dp_full = bars + 6;    // dP in TMEM
+  uint64_t* p_full = bars + 7;     // P in shared memory (256 arrivals)
+  uint64_t* ds_full = bars + 8;    // dS in shared memory (256 arrivals)
+  uint64_t* dq_full = bars + 9;    // every MMA of step i complete (dQ in TMEM; P / dS staging reusable)
+  uint64_t* dq_read = bars + 10;   // dQ drained from TMEM (256 arrivals): S region reusable
   uint32_t* tmem_ptr_smem = reinterpret_cast<uint32_t*>(bars + Cfg::kNumBars);
 
   const int warp = threadIdx.x >> 5;
@@ -91,12 +102,16 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid_constan
   }
   if (warp == 1 && elect_one()) {
     mbar_init(kv_full, 1);
-    mbar_init(qdo_full, 1);
-    mbar_init(qdo_empty, 1);
-    mbar_init(sdp_full, 1);
-    mbar_init(pds_full, 128);
+    mbar_init(q_full, 1);
+    mbar_init(do_full, 1);
+    mbar_init(q_empty, 1);
+    mbar_init(do_empty, 1);
+    mbar_init(s_full, 1);
+    mbar_init(dp_full, 1);
+    mbar_init(p_full, kBwdSoftmaxThreads);
+    mbar_init(ds_full, kBwdSoftmaxThreads);
     mbar_init(dq_full, 1);
-    mbar_init(dq_read, 128);
+    mbar_init(dq_read, kBwdSoftmaxThreads);
     fence_barrier_init();
   }
   if (warp == 2) tmem_alloc<512>(tmem_ptr_smem);
@@ -117,13 +132,16 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid_constan
       }
       for (int s = 0; s < n_steps; ++s) {
         const int q0 = (i_begin + s) * kBwdBlock;
-        mbar_wait(qdo_empty, (s & 1) ^ 1);
-        mbar_expect_tx(qdo_full, 2 * Cfg::kTileBytes);
+        mbar_wait(do_empty, (s & 1) ^ 1);          // frees first: right after dV of the previous step
+        mbar_expect_tx(do_full, Cfg::kTileBytes);
 #pragma unroll
-        for (int a = 0; a < kAtoms; ++a) {
-          tma_load_3d(&tm_qkv, qdo_full, sq + a * kAtomBytes, p.q_col0 + head * HD + a * 64, q0, batch, kEvictLast);
-          tma_load_3d(&tm_do, qdo_full, sdo + a * kAtomBytes, head * HD + a * 64, q0, batch, kEvictLast);
-        }
+        for (int a = 0; a < kAtoms; ++a)
+          tma_load_3d(&tm_do, do_full, sdo + a * kAtomBytes, head * HD + a * 64, q0, batch, kEvictLast);
+        mbar_wait(q_empty, (s & 1) ^ 1);           // after dK of the previous step
+        mbar_expect_tx(q_full, Cfg::kTileBytes);
+#pragma unroll
+        for (int a = 0; a < kAtoms; ++a)
+          tma_load_3d(&tm_qkv, q_full, sq + a * kAtomBytes, p.q_col0 + head * HD + a * 64, q0, batch, kEvictLast);
       }
     }
     __syncwarp();
@@ -137,22 +155,29 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid_constan
                      a_p = smem_u32(sp), a_ds = smem_u32(sds);
       mbar_wait(kv_full, 0);
       for (int s = 0; s < n_steps; ++s) {
-        mbar_wait(qdo_full, s & 1);
-        mbar_wait(dq_read, (s & 1) ^ 1);   // dQ of the previous step has left the S region
+        const uint32_t ph = s & 1;
+        // ---- S = Q Kᵀ  (the S region held dQ of the previous step until the softmax warps drained it)
+        mbar_wait(q_full, ph);
+        mbar_wait(dq_read, ph ^ 1);
         tc_fence_after();
 #pragma unroll
         for (int kk = 0; kk < HD / 16; ++kk) {
           const uint32_t off = (kk >> 2) * kAtomBytes + (kk & 3) * 32;
           umma_ss(t_s, umma_desc_k_sw128(a_q + off), umma_desc_k_sw128(a_k + off), idesc_kk, kk != 0);
         }
+        umma_commit(s_full);
+        // ---- dP = dO Vᵀ  (runs while the softmax warps turn S into P; dP of the previous step was consumed
+        //      before its dS was published, which this thread waited for)
+        mbar_wait(do_full, ph);
+        tc_fence_after();
 #pragma unroll
         for (int kk = 0; kk < HD / 16; ++kk) {
           const uint32_t off = (kk >> 2) * kAtomBytes + (kk & 3) * 32;
           umma_ss(t_dp, umma_desc_k_sw128(a_do + off), umma_desc_k_sw128(a_v + off), idesc_kk, kk != 0);
         }
-        umma_commit(sdp_full);
-
-        mbar_wait(pds_full, s & 1);
+        umma_commit(dp_full);
+        // ---- dV += Pᵀ dO  (runs while the softmax warps turn P, dP into dS)
+        mbar_wait(p_full, ph);
         tc_fence_after();
 #pragma unroll
         for (int kk = 0; kk < kBwdBlock / 16; ++kk) {
@@ -161,12 +186,17 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid_constan
           umma_ss(t_dv, umma_desc_mn_sw128(a_p + roff, kAtomBytes), umma_desc_mn_sw128(a_do + roff, kAtomBytes),
                   idesc_mm, (s | kk) != 0);
         }
+        umma_commit(do_empty);
+        // ---- dK += dSᵀ Q, then dQ = dS K into the S region (S was consumed before P was published)
+        mbar_wait(ds_full, ph);
+        tc_fence_after();
 #pragma unroll
         for (int kk = 0; kk < kBwdBlock / 16; ++kk) {
           const uint32_t roff = kk * 2048;
           umma_ss(t_dk, umma_desc_mn_sw128(a_ds + roff, kAtomBytes), umma_desc_mn_sw128(a_q + roff, kAtomBytes),
                   idesc_mm, (s | kk) != 0);
         }
+        umma_commit(q_empty);
 #pragma unroll
         for (int kk = 0; kk < kBwdBlock / 16; ++kk) {
           // dQ = dS K: reduction over 16 keys: A advances inside the key-major rows, B by 16 key rows
@@ -174,71 +204,96 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid_constan
           umma_ss(t_s, umma_desc_k_sw128(a_ds + aoff), umma_desc_mn_sw128(a_k + kk * 2048, kAtomBytes), idesc_km,
                   kk != 0);
         }
-        umma_commit(qdo_empty);
         umma_commit(dq_full);
       }
     }
     __syncwarp();
   } else if (warp >= 4) {
-    // ===================================================== P / dS / dQ threads
-    const int ewarp = warp - 4;
-    const int row = ewarp * 32 + static_cast<int>(lane_id());
-    const uint32_t lane_sel = static_cast<uint32_t>(ewarp * 32) << 16;
+    // ===================================================== P / dS / dQ threads: (query row) x (column half)
+    const int sw = warp - 4;
+    const int quarter = sw & 3;                     // TMEM lane quarter this warp may touch (warp id % 4)
+    const int half = sw >> 2;                       // key columns [64 half, 64 half + 64)
+    const int row = quarter * 32 + static_cast<int>(lane_id());
+    const uint32_t lane_sel = static_cast<uint32_t>(quarter * 32) << 16;
+    const bool leader = threadIdx.x == 128;
     const float log2e = 1.4426950408889634f;
     for (int s = 0; s < n_steps; ++s) {
+      const uint32_t ph = s & 1;
       const int i = i_begin + s;
       const int q_idx = i * kBwdBlock + row;
       const bool q_valid = q_idx < len;
       const size_t stat = (static_cast<size_t>(batch) * p.H + head) * p.S + (q_valid ? q_idx : 0);
       const float lse2 = q_valid ? p.lse[stat] * log2e : 0.f;
       const float dlt = q_valid ? p.delta[stat] : 0.f;
-      mbar_wait(sdp_full, s & 1);
+      float pv[64];
+      // ---- P = exp2(S c − lse)
+      mbar_wait(s_full, ph);
       tc_fence_after();
       if (s > 0) {
         // the previous step's dQ reduction must have finished READING the P|dS staging bytes
-        if (threadIdx.x == 128) tma_store_wait_read<0>();
-        named_bar_sync(1, 128);
+        if (leader) tma_store_wait_read<0>();
+        named_bar_sync(1, kBwdSoftmaxThreads);
       }
 #pragma unroll
-      for (int ch = 0; ch < 4; ++ch) {
-        uint32_t sv_[32], dpv[32];
+      for (int c2 = 0; c2 < 2; ++c2) {
+        const int ch = half * 2 + c2;               // 32-key chunk
+        uint32_t sv_[32];
         tmem_ld32(t_s + lane_sel + ch * 32, sv_);
-        tmem_ld32(t_dp + lane_sel + ch * 32, dpv);
         tmem_ld_wait();
-        uint32_t pw[16], dw[16];
+        uint32_t pw[16];
 #pragma unroll
         for (int c = 0; c < 32; c += 2) {
-          float pv[2], dv[2];
 #pragma unroll
           for (int e = 0; e < 2; ++e) {
             const int kv = kv0 + ch * 32 + c + e;
             const bool dead = !q_valid || kv >= len || (kCausal && kv > q_idx);
-            const float pe = dead ? 0.f : fast_exp2(fmaf(__uint_as_float(sv_[c + e]), p.scale_log2e, -lse2));
-            pv[e] = pe;
-            dv[e] = pe * (__uint_as_float(dpv[c + e]) - dlt) * p.scale;
+            pv[c2 * 32 + c + e] = dead ? 0.f : fast_exp2(fmaf(__uint_as_float(sv_[c + e]), p.scale_log2e, -lse2));
           }
-          pw[c >> 1] = pack_bf16(pv[0], pv[1]);
-          dw[c >> 1] = pack_bf16(dv[0], dv[1]);
+          pw[c >> 1] = pack_bf16(pv[c2 * 32 + c], pv[c2 * 32 + c + 1]);
         }
         // 32 keys = 64 bytes = four 16-byte chunks of this row inside atom (ch >> 1)
 #pragma unroll
         for (int q4 = 0; q4 < 4; ++q4) {
-          const int chunk = (ch & 1) * 4 + q4;
-          const uint32_t off = (ch >> 1) * kAtomBytes + sw128_offset(row, chunk);
+          const uint32_t off = (ch >> 1) * kAtomBytes + sw128_offset(row, (ch & 1) * 4 + q4);
           *reinterpret_cast<uint4*>(sp + off) = make_uint4(pw[q4 * 4], pw[q4 * 4 + 1], pw[q4 * 4 + 2], pw[q4 * 4 + 3]);
+        }
+      }
+      fence_proxy_async_smem();
+      tc_fence_before();
+      mbar_arrive(p_full);
+      // ---- dS = P ∘ (dP − δ) · scale
+      mbar_wait(dp_full, ph);
+      tc_fence_after();
+#pragma unroll
+      for (int c2 = 0; c2 < 2; ++c2) {
+        const int ch = half * 2 + c2;
+        uint32_t dpv[32];
+        tmem_ld32(t_dp + lane_sel + ch * 32, dpv);
+        tmem_ld_wait();
+        uint32_t dw[16];
+#pragma unroll
+        for (int c = 0; c < 32; c += 2) {
+          const float d0 = pv[c2 * 32 + c] * (__uint_as_float(dpv[c]) - dlt) * p.scale;
+          const float d1 = pv[c2 * 32 + c + 1] * (__uint_as_float(dpv[c + 1]) - dlt) * p.scale;
+          dw[c >> 1] = pack_bf16(d0, d1);
+        }
+#pragma unroll
+        for (int q4 = 0; q4 < 4; ++q4) {
+          const uint32_t off = (ch >> 1) * kAtomBytes + sw128_offset(row, (ch & 1) * 4 + q4);
           *reinterpret_cast<uint4*>(sds + off) = make_uint4(dw[q4 * 4], dw[q4 * 4 + 1], dw[q4 * 4 + 2], dw[q4 * 4 + 3]);
         }
       }
       fence_proxy_async_smem();
       tc_fence_before();
-      mbar_arrive(pds_full);
+      mbar_arrive(ds_full);
 
-      // dQ_i tile: TMEM -> fp32 128B-swizzled staging (aliasing P|dS, which the MMAs have finished
+      // ---- dQ_i tile: TMEM -> fp32 128B-swizzled staging (aliasing P|dS, which the MMAs have finished
       // reading) -> ONE TMA reduce-add per [128 rows x 32 floats] box into the fp32 dQ accumulator
-      mbar_wait(dq_full, s & 1);
+      mbar_wait(dq_full, ph);
       tc_fence_after();
 #pragma unroll
-      for (int ch = 0; ch < HD / 32; ++ch) {
+      for (int c2 = 0; c2 < HD / 64; ++c2) {
+        const int ch = half * (HD / 64) + c2;       // 32-float column chunk of dQ
         uint32_t v[32];
         tmem_ld32(t_s + lane_sel + ch * 32, v);
         tmem_ld_wait();
@@ -250,17 +305,17 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid_constan
       tc_fence_before();
       mbar_arrive(dq_read);
       fence_proxy_async_smem();
-      named_bar_sync(1, 128);
-      if (threadIdx.x == 128) {
+      named_bar_sync(1, kBwdSoftmaxThreads);
+      if (leader) {
 #pragma unroll
         for (int ch = 0; ch < HD / 32; ++ch)
           tma_reduce_add_2d(&tm_dq, sp + ch * kAtomBytes, head * HD + ch * 32, batch * p.S + i * kBwdBlock);
         tma_store_commit();
       }
     }
-    if (threadIdx.x == 128) tma_store_wait_all<0>();
+    if (leader) tma_store_wait_all<0>();
 
-    // ---- dK, dV of this key tile (thread = key row).  The TMEM loads are warp-collective
+    // ---- dK, dV of this key tile (thread = key row x column half).  The TMEM loads are warp-collective
     // (.sync.aligned): every lane executes them, only the global stores are predicated.
     const int kv_idx = kv0 + row;
     const bool in_range = kv_idx < p.S;
@@ -271,7 +326,8 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid_constan
       const uint32_t t_acc = which == 0 ? t_dk : t_dv;
       __nv_bfloat16* dst = out_row + (which == 0 ? p.k_col0 : p.v_col0) + head * HD;
 #pragma unroll
-      for (int ch = 0; ch < HD / 32; ++ch) {
+      for (int c2 = 0; c2 < HD / 64; ++c2) {
+        const int ch = half * (HD / 64) + c2;
         uint32_t v[32];
         if (n_steps > 0) {  // block-uniform
           tmem_ld32(t_acc + lane_sel + ch * 32, v);

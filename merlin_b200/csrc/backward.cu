@@ -7,6 +7,7 @@
 #include "ptx.cuh"
 
 #include <algorithm>
+#include <mutex>
 
 namespace mb {
 
@@ -113,6 +114,115 @@ rmsnorm_bwd_kernel(const __nv_bfloat16* __restrict__ x, const __nv_bfloat16* __r
 #pragma unroll
         for (int e = 0; e < 8; ++e) atomicAdd(&dw[idx * 8 + e], dwacc[i][e]);
     }
+  }
+}
+
+// Warp-per-row variant (the default): no block-wide reductions, 2·NV 16-byte loads in flight per lane, so the
+// kernel streams at HBM rate instead of waiting on two __syncthreads() reductions per row.
+//   Σx² and Σ(w⊙dy)·x are reduced TOGETHER (one shuffle tree): mean(g⊙x̂) = rstd·Σ(g·x)/D, hence
+//   dx = rstd·g − x·(rstd³·Σ(g·x)/D) (+ dres).
+// dw: every warp accumulates dy⊙x̂ into its PRIVATE shared-memory copy ([e][vec] layout: conflict-free plain
+// read-modify-write, no atomics); the CTA folds its 8 copies and issues one 16-byte red.global.add per 4 columns.
+constexpr int kRnwWarps = 8;
+
+__device__ __forceinline__ uint4 ld_stream_u4(const uint4* p) {
+  uint4 v;
+  asm volatile("ld.global.L1::no_allocate.v4.u32 {%0, %1, %2, %3}, [%4];"
+               : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "l"(p));
+  return v;
+}
+
+template <int NV>
+__global__ void __launch_bounds__(kRnwWarps * 32)
+rmsnorm_bwd_warp_kernel(const __nv_bfloat16* __restrict__ x, const __nv_bfloat16* __restrict__ w,
+                        const __nv_bfloat16* __restrict__ dy, const __nv_bfloat16* __restrict__ dres,
+                        __nv_bfloat16* __restrict__ dx, float* __restrict__ dw, int M, int D, float eps) {
+  extern __shared__ float dwsm[];   // [kRnwWarps][8][D/8]
+  const int nvec = D >> 3;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  float* mine = dwsm + static_cast<size_t>(warp) * D;
+  if (dw != nullptr) {
+    for (int i = lane; i < D; i += 32) mine[i] = 0.f;
+    __syncwarp();
+  }
+  const uint4* w4 = reinterpret_cast<const uint4*>(w);
+  const float inv_d = 1.f / static_cast<float>(D);
+  for (int row = blockIdx.x * kRnwWarps + warp; row < M; row += gridDim.x * kRnwWarps) {
+    const size_t off = static_cast<size_t>(row) * D;
+    const uint4* x4 = reinterpret_cast<const uint4*>(x + off);
+    const uint4* g4 = reinterpret_cast<const uint4*>(dy + off);
+    uint4 xq[NV], gq[NV];
+#pragma unroll
+    for (int i = 0; i < NV; ++i) {
+      const int idx = lane + 32 * i;
+      if (idx < nvec) {
+        xq[i] = ld_stream_u4(x4 + idx);
+        gq[i] = ld_stream_u4(g4 + idx);
+      }
+    }
+    float ss = 0.f, gx = 0.f;
+#pragma unroll
+    for (int i = 0; i < NV; ++i) {
+      const int idx = lane + 32 * i;
+      if (idx < nvec) {
+        float xv[8], gv[8], wv[8];
+        unpack8b(xq[i], xv);
+        unpack8b(gq[i], gv);
+        unpack8b(__ldg(w4 + idx), wv);
+        // short independent chains (the two 128-long serial FMA chains were the latency bound of this kernel)
+        const float s0 = fmaf(xv[0], xv[0], xv[1] * xv[1]), s1 = fmaf(xv[2], xv[2], xv[3] * xv[3]);
+        const float s2 = fmaf(xv[4], xv[4], xv[5] * xv[5]), s3 = fmaf(xv[6], xv[6], xv[7] * xv[7]);
+        const float g0 = fmaf(gv[0] * wv[0], xv[0], gv[1] * wv[1] * xv[1]);
+        const float g1 = fmaf(gv[2] * wv[2], xv[2], gv[3] * wv[3] * xv[3]);
+        const float g2 = fmaf(gv[4] * wv[4], xv[4], gv[5] * wv[5] * xv[5]);
+        const float g3 = fmaf(gv[6] * wv[6], xv[6], gv[7] * wv[7] * xv[7]);
+        ss += (s0 + s1) + (s2 + s3);
+        gx += (g0 + g1) + (g2 + g3);
+      }
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+      ss += __shfl_xor_sync(0xffffffffu, ss, o);
+      gx += __shfl_xor_sync(0xffffffffu, gx, o);
+    }
+    const float rstd = rsqrtf(ss * inv_d + eps);
+    const float c = rstd * rstd * rstd * gx * inv_d;
+#pragma unroll
+    for (int i = 0; i < NV; ++i) {
+      const int idx = lane + 32 * i;
+      if (idx < nvec) {
+        float xv[8], gv[8], wv[8], o[8];
+        unpack8b(xq[i], xv);
+        unpack8b(gq[i], gv);
+        unpack8b(__ldg(w4 + idx), wv);
+        if (dres != nullptr) unpack8b(ld_stream_u4(reinterpret_cast<const uint4*>(dres + off) + idx), o);
+#pragma unroll
+        for (int e = 0; e < 8; ++e) {
+          const float v = rstd * (gv[e] * wv[e]) - xv[e] * c;
+          o[e] = dres != nullptr ? o[e] + v : v;
+        }
+        reinterpret_cast<uint4*>(dx + off)[idx] = pack8b(o);
+        if (dw != nullptr) {
+#pragma unroll
+          for (int e = 0; e < 8; ++e) mine[e * nvec + idx] += gv[e] * (xv[e] * rstd);
+        }
+      }
+    }
+  }
+  if (dw == nullptr) return;
+  __syncthreads();
+  // fold the 8 private copies; element (e, idx) is column idx*8 + e: lanes take 4 consecutive columns
+  for (int q = threadIdx.x; q < D / 4; q += kRnwWarps * 32) {
+    const int col = q * 4, idx = col >> 3, e0 = col & 7;
+    float a[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+    for (int ww = 0; ww < kRnwWarps; ++ww) {
+      const float* src = dwsm + static_cast<size_t>(ww) * D;
+#pragma unroll
+      for (int e = 0; e < 4; ++e) a[e] += src[(e0 + e) * nvec + idx];
+    }
+    asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(dw + col), "f"(a[0]), "f"(a[1]), "f"(a[2]),
+                 "f"(a[3]) : "memory");
   }
 }
 
@@ -346,6 +456,26 @@ static int grid_for(int64_t work_items, int threads) {
 
 using namespace mb;
 
+template <int NV>
+static int launch_rmsnorm_bwd_warp(cudaStream_t st, const void* x, const void* weight, const void* dy, const void* dres,
+                                   void* dx, float* dweight, int M, int D, float eps) {
+  const size_t smem = static_cast<size_t>(kRnwWarps) * D * sizeof(float);
+  static std::once_flag once;
+  static cudaError_t attr_rc = cudaSuccess;
+  std::call_once(once, [] {
+    attr_rc = cudaFuncSetAttribute(rmsnorm_bwd_warp_kernel<NV>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                   kRnwWarps * NV * 256 * static_cast<int>(sizeof(float)));
+  });
+  MB_CHECK_CUDA(attr_rc);
+  const int grid = std::min((M + kRnwWarps - 1) / kRnwWarps, sm_count());
+  rmsnorm_bwd_warp_kernel<NV><<<grid, kRnwWarps * 32, smem, st>>>(
+      static_cast<const __nv_bfloat16*>(x), static_cast<const __nv_bfloat16*>(weight),
+      static_cast<const __nv_bfloat16*>(dy), static_cast<const __nv_bfloat16*>(dres),
+      static_cast<__nv_bfloat16*>(dx), dweight, M, D, eps);
+  MB_CHECK_CUDA(cudaGetLastError());
+  return MERLIN_OK;
+}
+
 extern "C" {
 
 int merlin_rmsnorm_bwd(void* stream, const void* x, const void* weight, const void* dy, const void* dres,
@@ -353,7 +483,15 @@ int merlin_rmsnorm_bwd(void* stream, const void* x, const void* weight, const vo
   MB_CHECK_ARG(x && weight && dy && dx, "rmsnorm_bwd: null tensor");
   MB_CHECK_ARG(D % 8 == 0 && D <= 8 * kRnbThreads * kRnbVec, "rmsnorm_bwd: D=%d unsupported", D);
   if (M == 0) return MERLIN_OK;
-  rmsnorm_bwd_kernel<<<std::min(M, sm_count() * 4), kRnbThreads, 0, static_cast<cudaStream_t>(stream)>>>(
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  // warp-per-row kernel for every width the decoder uses (registers hold the row: D <= 5120), D % 32 == 0 so that
+  // the 16-byte dw reductions stay aligned; anything else takes the CTA-per-row kernel
+  if (D % 32 == 0 && D <= 256) return launch_rmsnorm_bwd_warp<1>(st, x, weight, dy, dres, dx, dweight, M, D, eps);
+  if (D % 32 == 0 && D <= 1024) return launch_rmsnorm_bwd_warp<4>(st, x, weight, dy, dres, dx, dweight, M, D, eps);
+  if (D % 32 == 0 && D <= 2048) return launch_rmsnorm_bwd_warp<8>(st, x, weight, dy, dres, dx, dweight, M, D, eps);
+  if (D % 32 == 0 && D <= 4096) return launch_rmsnorm_bwd_warp<16>(st, x, weight, dy, dres, dx, dweight, M, D, eps);
+  if (D % 32 == 0 && D <= 5120) return launch_rmsnorm_bwd_warp<20>(st, x, weight, dy, dres, dx, dweight, M, D, eps);
+  rmsnorm_bwd_kernel<<<std::min(M, sm_count() * 4), kRnbThreads, 0, st>>>(
       static_cast<const __nv_bfloat16*>(x), static_cast<const __nv_bfloat16*>(weight),
       static_cast<const __nv_bfloat16*>(dy), static_cast<const __nv_bfloat16*>(dres),
       static_cast<__nv_bfloat16*>(dx), dweight, M, D, eps);

@@ -37,7 +37,15 @@ def train(model_args, data_args, training_args, batches, step_args: TrainingArgu
         max_steps=getattr(training_args, "max_steps", 1000),
         warmup_ratio=getattr(training_args, "warmup_ratio", 0.01),
         gradient_accumulation_steps=getattr(training_args, "gradient_accumulation_steps", 1),
-        llrd=getattr(training_args, "llrd", False), llm_llrd=getattr(training_args, "llm_llrd", False)))
+        llrd=getattr(training_args, "llrd", False), llm_llrd=getattr(training_args, "llm_llrd", False),
+        gradient_checkpointing=getattr(training_args, "gradient_checkpointing", False),
+        output_dir=getattr(training_args, "output_dir", None), save_steps=getattr(training_args, "save_steps", 0) or 0,
+        save_total_limit=getattr(training_args, "save_total_limit", 2) or 0))
+    # train.py:56-59: trainer.train(resume_from_checkpoint=True) when output_dir already holds checkpoint-*
+    if trainer.args.output_dir:
+        resumed = trainer.resume_from_checkpoint(True)
+        if resumed and int(os.environ.get("RANK", "0")) == 0:
+            print(f"resumed from {resumed} at step {trainer.global_step}", flush=True)
     trainer.train(batches)
     out = getattr(training_args, "output_dir", None)
     if out and int(os.environ.get("RANK", "0")) == 0:

@@ -8,8 +8,14 @@ the HF `Trainer._inner_training_loop` + FSDP + autograd machinery underneath it 
     lr-multiplier / weight-decay tables, bf16 weights and state like the reference (builder.py:110-114,163).
   * `training_step(batch)` — explicit forward + backward of MMGPTLlamaForCausalLM.forward
     (llama_mmgpt.py:53-112) as a fixed schedule of kernel launches (no autograd graph): per decoder layer
-    7 forward and 13 backward kernels, activations kept in HBM (17 GB at S=4096 — no re-computation, the
-    reference needs gradient checkpointing, pretrain.sh:35).
+    7 forward and 13 backward kernels, activations kept in HBM (17 GB at S=4096 for the 7B model — the reference
+    needs gradient checkpointing for that, pretrain.sh:35).  `gradient_checkpointing=True` is that policy here:
+    only each layer's input is kept (L x [tokens, D]) and the layer forward is re-run into ONE shared activation
+    block right before its backward — what makes Merlin-13B at S=8192 (BASELINE config C5) fit next to 104 GB of
+    weights + gradients + AdamW moments.
+  * `save_checkpoint` / `resume_from_checkpoint` — `checkpoint-<step>` directories holding the weights (reference
+    state-dict names), the AdamW moments, the step counters and the RNG-free schedule state; `train()` resumes
+    from the newest one automatically like mmgpt/engine/train/train.py:56-59.
   * gradients are exchanged with bucketed NCCL all-reduces over slices of the flat gradient arena, launched
     while backward is still running (engine/train/dp.py); north_star: data-parallel only.
   * cosine schedule with warm-up ratio, gradient accumulation, global-norm clipping (HF defaults used by
@@ -20,7 +26,12 @@ Everything on the path trains: language model, lm_head, embeddings, projector an
 """
 from __future__ import annotations
 
+import glob
+import json
 import math
+import os
+import re
+import shutil
 from dataclasses import dataclass
 from typing import Dict, List, Optional
 
@@ -51,6 +62,10 @@ class TrainingArguments:
     llrd: bool = False
     llm_llrd: bool = False
     bucket_mb: int = 256
+    gradient_checkpointing: bool = False   # pretrain.sh:35: keep only each layer's input, re-run the layer in backward
+    output_dir: Optional[str] = None       # checkpoint-<step> directories (pretrain.sh:19-22: save_steps / save_total_limit)
+    save_steps: int = 0                    # 0 = never
+    save_total_limit: int = 2
 
 
 def cosine_lr(step: int, base_lr: float, max_steps: int, warmup_ratio: float) -> float:
@@ -137,11 +152,21 @@ class MMGPTTrainer:
         # per-layer blocks whose first slot is x_in, so layer i writes its output straight into block i+1
         bufs = self._layer_buffers(B, S)
         x_final = bufs["x_final"]
-        for i in range(L):
-            x_src = x if i == 0 else bufs["saved"][i]
-            x_dst = bufs["saved"][i + 1] if i + 1 < L else x_final
-            ops.decoder_layer_forward_train(self._layer_weights(i), x_src, x_dst, bufs["saved"][i], cos, sin, seqlens,
-                                            B, S, D, H, cfg.intermediate_size, cfg.rms_norm_eps)
+        recompute = self.args.gradient_checkpointing
+        if recompute:
+            # forward keeps x_in of every layer only: layer i reads xin[i] and writes xin[i + 1]
+            for i in range(L):
+                x_dst = bufs["xin"][i + 1] if i + 1 < L else x_final
+                if i == 0:
+                    bufs["xin"][0].copy_(x)
+                ops.decoder_layer_forward_train(self._layer_weights(i), bufs["xin"][i], x_dst, bufs["saved"][0], cos, sin,
+                                                seqlens, B, S, D, H, cfg.intermediate_size, cfg.rms_norm_eps)
+        else:
+            for i in range(L):
+                x_src = x if i == 0 else bufs["saved"][i]
+                x_dst = bufs["saved"][i + 1] if i + 1 < L else x_final
+                ops.decoder_layer_forward_train(self._layer_weights(i), x_src, x_dst, bufs["saved"][i], cos, sin, seqlens,
+                                                B, S, D, H, cfg.intermediate_size, cfg.rms_norm_eps)
         hn = ops.rmsnorm(x_final, m.norm_w, cfg.rms_norm_eps)
         # lm_head + shifted CE, forward and backward, one library call each (merlin_lmhead_ce_forward / _backward)
         logits, loss, loss_acc = ops.lmhead_ce_forward(hn, model.lm_head_w, labels_dev, B, S, IGNORE_INDEX)
@@ -158,7 +183,15 @@ class MMGPTTrainer:
                                     g(p + "mlp.gate_up_proj.weight").data_ptr(), g(p + "mlp.down_proj.weight").data_ptr(),
                                     self._f32[p + "input_layernorm.weight"].data_ptr(),
                                     self._f32[p + "post_attention_layernorm.weight"].data_ptr())
-            ops.decoder_layer_backward(self._layer_weights(i), grads, bufs["saved"][i], dx, bufs["ws"], cos, sin,
+            if recompute:
+                if i != L - 1:   # the shared block still holds layer L-1's activations right after the forward
+                    ops.decoder_layer_forward_train(self._layer_weights(i), bufs["xin"][i], bufs["scratch"],
+                                                    bufs["saved"][0], cos, sin, seqlens, B, S, D, H,
+                                                    cfg.intermediate_size, cfg.rms_norm_eps)
+                block = bufs["saved"][0]
+            else:
+                block = bufs["saved"][i]
+            ops.decoder_layer_backward(self._layer_weights(i), grads, block, dx, bufs["ws"], cos, sin,
                                        seqlens, B, S, D, H, cfg.intermediate_size, cfg.rms_norm_eps, acc)
             self._ready_after(p + "input_layernorm.weight")
         # embeddings + projector
@@ -192,18 +225,24 @@ class MMGPTTrainer:
 
     def _layer_buffers(self, B: int, S: int):
         """Persistent activation blocks (one per decoder layer) + backward workspace for this batch shape."""
-        if getattr(self, "_buf_key", None) != (B, S):
+        key = (B, S, self.args.gradient_checkpointing)
+        if getattr(self, "_buf_key", None) != key:
+            self._bufs = None                      # release the old shape's blocks before allocating the new ones
             cfg = self.model.config
             D, FF, H, L = cfg.hidden_size, cfg.intermediate_size, cfg.num_attention_heads, cfg.num_hidden_layers
             L_ = _lib.load()
             dev = self.model.device
             nbytes = L_.merlin_decoder_layer_saved_bytes(B * S, D, FF, H, B, S)
+            n_blocks = 1 if self.args.gradient_checkpointing else L
             self._bufs = dict(
-                saved=[torch.empty(nbytes, dtype=torch.uint8, device=dev) for _ in range(L)],
+                saved=[torch.empty(nbytes, dtype=torch.uint8, device=dev) for _ in range(n_blocks)],
                 ws=torch.empty(L_.merlin_decoder_layer_backward_workspace_bytes(B * S, D, FF, H, B, S), dtype=torch.uint8,
                                device=dev),
                 x_final=torch.empty((B * S, D), dtype=torch.bfloat16, device=dev))
-            self._buf_key = (B, S)
+            if self.args.gradient_checkpointing:
+                self._bufs["xin"] = [torch.empty((B * S, D), dtype=torch.bfloat16, device=dev) for _ in range(L)]
+                self._bufs["scratch"] = torch.empty((B * S, D), dtype=torch.bfloat16, device=dev)
+            self._buf_key = key
         return self._bufs
 
     def _ready_after(self, name: str):
@@ -257,12 +296,88 @@ class MMGPTTrainer:
     def grad_norm(self) -> float:
         return float(self._sumsq[0].sqrt())
 
+    # ------------------------------------------------------------------ checkpoint / resume
+    # Reference: HF Trainer `save_strategy steps` + `save_total_limit` (pretrain.sh:19-22) and the auto-resume of
+    # mmgpt/engine/train/train.py:56-59 (`resume_from_checkpoint=True` when output_dir holds checkpoint-*).
+    @staticmethod
+    def checkpoints(output_dir: str) -> List[str]:
+        """checkpoint-<step> directories under output_dir, oldest first."""
+        found = [(int(m.group(1)), d) for d in glob.glob(os.path.join(output_dir, "checkpoint-*"))
+                 if (m := re.search(r"checkpoint-(\d+)$", d)) and os.path.isdir(d)]
+        return [d for _, d in sorted(found)]
+
+    def _layout(self):
+        return [[n, *self.arena.offsets[n][:2]] for n in self.arena.names]
+
+    def save_checkpoint(self, output_dir: Optional[str] = None) -> Optional[str]:
+        """Weights (reference state-dict names, `pytorch_model.bin` + config.json), AdamW moments (flat bf16 arenas +
+        the layout they were saved with) and the step counters -> output_dir/checkpoint-<global_step>.  Rank 0
+        writes (replicas are bit-identical); older checkpoints beyond save_total_limit are removed."""
+        output_dir = output_dir or self.args.output_dir
+        if not output_dir:
+            raise ValueError("save_checkpoint: no output_dir")
+        rank = int(os.environ.get("RANK", "0"))
+        path = os.path.join(output_dir, f"checkpoint-{self.global_step}")
+        if rank == 0:
+            tmp = path + ".tmp"
+            shutil.rmtree(tmp, ignore_errors=True)
+            os.makedirs(tmp)
+            self.model.save_pretrained(tmp)
+            torch.save({"exp_avg": self.arena.exp_avg.cpu(), "exp_avg_sq": self.arena.exp_avg_sq.cpu(),
+                        "layout": self._layout(), "chunk": self.arena.chunk}, os.path.join(tmp, "optimizer.pt"))
+            a = self.args
+            json.dump({"global_step": self.global_step, "micro_step": self.micro_step,
+                       "last_lr": getattr(self, "last_lr", None),
+                       "args": {k: getattr(a, k) for k in ("learning_rate", "weight_decay", "adam_beta1", "adam_beta2",
+                                                          "adam_epsilon", "max_grad_norm", "warmup_ratio", "max_steps",
+                                                          "gradient_accumulation_steps", "llrd", "llm_llrd")}},
+                      open(os.path.join(tmp, "trainer_state.json"), "w"), indent=1)
+            shutil.rmtree(path, ignore_errors=True)
+            os.replace(tmp, path)                       # a checkpoint directory appears only when it is complete
+            limit = self.args.save_total_limit
+            if limit and limit > 0:
+                for old in self.checkpoints(output_dir)[:-limit]:
+                    shutil.rmtree(old, ignore_errors=True)
+        if self.reducer.world > 1:
+            import torch.distributed as dist
+            dist.barrier()
+        return path
+
+    def resume_from_checkpoint(self, checkpoint=True) -> Optional[str]:
+        """checkpoint: a checkpoint-<step> directory, or True = the newest one under args.output_dir (None if there
+        is none).  Restores weights into the parameter arena, the AdamW moments and the counters; the LR schedule
+        is a pure function of global_step, so nothing else needs saving."""
+        if checkpoint is True:
+            found = self.checkpoints(self.args.output_dir) if self.args.output_dir else []
+            if not found:
+                return None
+            checkpoint = found[-1]
+        state = json.load(open(os.path.join(checkpoint, "trainer_state.json")))
+        opt = torch.load(os.path.join(checkpoint, "optimizer.pt"), map_location="cpu")
+        if opt["layout"] != self._layout() or opt["chunk"] != self.arena.chunk:
+            raise RuntimeError("resume_from_checkpoint: the optimizer state was saved for another set / order of "
+                               "trainable parameters")
+        sd = self.model._read_checkpoint(checkpoint)
+        self.model.load_state_dict(sd, strict=False)    # parameters are views of the arena: this fills it
+        self.arena.exp_avg.copy_(opt["exp_avg"])
+        self.arena.exp_avg_sq.copy_(opt["exp_avg_sq"])
+        self.global_step, self.micro_step = int(state["global_step"]), int(state["micro_step"])
+        if state.get("last_lr") is not None:
+            self.last_lr = state["last_lr"]
+        return checkpoint
+
     def train(self, batches, log_every: int = 1):
         """Minimal loop with the reference's logging cadence (--logging_steps 1): loss, lr, tokens/s."""
         import time
+        a = self.args
         for step, batch in enumerate(batches):
+            if a.max_steps and self.global_step >= a.max_steps:
+                break
             t0 = time.perf_counter()
+            before = self.global_step
             loss = self.training_step(batch)
+            if a.save_steps and a.output_dir and self.global_step != before and self.global_step % a.save_steps == 0:
+                self.save_checkpoint()
             if (step + 1) % log_every == 0:
                 torch.cuda.synchronize()
                 dt = time.perf_counter() - t0

@@ -304,6 +304,18 @@ def test_elementwise_backward_kernels():
     close(dx, xr.grad + dres.float())
     close(dw, wr.grad, tol=2.0 ** -9)
     close(ops.rmsnorm_bwd(x, w, dy, None, None, 1e-5), xr.grad)
+    # every width class of the warp-per-row kernel (D <= 256 / 1024 / 2048 / 4096 / 5120) and the CTA-per-row
+    # fallback (6144), with a row count that is not a multiple of the 8 rows a CTA takes per sweep
+    for D2, M2 in ((256, 77), (1024, 130), (1536, 9), (5120, 1001), (6144, 50)):
+        x2 = torch.randn(M2, D2, device=DEV).to(torch.bfloat16)
+        w2 = (1 + 0.1 * torch.randn(D2, device=DEV)).to(torch.bfloat16)
+        dy2 = torch.randn(M2, D2, device=DEV).to(torch.bfloat16)
+        dr2 = torch.randn(M2, D2, device=DEV).to(torch.bfloat16)
+        xr2, wr2 = x2.float().requires_grad_(True), w2.float().requires_grad_(True)
+        (wr2 * (xr2 * torch.rsqrt(xr2.pow(2).mean(-1, keepdim=True) + 1e-5))).backward(dy2.float())
+        dw2 = torch.full((D2,), 0.5, dtype=torch.float32, device=DEV)          # accumulates onto what is there
+        close(ops.rmsnorm_bwd(x2, w2, dy2, dr2, dw2, 1e-5), xr2.grad + dr2.float())
+        close(dw2 - 0.5, wr2.grad, tol=2.0 ** -9)
     # swiglu
     g = torch.randn(M, FF, device=DEV).to(torch.bfloat16)
     u = torch.randn(M, FF, device=DEV).to(torch.bfloat16)

@@ -2,6 +2,8 @@
 (the oracle's forward is pinned to the real reference, so its autograd gradients are the reference's),
 plus one optimizer step and a short loss-goes-down run.  Tolerance: cosine >= 0.999 and
 max|Δ| <= 5% of max|ref| per parameter tensor (bf16 activations and gradients vs fp32)."""
+import os
+
 import pytest
 import torch
 
@@ -234,6 +236,7 @@ def test_local_shards_to_training_step_end_to_end(tmp_path):
     parts = build_dataloader(Tok(), data_args)
     ds, collate = parts["train_dataset"], parts["data_collator"]
     assert len(ds) == 4
+    ds.shuffle = False        # file order, so that the records can be restated below (the seeded shuffles are covered on CPU)
     batch = collate([ds[0], ds[1]])
     assert batch["input_ids"].shape[0] == 2 and [tuple(i.shape) for i in batch["images"]] == [(2, 3, 56, 56)] * 2
     assert int((batch["input_ids"] == cfg.im_patch_token).sum()) == 2 * 2 * cfg.num_patches
@@ -255,3 +258,64 @@ def test_local_shards_to_training_step_end_to_end(tmp_path):
     losses = [trainer.training_step(dev_batch).item() for _ in range(8)]
     assert abs(losses[0] - ref["loss"].item()) <= 2e-3, (losses[0], ref["loss"].item())
     assert losses[-1] < losses[0] - 0.5, losses
+
+
+def _tiny_trainer(**kw):
+    g, cfg = load_golden("tiny_conv")
+    sd = O.init_state_dict(cfg, seed=0)
+    model = build_product_model(cfg, sd)
+    for p in model.parameters():
+        p.requires_grad_(True)
+    for p in model.get_model().vision_tower.parameters():
+        p.requires_grad_(False)
+    trainer = MMGPTTrainer(model, TrainingArguments(learning_rate=2e-3, warmup_ratio=0.0, max_steps=20, **kw))
+    batch = {k: g[k] for k in ("input_ids", "labels", "attention_mask")}
+    batch["images"] = [im.to(DEV) for im in g["images"]]
+    return trainer, batch
+
+
+def test_activation_recompute_gives_the_same_gradients():
+    """gradient_checkpointing (pretrain.sh:35): only layer inputs are kept, each layer forward is re-run before its
+    backward into one shared activation block — same kernels on the same inputs, so the gradients are identical
+    up to the fp32 atomics of the attention dq reduction."""
+    a, batch = _tiny_trainer()
+    b, _ = _tiny_trainer(gradient_checkpointing=True)
+    for t in (a, b):
+        t.args.max_grad_norm = 0.0
+        with torch.no_grad():
+            t._last_micro, t._fold_ptr = True, 0
+            t.reducer.start_step()
+            t.loss = t._forward_backward(batch, accumulate=False, grad_scale=1.0)
+    assert abs(a.loss.item() - b.loss.item()) <= 1e-6
+    assert len(b._bufs["saved"]) == 1 and len(b._bufs["xin"]) == b.model.config.num_hidden_layers
+    ga, gb = a.arena.grads.float(), b.arena.grads.float()
+    assert (ga - gb).abs().max().item() <= 2.0 ** -6 * ga.abs().max().item()      # a bf16 ulp or two: the dq reduction order
+    la = [a.training_step(batch).item() for _ in range(4)]
+    lb = [b.training_step(batch).item() for _ in range(4)]
+    assert max(abs(x - y) for x, y in zip(la, lb)) <= 2e-2 and la[-1] < la[0]
+
+
+def test_checkpoint_resume_restores_weights_moments_and_counters(tmp_path):
+    """HF Trainer save_steps / save_total_limit + auto-resume (pretrain.sh:19-22, train.py:56-59)."""
+    out = str(tmp_path / "run")
+    a, batch = _tiny_trainer(output_dir=out, save_steps=2, save_total_limit=2)
+    a.train([batch] * 6, log_every=100)
+    assert [os.path.basename(d) for d in MMGPTTrainer.checkpoints(out)] == ["checkpoint-4", "checkpoint-6"]
+    assert {"config.json", "optimizer.pt", "pytorch_model.bin", "trainer_state.json"} <= set(
+        os.listdir(os.path.join(out, "checkpoint-6")))
+    b, _ = _tiny_trainer(output_dir=out, save_steps=0)
+    assert b.resume_from_checkpoint(True).endswith("checkpoint-6")
+    assert b.global_step == 6 and b.micro_step == 6
+    assert torch.equal(b.arena.params, a.arena.params)
+    assert torch.equal(b.arena.exp_avg, a.arena.exp_avg) and torch.equal(b.arena.exp_avg_sq, a.arena.exp_avg_sq)
+    la, lb = a.training_step(batch).item(), b.training_step(batch).item()
+    assert abs(la - lb) <= 1e-3 and b.global_step == 7 and abs(a.last_lr - b.last_lr) < 1e-12
+    # a trainer over a different set of trainable parameters refuses the optimizer state
+    g, cfg = load_golden("tiny_conv")
+    other = build_product_model(cfg, O.init_state_dict(cfg, seed=0))
+    other.lm_head_w.requires_grad_(True)
+    c = MMGPTTrainer(other, TrainingArguments(output_dir=out))
+    with pytest.raises(RuntimeError, match="another set"):
+        c.resume_from_checkpoint(True)
+    empty, _ = _tiny_trainer(output_dir=str(tmp_path / "nothing"))
+    assert empty.resume_from_checkpoint(True) is None
