@@ -22,7 +22,7 @@ static int launch_attn(cudaStream_t stream, const CUtensorMap& tq, const CUtenso
                                        cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::kSmemBytes); });
   MB_CHECK_CUDA(attr_rc);
   const int nq = (p.S + kAttnBlock - 1) / kAttnBlock;
-  dim3 grid(static_cast<unsigned>(nq), static_cast<unsigned>(p.H), static_cast<unsigned>(p.B));
+  dim3 grid(static_cast<unsigned>(p.H), static_cast<unsigned>(nq), static_cast<unsigned>(p.B));
   attn_fwd_kernel<HD, kCausal><<<grid, kAttnThreads, Cfg::kSmemBytes, stream>>>(tq, to, p);
   MB_CHECK_CUDA(cudaGetLastError());
   return MERLIN_OK;
@@ -38,7 +38,7 @@ static int launch_attn2(cudaStream_t stream, const CUtensorMap& tq, const CUtens
                                        cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::kSmemBytes); });
   MB_CHECK_CUDA(attr_rc);
   const int nq = (p.S + kAttnBlock - 1) / kAttnBlock;
-  dim3 grid(static_cast<unsigned>((nq + 1) / 2), static_cast<unsigned>(p.H), static_cast<unsigned>(p.B));
+  dim3 grid(static_cast<unsigned>(p.H), static_cast<unsigned>((nq + 1) / 2), static_cast<unsigned>(p.B));
   attn_fwd2_kernel<HD, kCausal><<<grid, kAttn2Threads, Cfg::kSmemBytes, stream>>>(tq, to, p);
   MB_CHECK_CUDA(cudaGetLastError());
   return MERLIN_OK;
@@ -146,6 +146,10 @@ extern "C" int merlin_flash_attn_bwd(void* stream, const void* qkv, int64_t ld_q
   p.dq_accum = dq_acc;
   p.dqkv = static_cast<__nv_bfloat16*>(dqkv);
   p.ld_dqkv = ld_dqkv;
+  {
+    const char* e = getenv("MERLIN_ATTN_BWD_DBG");
+    p.dbg = e ? atoi(e) : 0;
+  }
 
   CUtensorMap tq, tdo;
   {
@@ -170,7 +174,7 @@ extern "C" int merlin_flash_attn_bwd(void* stream, const void* qkv, int64_t ld_q
     uint32_t box[2] = {32, kBwdBlock};
     if ((rc = make_tmap_f32(&tdq, dq_acc, 2, dims, str, box)) != MERLIN_OK) return rc;
   }
-  dim3 grid(static_cast<unsigned>((S + kBwdBlock - 1) / kBwdBlock), static_cast<unsigned>(H),
+  dim3 grid(static_cast<unsigned>(H), static_cast<unsigned>((S + kBwdBlock - 1) / kBwdBlock),
             static_cast<unsigned>(B));
   auto launch = [&](auto kernel, int smem) -> int {
     MB_CHECK_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
@@ -192,3 +196,10 @@ extern "C" int merlin_flash_attn_bwd(void* stream, const void* qkv, int64_t ld_q
   MB_CHECK_CUDA(cudaGetLastError());
   return MERLIN_OK;
 }
+
+#ifdef MERLIN_ATTN_TRACE
+extern "C" int merlin_debug_attn_bwd_trace(unsigned long long* host_out) {
+  MB_CHECK_CUDA(cudaMemcpyFromSymbol(host_out, mb::g_attn_bwd_trace, sizeof(unsigned long long) * 64 * 16));
+  return MERLIN_OK;
+}
+#endif

@@ -65,8 +65,9 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid_constan
 
   const int warp = threadIdx.x >> 5;
   const int nq = (p.S + kAttnBlock - 1) / kAttnBlock;
-  const int q_tile = kCausal ? (nq - 1 - static_cast<int>(blockIdx.x)) : static_cast<int>(blockIdx.x);
-  const int head = blockIdx.y;
+  // grid = (heads, query tiles, batch): heads vary fastest, so CTAs are dispatched longest-first ACROSS heads
+  const int q_tile = kCausal ? (nq - 1 - static_cast<int>(blockIdx.y)) : static_cast<int>(blockIdx.y);
+  const int head = blockIdx.x;
   const int batch = blockIdx.z;
   const int q0 = q_tile * kAttnBlock;
   const int len = p.seqlens ? p.seqlens[batch] : p.S;

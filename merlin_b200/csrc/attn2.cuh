@@ -16,6 +16,11 @@ namespace mb {
 
 constexpr int kAttn2Threads = 384;
 
+#ifndef MERLIN_ATTN_POLY_EVERY
+#define MERLIN_ATTN_POLY_EVERY 2     // every 2nd pair -> 25 % of the exponentials on the FMA pipe
+#endif
+constexpr int kPolyEvery = MERLIN_ATTN_POLY_EVERY;
+
 template <int HD>
 struct Attn2Cfg {
   static constexpr int kAtoms = HD / 64;
@@ -71,8 +76,9 @@ attn_fwd2_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid_consta
   const int warp = threadIdx.x >> 5;
   const int nq = (p.S + kAttnBlock - 1) / kAttnBlock;
   const int npairs = (nq + 1) / 2;
-  const int pair = kCausal ? (npairs - 1 - static_cast<int>(blockIdx.x)) : static_cast<int>(blockIdx.x);
-  const int head = blockIdx.y;
+  // grid = (heads, tile pairs, batch): heads vary fastest, so CTAs are dispatched longest-first ACROSS heads
+  const int pair = kCausal ? (npairs - 1 - static_cast<int>(blockIdx.y)) : static_cast<int>(blockIdx.y);
+  const int head = blockIdx.x;
   const int batch = blockIdx.z;
   const int len = p.seqlens ? p.seqlens[batch] : p.S;
   const int n_len = (len + kAttnBlock - 1) / kAttnBlock;
@@ -232,10 +238,14 @@ attn_fwd2_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid_consta
       }
       float rowsum = 0.f;
       uint32_t pk[64];
+      // kPolyEvery-th exponential runs as a cubic on the FMA pipe instead of ex2.approx: with every exponent on the
+      // 16-per-clock MUFU unit the kernel measured XU = 48 % next to tensor = 48 % (profiles/r1_attn_v2_metrics.csv)
 #pragma unroll
       for (int c = 0; c < 128; c += 2) {
-        const float p0 = fast_exp2(fmaf(__uint_as_float(s[c]), p.scale_log2e, -m_new));
-        const float p1 = fast_exp2(fmaf(__uint_as_float(s[c + 1]), p.scale_log2e, -m_new));
+        const float x0 = fmaf(__uint_as_float(s[c]), p.scale_log2e, -m_new);
+        const float x1 = fmaf(__uint_as_float(s[c + 1]), p.scale_log2e, -m_new);
+        const float p0 = fast_exp2(x0);
+        const float p1 = ((c >> 1) % kPolyEvery == kPolyEvery - 1) ? exp2_poly3(x1) : fast_exp2(x1);
         rowsum += p0 + p1;
         pk[c >> 1] = pack_bf16(p0, p1);
       }
