@@ -79,6 +79,29 @@ class LibraryComm:
             pass
 
 
+class NcclBuffer:
+    """Device memory from ncclMemAlloc (merlin_dp_mem_alloc) exposed to torch through __cuda_array_interface__.
+    NCCL can register such a buffer (merlin_dp_register): with NVLS the switch then reduces straight out of the
+    gradient arena — no staging copies through NCCL's own buffers, i.e. less SM work per byte."""
+
+    def __init__(self, nbytes: int):
+        from .... import lib as _lib
+        self._lib, self._check = _lib.load(), _lib.check
+        ptr = ctypes.c_void_p()
+        self._check(self._lib.merlin_dp_mem_alloc(ctypes.byref(ptr), int(nbytes)), "merlin_dp_mem_alloc")
+        self.ptr, self.nbytes = ptr.value, int(nbytes)
+        self.__cuda_array_interface__ = {"shape": (self.nbytes,), "typestr": "|u1", "data": (self.ptr, False),
+                                         "version": 3, "strides": None}
+
+    def tensor(self, dtype: torch.dtype) -> torch.Tensor:
+        return torch.as_tensor(self, device=torch.device("cuda", torch.cuda.current_device())).view(dtype)
+
+    def free(self):
+        if self.ptr:
+            self._lib.merlin_dp_mem_free(ctypes.c_void_p(self.ptr))
+            self.ptr = 0
+
+
 class GradBucketReducer:
     def __init__(self, flat_grads: torch.Tensor, bucket_elems: int = 128 * 1024 * 1024, group=None,
                  backend: Optional[str] = None, max_ctas: Optional[int] = None, sm_reserve: Optional[int] = None):
@@ -97,14 +120,35 @@ class GradBucketReducer:
         backend = backend or os.environ.get("MERLIN_DP_BACKEND", "library")
         if backend not in ("library", "torch"):
             raise ValueError(f"MERLIN_DP_BACKEND={backend!r}: expected 'library' or 'torch'")
-        self.max_ctas = int(os.environ.get("MERLIN_DP_CTAS", "8")) if max_ctas is None else int(max_ctas)
+        # measured (profiles/r2_dp_overlap_sweep_n{2,8}.md): 8 CTAs finish the 13.55 GB under backward on 2 GPUs (ring),
+        # on 8 GPUs (NVLS, 1.75x the traffic per GPU) it takes 16; fewer is slower than backward, more costs SMs
+        default_ctas = "8" if self.world <= 2 else "16"
+        self.max_ctas = int(os.environ.get("MERLIN_DP_CTAS", default_ctas)) if max_ctas is None else int(max_ctas)
         if sm_reserve is None:
             sm_reserve = int(os.environ.get("MERLIN_DP_SM_RESERVE", str((self.max_ctas + 1) // 2 * 2)))
         self.sm_reserve = int(sm_reserve)
         self.backend = "torch"
+        self.registered = None
         if self.world > 1 and flat_grads.is_cuda and backend == "library":
             self.lib_comm = LibraryComm(group, self.max_ctas)
             self.backend = "library"
+
+    def adopt_registered_arena(self, arena) -> bool:
+        """MERLIN_DP_REGISTER=1: move the gradient arena into an ncclMemAlloc'ed buffer and register it with the
+        communicator (user-buffer registration: NVLS reduces in place).  Returns False when not applicable."""
+        if self.lib_comm is None or os.environ.get("MERLIN_DP_REGISTER", "0") != "1":
+            return False
+        buf = NcclBuffer(arena.grads.numel() * arena.grads.element_size())
+        t = buf.tensor(arena.grads.dtype)
+        t.zero_()
+        arena.grads = t
+        self.flat = t
+        handle = ctypes.c_void_p()
+        L = self.lib_comm
+        L._check(L._lib.merlin_dp_register(L.handle, ctypes.c_void_p(buf.ptr), buf.nbytes, ctypes.byref(handle)),
+                 "merlin_dp_register")
+        self.registered = (buf, handle)
+        return True
 
     def start_step(self):
         self.next_bucket = 0
@@ -156,6 +200,10 @@ class GradBucketReducer:
 
     def close(self):
         self._set_budget(False)
+        if self.registered is not None and self.lib_comm is not None:
+            buf, handle = self.registered
+            self.lib_comm._lib.merlin_dp_deregister(self.lib_comm.handle, handle)
+            self.registered = None
         if self.lib_comm is not None:
             self.lib_comm.close()
             self.lib_comm = None

@@ -95,6 +95,7 @@ class MMGPTTrainer:
         self.arena = ParamArena(named, lambda n, s: param_hyper(n, s, scale, a.weight_decay))
         self.names = [n for n, _ in named]
         self.reducer = GradBucketReducer(self.arena.grads, bucket_elems=a.bucket_mb * 1024 * 1024 // 2)
+        self.reducer.adopt_registered_arena(self.arena)      # optional NCCL user-buffer registration of the gradients
         dev = self.arena.params.device
         self._sumsq = torch.zeros(4, dtype=torch.float32, device=dev)  # [0] = Σg², [2:4] = fixed-point accumulator
         # fp32 accumulators for 1-D gradients (norm weights, projector bias)

@@ -130,10 +130,36 @@ def make_case(ref, name: str, cfg: O.OracleConfig, batch, gen_tokens: int):
     print(f"  wrote {path} ({os.path.getsize(path) / 1024:.0f} KiB)")
 
 
+def make_llrd_golden(ref):
+    """Pins the optimizer grouping (N1) against the reference's OWN `get_param_groups` + `vit_lr_scale_func` /
+    `llm_lr_scale_func` (mmgpt/utils/llrd_utils.py:4-79), called the way MMGPTTrainer.create_optimizer does
+    (mmgpt/engine/train/trainer.py:53-66), on the parameter names / shapes of an assembled reference model."""
+    import json
+    cfg = O.OracleConfig.tiny(vit_layers=24)          # real CLIP depth: the LLRD exponent depends on the layer index
+    model = build_reference_model(ref, cfg, O.init_state_dict(cfg, seed=0))
+    named = [(n, p) for n, p in model.named_parameters()]
+    out = {"names": [[n, list(p.shape)] for n, p in named], "cases": {}}
+    U = ref.llrd_utils
+    for tag, fn in (("llrd", U.vit_lr_scale_func), ("llm_llrd", U.llm_lr_scale_func), ("none", None)):
+        fake = type("M", (), {"named_parameters": staticmethod(lambda: named)})
+        groups = U.get_param_groups(fake, None, fn, 1e-3, 0.05)
+        ids = {id(p): n for n, p in named}
+        out["cases"][tag] = [{"lr": g["lr"], "weight_decay": g["weight_decay"], "params": [ids[id(p)] for p in g["params"]]}
+                             for g in groups]
+        mine = O.param_groups([(n, tuple(p.shape)) for n, p in named], 1e-3, 0.05, llrd=(tag == "llrd")) if tag != "llm_llrd" else None
+        if mine is not None:
+            assert [(g["lr"], g["weight_decay"], g["names"]) for g in mine] == \
+                [(g["lr"], g["weight_decay"], g["params"]) for g in out["cases"][tag]], f"oracle param_groups != reference ({tag})"
+    path = os.path.join(ROOT, "tests", "golden", "llrd_groups.json")
+    json.dump(out, open(path, "w"))
+    print(f"  llrd: {len(named)} parameters, {[len(v) for v in out['cases'].values()]} groups -> {path}")
+
+
 def main():
     torch.manual_seed(0)
     torch.set_num_threads(8)
     ref = import_reference()
+    make_llrd_golden(ref)
     cfg = O.OracleConfig.tiny()
     # two samples, 1 and 2 images, S=48 (P' = 4 visual tokens per image at 56 px / stride 2)
     make_case(ref, "tiny_conv", cfg, O.synthetic_batch(cfg, 2, 48, [1, 2], seed=1234), gen_tokens=12)

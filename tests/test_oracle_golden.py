@@ -112,3 +112,40 @@ def test_oracle_autograd_matches_reference_golden(name):
         assert float(leaves[k].grad.norm()) == pytest.approx(norm, rel=1e-4, abs=1e-7), k
     for k, probe in g["ref_grad_probe"].items():
         torch.testing.assert_close(leaves[k].grad.flatten()[:64], probe, rtol=1e-4, atol=1e-7)
+
+
+def test_llrd_param_groups_match_the_reference_function_outputs():
+    """tests/golden/llrd_groups.json holds what the reference's OWN get_param_groups (+ vit_lr_scale_func /
+    llm_lr_scale_func, mmgpt/utils/llrd_utils.py:4-79, called as MMGPTTrainer.create_optimizer does) returned for the
+    414 parameters of an assembled reference model with the real 24-layer CLIP depth (oracle/make_golden.py).  The
+    oracle's grouping, the product's get_param_groups mirror and the per-parameter (lr multiplier, weight decay)
+    tables the fused AdamW kernel consumes must all reproduce it; when oracle/_ref is importable the reference
+    function is also called live."""
+    import json
+    import os
+    from helpers import GOLDEN_DIR
+    from merlin_b200.mmgpt.utils import llrd_utils as P
+    gold = json.load(open(os.path.join(GOLDEN_DIR, "llrd_groups.json")))
+    named = [(n, tuple(s)) for n, s in gold["names"]]
+    fns = {"llrd": P.vit_lr_scale_func, "llm_llrd": P.llm_lr_scale_func, "none": None}
+    for tag, want in gold["cases"].items():
+        got = P.get_param_groups(named, None, fns[tag], 1e-3, 0.05)
+        assert [(g["lr"], g["weight_decay"], g["params"]) for g in got] == \
+            [(g["lr"], g["weight_decay"], g["params"]) for g in want], tag
+        by_name = {n: g for g in want for n in g["params"]}
+        for n, shape in named:                       # what the AdamW kernel's per-chunk tables are built from
+            mult, wd = P.param_hyper(n, shape, fns[tag], 0.05)
+            assert wd == by_name[n]["weight_decay"] and 1e-3 * mult == pytest.approx(by_name[n]["lr"], rel=1e-12), (tag, n)
+        if tag != "llm_llrd":
+            mine = O.param_groups(named, 1e-3, 0.05, llrd=(tag == "llrd"))
+            assert [(g["lr"], g["weight_decay"], g["names"]) for g in mine] == \
+                [(g["lr"], g["weight_decay"], g["params"]) for g in want], tag
+    from oracle import refmodel
+    if refmodel.available():
+        U = refmodel.import_reference().llrd_utils
+        params = [(n, torch.nn.Parameter(torch.empty(s))) for n, s in named]
+        live = U.get_param_groups(type("M", (), {"named_parameters": staticmethod(lambda: params)}), None,
+                                  U.vit_lr_scale_func, 1e-3, 0.05)
+        ids = {id(p): n for n, p in params}
+        assert [(g["lr"], g["weight_decay"], [ids[id(p)] for p in g["params"]]) for g in live] == \
+            [(g["lr"], g["weight_decay"], g["params"]) for g in gold["cases"]["llrd"]]
