@@ -424,7 +424,7 @@ def train_detail(model, input_ids_h, img_d, world, device, timed, steps=3):
         del hi, lo
         r = trainer.reducer
         out["exchange"] = {"backend": r.backend, "nccl_max_ctas": r.max_ctas, "sm_reserve": r.sm_reserve,
-                           "buckets": len(r.buckets)}
+                           "buckets": len(r.buckets), "registered_arena": r.registered is not None}
         r.exchange_enabled = False          # compute-only step on the same box (gradients stay local)
         trainer.training_step(batch)
         ms0, _ = timed(lambda: trainer.training_step(batch), steps)

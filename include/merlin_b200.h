@@ -61,6 +61,15 @@ int merlin_gemm_qkv_rope(void* stream, const void* A, int64_t lda, const void* W
                          void* qkv, int64_t ldc, const float* rope_cos, const float* rope_sin,
                          const int* positions, int M, int N, int K, int rope_cols, int seq_len,
                          int cta_group);
+/* Same GEMM with the KV-cache append fused into its epilogue (kv_cache == NULL: identical to the above): every
+ * staged [128 tokens x 64 columns] chunk of the rotated k block and of the v block is also written, by a second
+ * TMA store, into kv_cache[B, kv_capacity/32, H, 32, 256] at tokens 0 .. seq_len-1 (the layout of
+ * merlin_decoder_weights.kv_cache / merlin_kv_append).  M == B * seq_len; B > 1 needs seq_len % 128 == 0.
+ * Replaces the HF `past_key_value` tuple update of the prefill (HF:llama/modeling_llama.py, `use_cache=True`). */
+int merlin_gemm_qkv_rope_kv(void* stream, const void* A, int64_t lda, const void* Wqkv, int64_t ldb, void* qkv,
+                            int64_t ldc, const float* rope_cos, const float* rope_sin, const int* positions, int M,
+                            int N, int K, int rope_cols, int seq_len, void* kv_cache, int64_t kv_capacity, int B,
+                            int H, int cta_group);
 
 /* out[B,S,H*hd] = softmax(scale·QKᵀ + mask)·V for a packed qkv buffer [B,S,3*H*hd] ([q|k|v] blocks),
  * head_dim 64 or 128.  causal != 0 adds the causal mask; seqlens[b] (NULL = S) is the number of valid

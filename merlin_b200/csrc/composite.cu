@@ -26,11 +26,13 @@ int merlin_decoder_layer_forward(void* stream, const merlin_layer_weights* w, vo
   int rc;
   // x + Attn(RMSNorm(x))          (HF:llama/modeling_llama.py:303-333, monkey_patch.py:20-103)
   if ((rc = merlin_rmsnorm(stream, x, D, w->ln1_w, xn, D, M, D, eps)) != MERLIN_OK) return rc;
-  if ((rc = merlin_gemm_qkv_rope(stream, xn, D, w->qkv_w, D, qkv, 3 * D, rope_cos, rope_sin, nullptr, M, 3 * D, D,
-                                 2 * D, S, cta_group)) != MERLIN_OK)
+  // rotated keys and values of the S prompt tokens go to the cache from the GEMM's own epilogue (a second TMA store
+  // of the staged chunk); a batch whose samples are not tile-aligned falls back to the gather kernel
+  const bool fuse_kv = kv_cache != nullptr && (B == 1 || S % 128 == 0);
+  if ((rc = merlin_gemm_qkv_rope_kv(stream, xn, D, w->qkv_w, D, qkv, 3 * D, rope_cos, rope_sin, nullptr, M, 3 * D, D,
+                                    2 * D, S, fuse_kv ? kv_cache : nullptr, kv_capacity, B, H, cta_group)) != MERLIN_OK)
     return rc;
-  if (kv_cache != nullptr) {
-    // rotated keys and values of the S prompt tokens -> head-major cache [B, H, kv_capacity, 256]
+  if (kv_cache != nullptr && !fuse_kv) {
     if ((rc = merlin_kv_append(stream, qkv, 3 * D, kv_cache, kv_capacity, B, S, D, H, 0)) != MERLIN_OK) return rc;
   }
   if ((rc = merlin_flash_attn_fwd(stream, qkv, 3 * D, att, D, nullptr, seqlens, B, S, H, 128, 1, 0.f)) != MERLIN_OK)

@@ -26,8 +26,13 @@
 #include <cstdlib>
 #include <cstring>
 
+#ifndef MERLIN_MERGE_UNROLL
+#define MERLIN_MERGE_UNROLL 12
+#endif
+
 namespace mb {
 
+constexpr int kMergeUnroll = MERLIN_MERGE_UNROLL;   // attention partials in flight per round of the last-arriver merge
 constexpr int kSC = 8;                            // consumer warps per CTA
 constexpr int kSConsThreads = kSC * 32;
 constexpr int kSThreads = kSConsThreads + 32;     // + 1 producer warp (warp index kSC)
@@ -521,7 +526,8 @@ __device__ __forceinline__ void att_flush(AttState& s, int h, unsigned int idx, 
   for (int o = 16; o > 0; o >>= 1) M = fmaxf(M, __shfl_xor_sync(0xffffffffu, M, o));
   float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
   float L = 0.f;
-#pragma unroll 4
+  // 12 partials in flight per round: with 4 the ~37 partials of a head took ten dependent L2 round trips
+#pragma unroll kMergeUnroll
   for (int q = 0; q < n; ++q) {
     const float m = __ldcg(ml + 2 * q), l = __ldcg(ml + 2 * q + 1);
     const float w = (m == -INFINITY) ? 0.f : fast_exp2(m - M);

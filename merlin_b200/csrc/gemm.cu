@@ -161,7 +161,7 @@ int sm_budget() {
 
 template <int kCtaGroup, bool kAMN, bool kBMN>
 static int launch_gemm(cudaStream_t stream, const CUtensorMap& ta, const CUtensorMap& tb,
-                       const CUtensorMap& tc, const CUtensorMap& tr, const GemmParams& p) {
+                       const CUtensorMap& tc, const CUtensorMap& tr, const CUtensorMap& tkv, const GemmParams& p) {
   using Cfg = GemmCfg<kCtaGroup>;
   static std::once_flag once;
   static cudaError_t attr_rc = cudaSuccess;
@@ -186,13 +186,13 @@ static int launch_gemm(cudaStream_t stream, const CUtensorMap& ta, const CUtenso
   attr[0].val.clusterDim.z = 1;
   cfg.attrs = attr;
   cfg.numAttrs = 1;
-  MB_CHECK_CUDA(cudaLaunchKernelEx(&cfg, gemm_bf16_kernel<kCtaGroup, kAMN, kBMN>, ta, tb, tc, tr, p));
+  MB_CHECK_CUDA(cudaLaunchKernelEx(&cfg, gemm_bf16_kernel<kCtaGroup, kAMN, kBMN>, ta, tb, tc, tr, tkv, p));
   return MERLIN_OK;
 }
 
 int gemm_dispatch(cudaStream_t stream, const void* A, int64_t lda, const void* B, int64_t ldb, void* C,
                   int64_t ldc, const void* R, int64_t ldr, const GemmParams& p, int cta_group,
-                  bool a_mn = false, bool b_mn = false) {
+                  bool a_mn = false, bool b_mn = false, const CUtensorMap* kv_map = nullptr) {
   MB_CHECK_ARG(p.M > 0 && p.N > 0 && p.K > 0, "gemm: empty problem M=%d N=%d K=%d", p.M, p.N, p.K);
   MB_CHECK_ARG(cta_group == 1 || cta_group == 2, "gemm: cta_group must be 1 or 2, got %d", cta_group);
   MB_CHECK_ARG(A && B && C, "gemm: null operand");
@@ -234,14 +234,15 @@ int gemm_dispatch(cudaStream_t stream, const void* A, int64_t lda, const void* B
     tr = tc;
   }
   MB_CHECK_ARG(!(a_mn && !b_mn), "gemm: A MN-major with B K-major is not instantiated");
+  const CUtensorMap& tkv = kv_map ? *kv_map : tc;
   if (cta_group == 2) {
-    if (a_mn) return launch_gemm<2, true, true>(stream, ta, tb, tc, tr, p);
-    if (b_mn) return launch_gemm<2, false, true>(stream, ta, tb, tc, tr, p);
-    return launch_gemm<2, false, false>(stream, ta, tb, tc, tr, p);
+    if (a_mn) return launch_gemm<2, true, true>(stream, ta, tb, tc, tr, tkv, p);
+    if (b_mn) return launch_gemm<2, false, true>(stream, ta, tb, tc, tr, tkv, p);
+    return launch_gemm<2, false, false>(stream, ta, tb, tc, tr, tkv, p);
   }
-  if (a_mn) return launch_gemm<1, true, true>(stream, ta, tb, tc, tr, p);
-  if (b_mn) return launch_gemm<1, false, true>(stream, ta, tb, tc, tr, p);
-  return launch_gemm<1, false, false>(stream, ta, tb, tc, tr, p);
+  if (a_mn) return launch_gemm<1, true, true>(stream, ta, tb, tc, tr, tkv, p);
+  if (b_mn) return launch_gemm<1, false, true>(stream, ta, tb, tc, tr, tkv, p);
+  return launch_gemm<1, false, false>(stream, ta, tb, tc, tr, tkv, p);
 }
 
 }  // namespace mb
@@ -263,6 +264,7 @@ int merlin_gemm_bf16(void* stream, const void* A, int64_t lda, const void* B, in
   MB_CHECK_ARG(epilogue >= MERLIN_EPI_STORE && epilogue <= MERLIN_EPI_SWIGLU,
                "merlin_gemm_bf16: unknown epilogue %d", epilogue);
   mb::GemmParams p = {};
+  p.kv_col0 = -1;
   p.M = M;
   p.N = N;
   p.K = K;
@@ -278,6 +280,7 @@ int merlin_gemm_bf16_ex(void* stream, const void* A, int64_t lda, int a_mn_major
   MB_CHECK_ARG(epilogue >= MERLIN_EPI_STORE && epilogue <= MERLIN_EPI_SWIGLU,
                "merlin_gemm_bf16_ex: unknown epilogue %d", epilogue);
   mb::GemmParams p = {};
+  p.kv_col0 = -1;
   p.M = M;
   p.N = N;
   p.K = K;
@@ -291,7 +294,16 @@ int merlin_gemm_qkv_rope(void* stream, const void* A, int64_t lda, const void* W
                          void* qkv, int64_t ldc, const float* rope_cos, const float* rope_sin,
                          const int* positions, int M, int N, int K, int rope_cols, int seq_len,
                          int cta_group) {
+  return merlin_gemm_qkv_rope_kv(stream, A, lda, Wqkv, ldb, qkv, ldc, rope_cos, rope_sin, positions, M, N, K, rope_cols,
+                                 seq_len, nullptr, 0, 0, 0, cta_group);
+}
+
+int merlin_gemm_qkv_rope_kv(void* stream, const void* A, int64_t lda, const void* Wqkv, int64_t ldb, void* qkv,
+                            int64_t ldc, const float* rope_cos, const float* rope_sin, const int* positions, int M,
+                            int N, int K, int rope_cols, int seq_len, void* kv_cache, int64_t kv_capacity, int B,
+                            int H, int cta_group) {
   mb::GemmParams p = {};
+  p.kv_col0 = -1;
   p.M = M;
   p.N = N;
   p.K = K;
@@ -301,8 +313,28 @@ int merlin_gemm_qkv_rope(void* stream, const void* A, int64_t lda, const void* W
   p.positions = positions;
   p.rope_cols = rope_cols;
   p.seq_len = seq_len;
-  return mb::gemm_dispatch(static_cast<cudaStream_t>(stream), A, lda, Wqkv, ldb, qkv, ldc, nullptr, 0,
-                           p, cta_group);
+  if (kv_cache == nullptr)
+    return mb::gemm_dispatch(static_cast<cudaStream_t>(stream), A, lda, Wqkv, ldb, qkv, ldc, nullptr, 0, p, cta_group);
+  const int D = N / 3;
+  MB_CHECK_ARG(N == 3 * D && D == H * 128 && rope_cols == 2 * D, "gemm_qkv_rope_kv: needs packed q|k|v with head_dim 128");
+  MB_CHECK_ARG(B >= 1 && M == B * seq_len && (B == 1 || seq_len % 128 == 0),
+               "gemm_qkv_rope_kv: M=%d must be B*seq_len and seq_len %% 128 == 0 for B > 1 (B=%d, seq_len=%d)", M, B, seq_len);
+  MB_CHECK_ARG(kv_capacity % 32 == 0 && seq_len <= kv_capacity, "gemm_qkv_rope_kv: %d tokens do not fit capacity %lld",
+               seq_len, static_cast<long long>(kv_capacity));
+  // cache [B, cap/32, H, 32, 256] as a 5-D tensor, innermost first: column, token % 32, head, token / 32, sample;
+  // box = 64 columns x 32 tokens x 1 head x 4 blocks = the [128 tokens x 64 columns] staging chunk of the epilogue
+  CUtensorMap tkv;
+  uint64_t dims[5] = {256, 32, static_cast<uint64_t>(H), static_cast<uint64_t>(kv_capacity / 32), static_cast<uint64_t>(B)};
+  uint64_t str[4] = {512, 32 * 512, static_cast<uint64_t>(H) * 32 * 512,
+                     static_cast<uint64_t>(kv_capacity / 32) * H * 32 * 512};
+  uint32_t box[5] = {64, 32, 1, 4, 1};
+  int rc = mb::make_tmap_bf16(&tkv, kv_cache, 5, dims, str, box);
+  if (rc != MERLIN_OK) return rc;
+  p.kv_col0 = D;
+  p.kv_hidden = D;
+  p.kv_seq = seq_len;
+  return mb::gemm_dispatch(static_cast<cudaStream_t>(stream), A, lda, Wqkv, ldb, qkv, ldc, nullptr, 0, p, cta_group,
+                           false, false, &tkv);
 }
 
 }  // extern "C"

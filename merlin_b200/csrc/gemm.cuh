@@ -31,6 +31,11 @@ struct GemmParams {
   const int* positions;      // [M] position id of every row, or nullptr -> row % seq_len
   int rope_cols;             // columns [0, rope_cols) are rotated (q and k blocks of a packed qkv)
   int seq_len;
+  // KV-cache append fused into the epilogue of the q|k|v GEMM (kv_col0 < 0: off): output columns
+  // [kv_col0, kv_col0 + 2 kv_hidden) are the k and v blocks; every staged [128 tokens x 64 columns] chunk of
+  // them is ALSO stored through tm_kv into the cache [B, cap/32, H, 32, 256] (k at columns [0,128), v at
+  // [128,256) of a (head, token) row).  Needs kv_seq % 128 == 0 or one sample (a tile may not straddle samples).
+  int kv_col0, kv_hidden, kv_seq;
 };
 
 constexpr int kGemmThreads = 256;
@@ -125,7 +130,7 @@ template <int kCtaGroup, bool kAMN = false, bool kBMN = false>
 __global__ void __launch_bounds__(kGemmThreads, 1)
 gemm_bf16_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant__ CUtensorMap tm_b,
                  const __grid_constant__ CUtensorMap tm_c, const __grid_constant__ CUtensorMap tm_r,
-                 const GemmParams p) {
+                 const __grid_constant__ CUtensorMap tm_kv, const GemmParams p) {
   using Cfg = GemmCfg<kCtaGroup>;
   constexpr int kStages = Cfg::kStages;
   constexpr int kEpiBufs = Cfg::kEpiBufs;
@@ -449,7 +454,17 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant
           const int out_col = (p.epilogue == EPI_SWIGLU) ? tc.n_blk * 128 + c * kEpiCols
                                                           : n0 + c * kEpiCols;
           // boxes that start outside the tensor carry no data; partial boxes are clipped by TMA
-          if (out_col < n_out && m0 < p.M) tma_store_2d(&tm_c, sbuf, out_col, m0);
+          if (out_col < n_out && m0 < p.M) {
+            tma_store_2d(&tm_c, sbuf, out_col, m0);
+            if (p.kv_col0 >= 0 && out_col >= p.kv_col0) {
+              // the same staged chunk, second destination: rows = 128 consecutive tokens = 4 cache blocks of 32,
+              // columns = one 64-wide half of head `e / 128` of the k (which = 0) or v (which = 1) block
+              const int e = out_col - p.kv_col0;
+              const int which = e / p.kv_hidden, eh = e % p.kv_hidden;
+              const int sample = m0 / p.kv_seq, t0 = m0 % p.kv_seq;
+              tma_store_5d(&tm_kv, sbuf, which * 128 + (eh & 127), 0, eh >> 7, t0 >> 5, sample);
+            }
+          }
           tma_store_commit();
           if (has_residual) {
             // every store but the newest has finished reading smem: release the previous buffer

@@ -27,6 +27,8 @@ _PROTOTYPES = {
     "merlin_gemm_bf16": [_P, _P, c_int64, _P, c_int64, _P, c_int64, _P, c_int64, _P, c_int, c_int, c_int, c_int, c_int],
     "merlin_gemm_bf16_ex": [_P, _P, c_int64, c_int, _P, c_int64, c_int, _P, c_int64, _P, c_int64, _P, c_int, c_int, c_int, c_int, c_int],
     "merlin_gemm_qkv_rope": [_P, _P, c_int64, _P, c_int64, _P, c_int64, _P, _P, _P, c_int, c_int, c_int, c_int, c_int, c_int],
+    "merlin_gemm_qkv_rope_kv": [_P, _P, c_int64, _P, c_int64, _P, c_int64, _P, _P, _P, c_int, c_int, c_int, c_int, c_int,
+                                _P, c_int64, c_int, c_int, c_int],
     "merlin_flash_attn_fwd": [_P, _P, c_int64, _P, c_int64, _P, _P, c_int, c_int, c_int, c_int, c_int, c_float],
     "merlin_rmsnorm": [_P, _P, c_int64, _P, _P, c_int64, c_int, c_int, c_float],
     "merlin_layernorm": [_P, _P, c_int64, _P, _P, _P, c_int64, c_int, c_int, c_float],

@@ -150,8 +150,10 @@ class MMGPTLlamaModel(nn.Module):
             return ops.rmsnorm(x, self.norm_w, cfg.rms_norm_eps, out=xn), None
         for i in range(cfg.num_hidden_layers):
             ops.rmsnorm(x, self.ln1_w[i], cfg.rms_norm_eps, out=xn)
-            qkv = ops.gemm_qkv_rope(xn, self.qkv_w[i], cos, sin, seq)
-            if cache is not None:
+            fuse_kv = cache is not None and (batch == 1 or seq % 128 == 0)
+            qkv = ops.gemm_qkv_rope(xn, self.qkv_w[i], cos, sin, seq, kv_cache=cache.kv[i] if fuse_kv else None,
+                                    batch=batch, heads=H)
+            if cache is not None and not fuse_kv:
                 ops.kv_append(qkv, cache.kv[i], batch, seq, D, H)
             att = ops.flash_attn(qkv, batch, seq, H, 128, causal=True, seqlens=seqlens)
             ops.gemm(att, self.o_w[i], residual=x, out=x, epilogue=EPI_RESIDUAL)

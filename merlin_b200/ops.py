@@ -158,8 +158,11 @@ def _gemm_ex(a, lda, a_mn, b, ldb, b_mn, M, N, K, out, accumulate, cta_group):
 
 def gemm_qkv_rope(a: torch.Tensor, w_qkv: torch.Tensor, rope_cos: torch.Tensor, rope_sin: torch.Tensor,
                   seq_len: int, *, positions: Optional[torch.Tensor] = None,
-                  out: Optional[torch.Tensor] = None, cta_group: Optional[int] = None) -> torch.Tensor:
-    """Packed qkv = a @ w_qkv.T with RoPE applied to the q and k blocks in the GEMM epilogue."""
+                  out: Optional[torch.Tensor] = None, cta_group: Optional[int] = None,
+                  kv_cache: Optional[torch.Tensor] = None, batch: int = 1, heads: int = 0) -> torch.Tensor:
+    """Packed qkv = a @ w_qkv.T with RoPE applied to the q and k blocks in the GEMM epilogue.  With `kv_cache`
+    ([batch, capacity/32, heads, 32, 256]) the rotated keys and the values are also appended to the cache from the
+    same epilogue (merlin_gemm_qkv_rope_kv; batch > 1 needs seq_len % 128 == 0)."""
     M, K, lda = _rows2d(a, "a")
     N, Kw, ldb = _rows2d(w_qkv, "w_qkv")
     if K != Kw or N % 3 != 0:
@@ -172,6 +175,15 @@ def gemm_qkv_rope(a: torch.Tensor, w_qkv: torch.Tensor, rope_cos: torch.Tensor, 
     if positions is not None and positions.dtype != torch.int32:
         raise ValueError("positions must be int32")
     L = _lib.load()
+    if kv_cache is not None:
+        if kv_cache.dim() != 5 or kv_cache.shape[0] != batch or kv_cache.shape[2] != heads or kv_cache.shape[3] != 32 \
+                or kv_cache.shape[4] != 256 or not kv_cache.is_contiguous():
+            raise ValueError("gemm_qkv_rope: cache must be a contiguous [batch, capacity/32, heads, 32, 256] tensor")
+        check(_gemm_call(L.merlin_gemm_qkv_rope_kv, 2 * M * N * K, _stream(), a.data_ptr(), lda, w_qkv.data_ptr(), ldb,
+                         out.data_ptr(), ldc, rope_cos.data_ptr(), rope_sin.data_ptr(), _ptr(positions), M, N, K,
+                         2 * N // 3, seq_len, kv_cache.data_ptr(), kv_cache.shape[1] * 32, batch, heads,
+                         cta_group or DEFAULT_CTA_GROUP), "merlin_gemm_qkv_rope_kv")
+        return out
     check(_gemm_call(L.merlin_gemm_qkv_rope, 2 * M * N * K, _stream(), a.data_ptr(), lda, w_qkv.data_ptr(), ldb,
                      out.data_ptr(), ldc, rope_cos.data_ptr(), rope_sin.data_ptr(), _ptr(positions), M, N, K,
                      2 * N // 3, seq_len, cta_group or DEFAULT_CTA_GROUP), "merlin_gemm_qkv_rope")

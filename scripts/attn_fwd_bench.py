@@ -11,7 +11,7 @@ import torch  # noqa: E402
 from merlin_b200 import ops  # noqa: E402
 
 H, hd = 32, 128
-for S in (2048, 4096, 8192):
+for S in [int(x) for x in os.environ.get("S_LIST", "2048,4096,8192").split(",")]:
     torch.manual_seed(0)
     qkv = (torch.randn(S, 3 * H * hd, device="cuda") * 0.5).to(torch.bfloat16)
     for _ in range(3):

@@ -11,7 +11,9 @@ KEYS = [("gpu__time_duration.sum", "duration"),
         ("dram__bytes_read.sum", "dram read"), ("dram__bytes_write.sum", "dram write"),
         ("dram__throughput.avg.pct_of_peak_sustained_elapsed", "dram % of peak"),
         ("sm__throughput.avg.pct_of_peak_sustained_elapsed", "SM throughput %"),
-        ("TPC.TriageCompute.sm__pipe_tensor_cycles_active_realtime.avg.pct_of_peak_sustained_elapsed", "tensor pipe active % (elapsed)"),
+        ("sm__pipe_tensor_cycles_active.avg.pct_of_peak_sustained_active", "tensor pipe active %"),
+        ("sm__pipe_tensor_subpipe_hmma_cycles_active.avg.pct_of_peak_sustained_active", "tensor hmma sub-pipe active %"),
+        ("TPC.TriageCompute.sm__pipe_tensor_cycles_active_realtime.avg.pct_of_peak_sustained_elapsed", "tensor pipe active % (TPC triage, elapsed)"),
         ("sm__inst_executed_pipe_xu.avg.pct_of_peak_sustained_active", "XU (MUFU) pipe %"),
         ("sm__inst_executed.avg.per_cycle_elapsed", "IPC (elapsed)"),
         ("smsp__issue_active.avg.pct", "issue slots busy %"),

@@ -565,3 +565,26 @@ def test_image_preprocess_pad_mode_matches_expand2square_then_pillow():
                                             pad_to_square=True)
         assert np.array_equal(resized.cpu().numpy(), want_u8)
         assert torch.equal(out.cpu(), torch.from_numpy(IO.rescale_normalize(want_u8, mean, std)))
+
+
+@pytest.mark.parametrize("B,S", [(1, 333), (1, 1024), (2, 256), (1, 40)])
+def test_kv_append_fused_into_the_qkv_gemm_epilogue_is_bit_exact(B, S):
+    """merlin_gemm_qkv_rope_kv writes the rotated keys and the values into the block-of-32 KV cache from the GEMM's own
+    epilogue (second TMA store of the staged chunk): same packed qkv, and the cache rows equal merlin_kv_append's
+    bit for bit — incl. a ragged last tile (S = 333, 40) and two tile-aligned samples."""
+    torch.manual_seed(B * 1000 + S)
+    H, D = 2, 256
+    x = torch.randn(B * S, D, device=DEV).to(torch.bfloat16)
+    w = (torch.randn(3 * D, D, device=DEV) * 0.05).to(torch.bfloat16)
+    cos, sin = ops.rope_tables(2048)
+    cap = (S + 95) // 32 * 32
+    plain = ops.gemm_qkv_rope(x, w, cos, sin, S)
+    want = torch.zeros(B, cap // 32, H, 32, 256, dtype=torch.bfloat16, device=DEV)
+    ops.kv_append(plain, want, B, S, D, H)
+    got = torch.zeros_like(want)
+    fused = ops.gemm_qkv_rope(x, w, cos, sin, S, kv_cache=got, batch=B, heads=H)
+    assert torch.equal(fused, plain)
+    t = torch.arange(S, device=DEV)
+    assert torch.equal(got[:, t // 32, :, t % 32], want[:, t // 32, :, t % 32])      # every appended (token, head) row
+    if S % 128 == 0:
+        assert torch.equal(got, want)                                                 # and nothing else was touched
