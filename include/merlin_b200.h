@@ -199,6 +199,27 @@ int merlin_embed_token(void* stream, const void* embed_table, const int64_t* tok
 int merlin_record_advance(void* stream, const int64_t* token_dev, int64_t* out_ids, int* n_out_dev,
                           int* pos_dev, int capacity);
 
+/* Beam search: ONE decode position of num_beams sequences that share a prompt (generate(num_beams=k),
+ * mmgpt/engine/eval/eval_box.py:246-254; HF GenerationMixin._beam_search runs the beams as a batch of k sequences, each
+ * with its own copy of the whole cache, and re-orders every cache tensor every step).  The cache is split: prefix_kv[l]
+ * is the prompt's cache (merlin_decoder_weights.kv_cache layout, shared and read once for all beams), suffix_kv[l] is
+ * [num_beams, suffix_capacity/32, heads, 32, 256] (same row layout, per beam: the tokens generated so far — the only
+ * thing a beam re-ordering has to move).  pos_dev = device int[2] {prefix_len, t}: the new token of every beam is
+ * suffix row t at position prefix_len + t (device memory, so the call can be captured in a CUDA graph). */
+typedef struct merlin_beam_state {
+  int num_beams;                /* 1..8 */
+  int64_t suffix_capacity;      /* tokens per beam (a multiple of 32) */
+  const void* const* prefix_kv; /* [L] */
+  void* const* suffix_kv;       /* [L] */
+  const int* pos_dev;
+} merlin_beam_state;
+size_t merlin_decode_batched_workspace_bytes(int hidden, int intermediate, int heads, int n_splits, int num_beams);
+/* x[num_beams, hidden] (bf16 token embeddings, overwritten with the final residual stream) -> logits[num_beams,
+ * ld_logits] (bf16; ld_logits >= vocab).  Every weight matrix is streamed from HBM once for all beams (mma.sync
+ * m16n8k16 with the beams as the 8 columns).  w->kv_cache / kv_capacity are not used. */
+int merlin_decode_step_batched(void* stream, const merlin_decoder_weights* w, const merlin_beam_state* bs, void* x,
+                               void* workspace, void* logits, int64_t ld_logits, int n_splits);
+
 /* Append S tokens to a KV cache (layout above): for b < B, s < S, h < H copies k and v of head h out of the packed
  * qkv row [b*S + s] (ldq elements per row; k at column D + h*128, v at 2D + h*128) into row (h, pos0 + s) of
  * cache block b.  cache holds B blocks of kv_capacity*H*256 elements.  (HF KV-cache update.) */

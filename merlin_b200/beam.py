@@ -63,10 +63,13 @@ class BeamSearch:
             return None
         nb, keep = self.nb, self.keep
         cur_len = self.running.shape[1]
-        logp = torch.log_softmax(logits.detach().to(dtype=torch.float32, device="cpu"), dim=-1)
+        # log-softmax and the top-2k selection run where the logits live (the GPU during generate): only the 2k
+        # candidates cross to the host
+        logp = torch.log_softmax(logits.detach().to(dtype=torch.float32), dim=-1)
         V = logp.shape[-1]
-        cand = (logp + self.running_scores[:, None]).reshape(-1)
+        cand = (logp + self.running_scores.to(logp.device)[:, None]).reshape(-1)
         top_scores, top_idx = torch.topk(cand, k=keep)
+        top_scores, top_idx = top_scores.cpu(), top_idx.cpu()
         parents, tokens = top_idx // V, top_idx % V
         cand_seqs = torch.cat([self.running[parents], tokens.view(-1, 1)], dim=1)
         hits = torch.zeros(keep, dtype=torch.bool)

@@ -1,0 +1,663 @@
+// merlin_b200 — batched decode step for beam search (generate(num_beams = k) of
+// mmgpt/engine/eval/eval_box.py:246-254 over HF `_beam_search`).
+//
+// The reference runs k beams as a batch of k sequences through the HF decoder, each with its own copy of the
+// whole KV cache (`repeat_interleave(5)` of the prompt, base_mmgpt.py:162-163; HF's cache re-ordering copies every
+// cache tensor every step).  Here one decode position of all k beams is ONE pass over the weights:
+//  * every projection is a [N, K] x [K, 8] product on the tensor cores (mma.sync m16n8k16, bf16 in, fp32
+//    accumulate): the 8 columns are the beams (unused ones are zero), a CTA owns 16 weight rows and its 8 warps
+//    split K, so each weight byte is read from HBM once per step whatever the beam count — the step stays bound by
+//    the weight bytes of a single sequence.  (tcgen05 has no use here: M = 128 rows x N = 8 would leave the
+//    operand staging, not the math, as the cost; the kernel is a pure HBM stream.)
+//  * the KV cache is split into the SHARED prefix (the prompt: the prefill's cache, read once for all beams — the
+//    k queries of a head are scored against each key while it is in registers) and a per-beam SUFFIX (the tokens
+//    generated so far), so a beam re-ordering moves only the small suffix blocks;
+//  * attention is one kernel: prefix partials (heads x key splits CTAs, k online-softmax states per thread), one CTA
+//    per head for the beams' suffixes, and the last CTA of a head merges all partials in index order.
+// Same arithmetic as decode.cu (fp32 accumulation, RMSNorm rounded to bf16 as the prefill does, RoPE in fp32 before the
+// bf16 rounding), so a beam's logits equal the single-sequence path's up to summation order.
+#include "host.cuh"
+
+#include <mutex>
+#include "ptx.cuh"
+
+#include <algorithm>
+#include <cmath>
+
+namespace mb {
+namespace {
+
+constexpr int kBWarps = 8;               // warps of a GEMV CTA: they split K
+constexpr int kBThreads = kBWarps * 32;
+constexpr int kU = 4;                    // 32-element K blocks in flight per warp
+constexpr int kMaxBeams = 8;             // the N of m16n8k16
+constexpr int kAThreads = 128;           // attention CTAs: 4 warps x 4 key slots x 8 lanes (16 dims each)
+
+enum BMode : int { B_PLAIN = 0, B_QKV_ROPE = 1, B_SWIGLU = 2 };
+
+struct BGemvParams {
+  const __nv_bfloat16* W;         // [N, K]
+  const __nv_bfloat16* x;         // [nb, ldx] input activations
+  int64_t ldx;
+  const __nv_bfloat16* residual;  // [nb, ldo] or nullptr (PLAIN)
+  __nv_bfloat16* out;             // PLAIN / SWIGLU: [nb, ldo]; QKV: q buffer [nb, D]
+  int64_t ldo;
+  __nv_bfloat16* suffix_kv;       // QKV: [nb, suffix_cap/32, H, 32, 256] of this layer
+  int64_t suffix_stride;          // elements between two beams' suffix caches
+  const float* rope_cos;
+  const float* rope_sin;
+  const int* pos;                 // device {prefix_len, t}: the new token is suffix row t, position prefix_len + t
+  int nb, N, K, D;
+};
+
+__device__ __forceinline__ uint4 ldg_stream(const uint4* p) {
+  uint4 r;
+  asm volatile("ld.global.nc.L1::no_allocate.v4.u32 {%0, %1, %2, %3}, [%4];"
+               : "=r"(r.x), "=r"(r.y), "=r"(r.z), "=r"(r.w)
+               : "l"(p));
+  return r;
+}
+__device__ __forceinline__ float sumsq8(const uint4& v) {
+  float s = bf16_lo(v.x) * bf16_lo(v.x);
+  s = fmaf(bf16_hi(v.x), bf16_hi(v.x), s);
+  s = fmaf(bf16_lo(v.y), bf16_lo(v.y), s);
+  s = fmaf(bf16_hi(v.y), bf16_hi(v.y), s);
+  s = fmaf(bf16_lo(v.z), bf16_lo(v.z), s);
+  s = fmaf(bf16_hi(v.z), bf16_hi(v.z), s);
+  s = fmaf(bf16_lo(v.w), bf16_lo(v.w), s);
+  s = fmaf(bf16_hi(v.w), bf16_hi(v.w), s);
+  return s;
+}
+// D(16x8, fp32) += A(16x16, bf16, row) * B(16x8, bf16, col)
+__device__ __forceinline__ void mma_16816(float (&c)[4], uint32_t a0, uint32_t a1, uint32_t a2, uint32_t a3, uint32_t b0,
+                                          uint32_t b1) {
+  asm volatile("mma.sync.aligned.m16n8k16.row.col.f32.bf16.bf16.f32 {%0, %1, %2, %3}, {%4, %5, %6, %7}, {%8, %9}, "
+               "{%0, %1, %2, %3};"
+               : "+f"(c[0]), "+f"(c[1]), "+f"(c[2]), "+f"(c[3])
+               : "r"(a0), "r"(a1), "r"(a2), "r"(a3), "r"(b0), "r"(b1));
+}
+__device__ __forceinline__ size_t kv_off(int h, int t, int H) {   // decode.cu: kv_row_off
+  return ((static_cast<size_t>(t >> 5) * H + h) * 32 + (t & 31)) * 256;
+}
+
+// xn[b] = bf16(weight * (x[b] * rstd_b)) — the rounding of the prefill's RMSNorm kernel.  One CTA per beam; the
+// projections that follow read xn through L1 instead of normalising a private copy in every CTA.
+__global__ void __launch_bounds__(256)
+norm_beams_kernel(const __nv_bfloat16* __restrict__ x, int64_t ldx, const __nv_bfloat16* __restrict__ weight,
+                  __nv_bfloat16* __restrict__ xn, int K, float eps) {
+  __shared__ float red[8];
+  asm volatile("griddepcontrol.wait;" ::: "memory");
+  asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+  const int nvec = K >> 3;
+  const uint4* xg = reinterpret_cast<const uint4*>(x + static_cast<size_t>(blockIdx.x) * ldx);
+  const uint4* wg = reinterpret_cast<const uint4*>(weight);
+  uint4* dst = reinterpret_cast<uint4*>(xn + static_cast<size_t>(blockIdx.x) * K);
+  uint4 v[3];                                     // K <= 6144: up to 3 vectors per thread stay in registers
+  float ss = 0.f;
+#pragma unroll
+  for (int u = 0; u < 3; ++u) {
+    const int i = threadIdx.x + 256 * u;
+    v[u] = make_uint4(0, 0, 0, 0);
+    if (i < nvec) v[u] = xg[i];
+    ss += sumsq8(v[u]);
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) ss += __shfl_xor_sync(0xffffffffu, ss, o);
+  if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = ss;
+  __syncthreads();
+  float tot = 0.f;
+#pragma unroll
+  for (int w = 0; w < 8; ++w) tot += red[w];
+  const float rstd = rsqrtf(tot / static_cast<float>(K) + eps);
+#pragma unroll
+  for (int u = 0; u < 3; ++u) {
+    const int i = threadIdx.x + 256 * u;
+    if (i < nvec) {
+      const uint4 w = wg[i];
+      uint4 o;
+      o.x = pack_bf16(bf16_lo(w.x) * (bf16_lo(v[u].x) * rstd), bf16_hi(w.x) * (bf16_hi(v[u].x) * rstd));
+      o.y = pack_bf16(bf16_lo(w.y) * (bf16_lo(v[u].y) * rstd), bf16_hi(w.y) * (bf16_hi(v[u].y) * rstd));
+      o.z = pack_bf16(bf16_lo(w.z) * (bf16_lo(v[u].z) * rstd), bf16_hi(w.z) * (bf16_hi(v[u].z) * rstd));
+      o.w = pack_bf16(bf16_lo(w.w) * (bf16_lo(v[u].w) * rstd), bf16_hi(w.w) * (bf16_hi(v[u].w) * rstd));
+      dst[i] = o;
+    }
+  }
+}
+
+// out[b, r] = dot(W[r], x_b) for all beams at once.  A CTA owns 8 row PAIRS (row_a -> MMA rows 0-7, row_b -> MMA rows
+// 8-15; a pair is what one epilogue needs: the two halves of a RoPE rotation, gate and up of one SwiGLU output, or two
+// adjacent rows).  Lane (g, t) = (lane / 4, lane % 4) loads 16 bytes of row_a(g) and row_b(g) at K offset 32 blk + 8 t
+// and the same 16 bytes of beam g's activation (through L1: every CTA of an SM reads the same few KB): both operands
+// see the same K permutation inside the 32-block, so two MMAs per block consume them without any shuffle.
+template <int kMode, int kU>
+__global__ void __launch_bounds__(kBThreads, kU <= 2 ? 4 : 2)
+gemv_beams_kernel(const BGemvParams p) {
+  __shared__ float red[kBWarps][32][4];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int g = lane >> 2, t = lane & 3;
+  const int pair = blockIdx.x * 8 + g;
+  int row_a, row_b;
+  if (kMode == B_QKV_ROPE) {
+    if (pair < p.D) {                       // q and k blocks: RoPE pair (j, j + 64) of one head
+      row_a = (pair >> 6) * 128 + (pair & 63);
+      row_b = row_a + 64;
+    } else {
+      row_a = 2 * p.D + 2 * (pair - p.D);
+      row_b = row_a + 1;
+    }
+  } else if (kMode == B_SWIGLU) {
+    row_a = (pair >> 7) * 256 + (pair & 127);
+    row_b = row_a + 128;
+  } else {
+    row_a = 2 * pair;
+    row_b = row_a + 1;
+  }
+  const bool active = row_a < p.N;
+  const bool has_b = row_b < p.N;
+  const int nblk = p.K >> 5;
+  const uint4* wa = reinterpret_cast<const uint4*>(p.W + static_cast<size_t>(active ? row_a : 0) * p.K) + t;
+  const uint4* wb = reinterpret_cast<const uint4*>(p.W + static_cast<size_t>(has_b ? row_b : (active ? row_a : 0)) * p.K) + t;
+
+  // ---- first weight batch BEFORE waiting on the producer kernel (programmatic dependent launch: overlaps its tail)
+  uint4 a[kU], b[kU];
+#pragma unroll
+  for (int u = 0; u < kU; ++u) {
+    const int blk = warp + kBWarps * u;
+    a[u] = b[u] = make_uint4(0, 0, 0, 0);
+    if (blk < nblk) {
+      a[u] = ldg_stream(wa + blk * 4);
+      b[u] = ldg_stream(wb + blk * 4);
+    }
+  }
+  asm volatile("griddepcontrol.wait;" ::: "memory");
+  asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+
+  const bool beam_live = g < p.nb;
+  const uint4* xrow = reinterpret_cast<const uint4*>(p.x + static_cast<size_t>(beam_live ? g : 0) * p.ldx) + t;
+
+  float c[4] = {0.f, 0.f, 0.f, 0.f};
+  for (int blk0 = warp; blk0 < nblk; blk0 += kBWarps * kU) {
+    uint4 na[kU], nb_[kU], xv[kU];
+#pragma unroll
+    for (int u = 0; u < kU; ++u) {
+      const int blk = blk0 + kBWarps * (kU + u);
+      na[u] = nb_[u] = make_uint4(0, 0, 0, 0);
+      if (blk < nblk) {
+        na[u] = ldg_stream(wa + blk * 4);
+        nb_[u] = ldg_stream(wb + blk * 4);
+      }
+    }
+#pragma unroll
+    for (int u = 0; u < kU; ++u) {
+      const int blk = blk0 + kBWarps * u;
+      xv[u] = (beam_live && blk < nblk) ? xrow[blk * 4] : make_uint4(0, 0, 0, 0);
+    }
+#pragma unroll
+    for (int u = 0; u < kU; ++u) {
+      if (blk0 + kBWarps * u < nblk) {      // warp-uniform
+        mma_16816(c, a[u].x, b[u].x, a[u].y, b[u].y, xv[u].x, xv[u].y);
+        mma_16816(c, a[u].z, b[u].z, a[u].w, b[u].w, xv[u].z, xv[u].w);
+      }
+    }
+#pragma unroll
+    for (int u = 0; u < kU; ++u) {
+      a[u] = na[u];
+      b[u] = nb_[u];
+    }
+  }
+  // ---- combine the K partitions (fixed order: deterministic)
+  red[warp][lane][0] = c[0];
+  red[warp][lane][1] = c[1];
+  red[warp][lane][2] = c[2];
+  red[warp][lane][3] = c[3];
+  __syncthreads();
+  if (warp != 0 || !active) return;
+#pragma unroll
+  for (int w = 1; w < kBWarps; ++w) {
+    c[0] += red[w][lane][0];
+    c[1] += red[w][lane][1];
+    c[2] += red[w][lane][2];
+    c[3] += red[w][lane][3];
+  }
+  // lane (g, t) holds rows (row_a, row_b) of pair g for beams 2t and 2t + 1
+#pragma unroll
+  for (int half = 0; half < 2; ++half) {
+    const int beam = 2 * t + half;
+    if (beam >= p.nb) continue;
+    float va = c[half], vb = c[2 + half];
+    if (kMode == B_QKV_ROPE) {
+      const int tok = p.pos[1];
+      const int position = p.pos[0] + tok;
+      const int H = p.D >> 7;
+      __nv_bfloat16* kvb = p.suffix_kv + static_cast<size_t>(beam) * p.suffix_stride;
+      auto kv_at = [&](int e, int which) { return kvb + kv_off(e >> 7, tok, H) + which * 128 + (e & 127); };
+      if (row_a < 2 * p.D) {
+        const int j = row_a & 63;
+        const float cs = p.rope_cos[static_cast<size_t>(position) * 64 + j];
+        const float sn = p.rope_sin[static_cast<size_t>(position) * 64 + j];
+        const float lo = va * cs - vb * sn, hi = vb * cs + va * sn;
+        if (row_a < p.D) {
+          p.out[static_cast<size_t>(beam) * p.ldo + row_a] = __float2bfloat16_rn(lo);
+          p.out[static_cast<size_t>(beam) * p.ldo + row_b] = __float2bfloat16_rn(hi);
+        } else {
+          *kv_at(row_a - p.D, 0) = __float2bfloat16_rn(lo);
+          *kv_at(row_b - p.D, 0) = __float2bfloat16_rn(hi);
+        }
+      } else {
+        *kv_at(row_a - 2 * p.D, 1) = __float2bfloat16_rn(va);
+        *kv_at(row_b - 2 * p.D, 1) = __float2bfloat16_rn(vb);
+      }
+    } else if (kMode == B_SWIGLU) {
+      p.out[static_cast<size_t>(beam) * p.ldo + (row_a >> 8) * 128 + (row_a & 127)] =
+          __float2bfloat16_rn(va / (1.f + __expf(-va)) * vb);
+    } else {
+      if (p.residual) {
+        va += __bfloat162float(p.residual[static_cast<size_t>(beam) * p.ldo + row_a]);
+        if (has_b) vb += __bfloat162float(p.residual[static_cast<size_t>(beam) * p.ldo + row_b]);
+      }
+      p.out[static_cast<size_t>(beam) * p.ldo + row_a] = __float2bfloat16_rn(va);
+      if (has_b) p.out[static_cast<size_t>(beam) * p.ldo + row_b] = __float2bfloat16_rn(vb);
+    }
+  }
+}
+
+// ---- attention of all beams for one head.  Grid (H, n_splits + 1): CTAs y < n_splits walk a key range of the SHARED
+// prefix once, scoring each key against the NB queries while it sits in registers (NB online-softmax states per
+// thread); CTA y == n_splits attends each beam over its own suffix rows 0 .. t (the new token included).  A lane owns
+// kDims of the 128 head dims (16, or 8 beyond 5 beams so the NB accumulators still fit the register file).  Partials
+// go to part_o[((h * NP + y) * NB + b) * 128 + d], part_ml[(...) * 2 + {m, l}]; the LAST CTA of a head to finish (per-
+// head arrival ticket, self-resetting) merges them in index order — deterministic — into att[b, h * 128 + d].
+template <int NB, int kDims>
+__global__ void __launch_bounds__(kAThreads)
+beam_attention_kernel(const __nv_bfloat16* __restrict__ q, int64_t ldq, const __nv_bfloat16* __restrict__ prefix_kv,
+                      const __nv_bfloat16* __restrict__ suffix_kv, int64_t suffix_stride, const int* __restrict__ pos,
+                      int H, int n_splits, float scale_log2e, float* __restrict__ part_o, float* __restrict__ part_ml,
+                      unsigned int* __restrict__ tickets, __nv_bfloat16* __restrict__ att, int64_t ld_att) {
+  constexpr int kLpk = 128 / kDims;            // lanes per key
+  constexpr int kSlots = 4 * (32 / kLpk);      // keys per CTA iteration
+  constexpr int kVecs = kDims / 8;             // 16-byte vectors of k (and of v) per lane
+  __shared__ float s_o[kSlots][128];
+  __shared__ float s_m[kSlots], s_l[kSlots];
+  __shared__ unsigned int s_last;
+  const int h = blockIdx.x, split = blockIdx.y, NP = n_splits + 1;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int slot = warp * (32 / kLpk) + lane / kLpk, sub = lane % kLpk;
+  const int d = threadIdx.x;
+  auto load_row = [&](const __nv_bfloat16* kv, int key, uint4 (&r)[2 * kVecs], bool stream) {
+    const __nv_bfloat16* row = kv + kv_off(h, key, H) + sub * kDims;
+#pragma unroll
+    for (int i = 0; i < kVecs; ++i) {
+      if (stream) {
+        r[i] = ldg_stream(reinterpret_cast<const uint4*>(row) + i);
+        r[kVecs + i] = ldg_stream(reinterpret_cast<const uint4*>(row + 128) + i);
+      } else {
+        r[i] = *(reinterpret_cast<const uint4*>(row) + i);
+        r[kVecs + i] = *(reinterpret_cast<const uint4*>(row + 128) + i);
+      }
+    }
+  };
+  auto unpack = [&](const uint4 (&r)[2 * kVecs], float (&kf)[kDims], float (&vf)[kDims]) {
+#pragma unroll
+    for (int i = 0; i < kVecs; ++i) {
+      const uint32_t kw[4] = {r[i].x, r[i].y, r[i].z, r[i].w};
+      const uint32_t vw[4] = {r[kVecs + i].x, r[kVecs + i].y, r[kVecs + i].z, r[kVecs + i].w};
+#pragma unroll
+      for (int e = 0; e < 4; ++e) {
+        kf[8 * i + 2 * e] = bf16_lo(kw[e]);
+        kf[8 * i + 2 * e + 1] = bf16_hi(kw[e]);
+        vf[8 * i + 2 * e] = bf16_lo(vw[e]);
+        vf[8 * i + 2 * e + 1] = bf16_hi(vw[e]);
+      }
+    }
+  };
+  auto key_reduce = [&](float s) {
+#pragma unroll
+    for (int o = 1; o < kLpk; o <<= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+    return s * scale_log2e;
+  };
+  // merge the key slots of the block for beam b and store partial (h, split, b)
+  auto store_partial = [&](int b, const float (&o)[kDims], float m, float l) {
+    __syncthreads();
+#pragma unroll
+    for (int e = 0; e < kDims; ++e) s_o[slot][sub * kDims + e] = o[e];
+    if (sub == 0) {
+      s_m[slot] = m;
+      s_l[slot] = l;
+    }
+    __syncthreads();
+    float M = -INFINITY;
+#pragma unroll
+    for (int gi = 0; gi < kSlots; ++gi) M = fmaxf(M, s_m[gi]);
+    float acc = 0.f, L = 0.f;
+#pragma unroll
+    for (int gi = 0; gi < kSlots; ++gi) {
+      const float w = (s_m[gi] == -INFINITY) ? 0.f : fast_exp2(s_m[gi] - M);
+      acc += s_o[gi][d] * w;
+      L += s_l[gi] * w;
+    }
+    const size_t idx = (static_cast<size_t>(h) * NP + split) * NB + b;
+    part_o[idx * 128 + d] = acc;
+    if (d == 0) {
+      part_ml[idx * 2] = M;
+      part_ml[idx * 2 + 1] = L;
+    }
+  };
+
+  if (split < n_splits) {
+    const int prefix_len = pos[0];                                   // written before the step / graph is launched
+    const int chunk = ((prefix_len + n_splits - 1) / n_splits + kSlots - 1) / kSlots * kSlots;
+    const int k0 = min(prefix_len, split * chunk), k1 = min(prefix_len, k0 + chunk);
+    uint4 cur[2 * kVecs], nxt[2 * kVecs];
+#pragma unroll
+    for (int i = 0; i < 2 * kVecs; ++i) cur[i] = nxt[i] = make_uint4(0, 0, 0, 0);
+    if (k0 < k1) load_row(prefix_kv, min(k0 + slot, k1 - 1), cur, true);   // the prompt cache is not written by this step
+    asm volatile("griddepcontrol.wait;" ::: "memory");
+    asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+    uint32_t qp[NB][kDims / 2];
+    float m[NB], l[NB], o[NB][kDims];
+#pragma unroll
+    for (int b = 0; b < NB; ++b) {
+      const uint4* qg = reinterpret_cast<const uint4*>(q + static_cast<size_t>(b) * ldq + h * 128 + sub * kDims);
+#pragma unroll
+      for (int i = 0; i < kVecs; ++i) {
+        const uint4 x = qg[i];
+        qp[b][4 * i] = x.x; qp[b][4 * i + 1] = x.y; qp[b][4 * i + 2] = x.z; qp[b][4 * i + 3] = x.w;
+      }
+      m[b] = -INFINITY;
+      l[b] = 0.f;
+#pragma unroll
+      for (int e = 0; e < kDims; ++e) o[b][e] = 0.f;
+    }
+    for (int base = k0; base < k1; base += kSlots) {
+      const bool live = base + slot < k1;
+      if (base + kSlots < k1) load_row(prefix_kv, min(base + kSlots + slot, k1 - 1), nxt, true);
+      float kf[kDims], vf[kDims];
+      unpack(cur, kf, vf);
+#pragma unroll
+      for (int b = 0; b < NB; ++b) {
+        float s = 0.f;
+#pragma unroll
+        for (int e = 0; e < kDims / 2; ++e) {
+          s = fmaf(bf16_lo(qp[b][e]), kf[2 * e], s);
+          s = fmaf(bf16_hi(qp[b][e]), kf[2 * e + 1], s);
+        }
+        s = key_reduce(s);
+        if (live) {
+          const float m_new = fmaxf(m[b], s);
+          const float alpha = fast_exp2(m[b] - m_new);
+          const float pr = fast_exp2(s - m_new);
+          l[b] = l[b] * alpha + pr;
+#pragma unroll
+          for (int e = 0; e < kDims; ++e) o[b][e] = fmaf(pr, vf[e], o[b][e] * alpha);
+          m[b] = m_new;
+        }
+      }
+#pragma unroll
+      for (int i = 0; i < 2 * kVecs; ++i) cur[i] = nxt[i];
+    }
+#pragma unroll
+    for (int b = 0; b < NB; ++b) store_partial(b, o[b], m[b], l[b]);
+  } else {
+    asm volatile("griddepcontrol.wait;" ::: "memory");
+    asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+    const int T = pos[1] + 1;
+    for (int b = 0; b < NB; ++b) {
+      const __nv_bfloat16* kv = suffix_kv + static_cast<size_t>(b) * suffix_stride;
+      uint32_t qp[kDims / 2];
+      const uint4* qg = reinterpret_cast<const uint4*>(q + static_cast<size_t>(b) * ldq + h * 128 + sub * kDims);
+#pragma unroll
+      for (int i = 0; i < kVecs; ++i) {
+        const uint4 x = qg[i];
+        qp[4 * i] = x.x; qp[4 * i + 1] = x.y; qp[4 * i + 2] = x.z; qp[4 * i + 3] = x.w;
+      }
+      float m = -INFINITY, l = 0.f, o[kDims];
+#pragma unroll
+      for (int e = 0; e < kDims; ++e) o[e] = 0.f;
+      for (int base = 0; base < T; base += kSlots) {
+        const bool live = base + slot < T;
+        uint4 r[2 * kVecs];
+        load_row(kv, live ? base + slot : 0, r, false);
+        float kf[kDims], vf[kDims];
+        unpack(r, kf, vf);
+        float s = 0.f;
+#pragma unroll
+        for (int e = 0; e < kDims / 2; ++e) {
+          s = fmaf(bf16_lo(qp[e]), kf[2 * e], s);
+          s = fmaf(bf16_hi(qp[e]), kf[2 * e + 1], s);
+        }
+        s = key_reduce(s);
+        if (live) {
+          const float m_new = fmaxf(m, s);
+          const float alpha = fast_exp2(m - m_new);
+          const float pr = fast_exp2(s - m_new);
+          l = l * alpha + pr;
+#pragma unroll
+          for (int e = 0; e < kDims; ++e) o[e] = fmaf(pr, vf[e], o[e] * alpha);
+          m = m_new;
+        }
+      }
+      store_partial(b, o, m, l);
+    }
+  }
+  // ---- the last CTA of this head merges (decode.cu: flash_decode_partial_kernel)
+  __threadfence();
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    const unsigned int tk = atomicAdd(&tickets[h], 1u);
+    s_last = (tk == static_cast<unsigned int>(NP) - 1u) ? 1u : 0u;
+    if (s_last) tickets[h] = 0;
+  }
+  __syncthreads();
+  if (!s_last) return;
+  __threadfence();
+#pragma unroll 1
+  for (int b = 0; b < NB; ++b) {
+    float M = -INFINITY;
+    for (int sp = 0; sp < NP; ++sp) M = fmaxf(M, __ldcg(&part_ml[((static_cast<size_t>(h) * NP + sp) * NB + b) * 2]));
+    float acc = 0.f, L = 0.f;
+    for (int sp = 0; sp < NP; ++sp) {
+      const size_t idx = (static_cast<size_t>(h) * NP + sp) * NB + b;
+      const float pm = __ldcg(&part_ml[idx * 2]);
+      const float w = (pm == -INFINITY) ? 0.f : fast_exp2(pm - M);
+      acc += __ldcg(&part_o[idx * 128 + d]) * w;
+      L += __ldcg(&part_ml[idx * 2 + 1]) * w;
+    }
+    att[static_cast<size_t>(b) * ld_att + h * 128 + d] = __float2bfloat16_rn(acc / L);
+  }
+}
+
+cudaLaunchAttribute g_battr;
+cudaLaunchConfig_t bpdl(dim3 grid, dim3 block, size_t smem, cudaStream_t st) {
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = grid;
+  cfg.blockDim = block;
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = st;
+  g_battr.id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  g_battr.val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = &g_battr;
+  cfg.numAttrs = 1;
+  return cfg;
+}
+
+int g_beam_ku = -1;   // MERLIN_BEAM_KU: K blocks in flight per warp (2: four CTAs per SM, 4: two)
+
+template <int kMode>
+int launch_bgemv(cudaStream_t st, const BGemvParams& p, int pairs) {
+  MB_CHECK_ARG(p.K % 32 == 0 && p.ldx % 8 == 0, "decode_step_batched: K=%d unsupported", p.K);
+  if (g_beam_ku < 0) {
+    const char* e = getenv("MERLIN_BEAM_KU");
+    g_beam_ku = (e && atoi(e) == 4) ? 4 : 2;
+  }
+  cudaLaunchConfig_t cfg = bpdl(dim3((pairs + 7) / 8), dim3(kBThreads), 0, st);
+  if (g_beam_ku == 4) {
+    MB_CHECK_CUDA(cudaLaunchKernelEx(&cfg, gemv_beams_kernel<kMode, 4>, p));
+  } else {
+    MB_CHECK_CUDA(cudaLaunchKernelEx(&cfg, gemv_beams_kernel<kMode, 2>, p));
+  }
+  return MERLIN_OK;
+}
+
+int launch_norm(cudaStream_t st, const __nv_bfloat16* x, int64_t ldx, const void* weight, __nv_bfloat16* xn, int K,
+                float eps, int nb) {
+  MB_CHECK_ARG(K % 8 == 0 && K <= 6144, "decode_step_batched: hidden size %d unsupported", K);
+  cudaLaunchConfig_t cfg = bpdl(dim3(nb), dim3(256), 0, st);
+  MB_CHECK_CUDA(cudaLaunchKernelEx(&cfg, norm_beams_kernel, x, ldx, static_cast<const __nv_bfloat16*>(weight), xn, K, eps));
+  return MERLIN_OK;
+}
+
+struct AttnArgs {
+  const __nv_bfloat16 *q, *prefix_kv, *suffix_kv;
+  int64_t ldq, suffix_stride, ld_att;
+  const int* pos;
+  int H, n_splits;
+  float scale;
+  float *part_o, *part_ml;
+  unsigned int* tickets;
+  __nv_bfloat16* att;
+};
+
+template <int NB>
+int launch_attention(cudaStream_t st, const AttnArgs& a) {
+  constexpr int kDims = NB <= 5 ? 16 : 8;
+  cudaLaunchConfig_t cfg = bpdl(dim3(a.H, a.n_splits + 1), dim3(kAThreads), 0, st);
+  MB_CHECK_CUDA(cudaLaunchKernelEx(&cfg, beam_attention_kernel<NB, kDims>, a.q, a.ldq, a.prefix_kv, a.suffix_kv,
+                                   a.suffix_stride, a.pos, a.H, a.n_splits, a.scale, a.part_o, a.part_ml, a.tickets, a.att,
+                                   a.ld_att));
+  return MERLIN_OK;
+}
+
+}  // namespace
+}  // namespace mb
+
+using namespace mb;
+
+extern "C" {
+
+size_t merlin_decode_batched_workspace_bytes(int hidden, int intermediate, int heads, int n_splits, int num_beams) {
+  size_t b = (static_cast<size_t>(num_beams) * (3 * hidden + intermediate) * 2 + 255) / 256 * 256;   // q, att, xn, mid
+  b += static_cast<size_t>(heads) * (n_splits + 1) * num_beams * (128 + 2) * 4;                      // partials
+  b += static_cast<size_t>(heads) * 4;                                                               // tickets
+  return b + 1024;
+}
+
+int merlin_decode_step_batched(void* stream, const merlin_decoder_weights* w, const merlin_beam_state* bs, void* x,
+                               void* workspace, void* logits, int64_t ld_logits, int n_splits) {
+  MB_CHECK_ARG(w && bs && x && workspace && logits, "decode_step_batched: null argument");
+  MB_CHECK_ARG(w->hidden == w->heads * 128 && w->intermediate % 128 == 0 && w->hidden % 128 == 0,
+               "decode_step_batched: head_dim must be 128");
+  MB_CHECK_ARG(bs->num_beams >= 1 && bs->num_beams <= kMaxBeams, "decode_step_batched: %d beams (1..%d)", bs->num_beams,
+               kMaxBeams);
+  MB_CHECK_ARG(n_splits >= 1 && n_splits <= 64, "decode_step_batched: n_splits %d", n_splits);
+  MB_CHECK_ARG(bs->suffix_capacity >= 32 && bs->suffix_capacity % 32 == 0 && bs->suffix_kv && bs->prefix_kv && bs->pos_dev,
+               "decode_step_batched: bad beam state");
+  MB_CHECK_ARG(ld_logits >= w->vocab, "decode_step_batched: logits pitch %lld < vocab", static_cast<long long>(ld_logits));
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  const int D = w->hidden, FF = w->intermediate, H = w->heads, NB = bs->num_beams;
+  uint8_t* ws = static_cast<uint8_t*>(workspace);
+  __nv_bfloat16* qbuf = reinterpret_cast<__nv_bfloat16*>(ws);                  // [NB, D]
+  __nv_bfloat16* att = qbuf + static_cast<size_t>(NB) * D;                      // [NB, D]
+  __nv_bfloat16* xn = att + static_cast<size_t>(NB) * D;                        // [NB, D]
+  __nv_bfloat16* mid = xn + static_cast<size_t>(NB) * D;                        // [NB, FF]
+  float* part_o = reinterpret_cast<float*>(ws + (static_cast<size_t>(NB) * (3 * D + FF) * 2 + 255) / 256 * 256);
+  float* part_ml = part_o + static_cast<size_t>(H) * (n_splits + 1) * NB * 128;
+  unsigned int* tickets = reinterpret_cast<unsigned int*>(part_ml + static_cast<size_t>(H) * (n_splits + 1) * NB * 2);
+  __nv_bfloat16* xb = static_cast<__nv_bfloat16*>(x);
+  const int64_t suffix_stride = bs->suffix_capacity * H * 256;
+  AttnArgs aa = {};
+  aa.q = qbuf;
+  aa.ldq = D;
+  aa.suffix_stride = suffix_stride;
+  aa.ld_att = D;
+  aa.pos = bs->pos_dev;
+  aa.H = H;
+  aa.n_splits = n_splits;
+  aa.scale = 1.4426950408889634f / sqrtf(128.f);
+  aa.part_o = part_o;
+  aa.part_ml = part_ml;
+  aa.tickets = tickets;
+  aa.att = att;
+  int rc;
+  for (int i = 0; i < w->num_layers; ++i) {
+    if ((rc = launch_norm(st, xb, D, w->ln1_w[i], xn, D, w->rms_eps, NB)) != MERLIN_OK) return rc;
+    BGemvParams p = {};
+    p.W = static_cast<const __nv_bfloat16*>(w->qkv_w[i]);
+    p.x = xn;
+    p.ldx = D;
+    p.out = qbuf;
+    p.ldo = D;
+    p.suffix_kv = static_cast<__nv_bfloat16*>(bs->suffix_kv[i]);
+    p.suffix_stride = suffix_stride;
+    p.rope_cos = w->rope_cos;
+    p.rope_sin = w->rope_sin;
+    p.pos = bs->pos_dev;
+    p.nb = NB;
+    p.N = 3 * D;
+    p.K = D;
+    p.D = D;
+    if ((rc = launch_bgemv<B_QKV_ROPE>(st, p, 3 * D / 2)) != MERLIN_OK) return rc;
+    aa.prefix_kv = static_cast<const __nv_bfloat16*>(bs->prefix_kv[i]);
+    aa.suffix_kv = static_cast<const __nv_bfloat16*>(bs->suffix_kv[i]);
+    switch (NB) {
+      case 1: rc = launch_attention<1>(st, aa); break;
+      case 2: rc = launch_attention<2>(st, aa); break;
+      case 3: rc = launch_attention<3>(st, aa); break;
+      case 4: rc = launch_attention<4>(st, aa); break;
+      case 5: rc = launch_attention<5>(st, aa); break;
+      case 6: rc = launch_attention<6>(st, aa); break;
+      case 7: rc = launch_attention<7>(st, aa); break;
+      default: rc = launch_attention<8>(st, aa); break;
+    }
+    if (rc != MERLIN_OK) return rc;
+    BGemvParams po = {};
+    po.W = static_cast<const __nv_bfloat16*>(w->o_w[i]);
+    po.x = att;
+    po.ldx = D;
+    po.residual = xb;
+    po.out = xb;
+    po.ldo = D;
+    po.nb = NB;
+    po.N = D;
+    po.K = D;
+    po.D = D;
+    if ((rc = launch_bgemv<B_PLAIN>(st, po, D / 2)) != MERLIN_OK) return rc;
+    if ((rc = launch_norm(st, xb, D, w->ln2_w[i], xn, D, w->rms_eps, NB)) != MERLIN_OK) return rc;
+    BGemvParams pg = {};
+    pg.W = static_cast<const __nv_bfloat16*>(w->gate_up_w[i]);
+    pg.x = xn;
+    pg.ldx = D;
+    pg.out = mid;
+    pg.ldo = FF;
+    pg.nb = NB;
+    pg.N = 2 * FF;
+    pg.K = D;
+    pg.D = D;
+    if ((rc = launch_bgemv<B_SWIGLU>(st, pg, FF)) != MERLIN_OK) return rc;
+    BGemvParams pd = {};
+    pd.W = static_cast<const __nv_bfloat16*>(w->down_w[i]);
+    pd.x = mid;
+    pd.ldx = FF;
+    pd.residual = xb;
+    pd.out = xb;
+    pd.ldo = D;
+    pd.nb = NB;
+    pd.N = D;
+    pd.K = FF;
+    pd.D = D;
+    if ((rc = launch_bgemv<B_PLAIN>(st, pd, D / 2)) != MERLIN_OK) return rc;
+  }
+  if ((rc = launch_norm(st, xb, D, w->norm_w, xn, D, w->rms_eps, NB)) != MERLIN_OK) return rc;
+  BGemvParams pl = {};
+  pl.W = static_cast<const __nv_bfloat16*>(w->lm_head_w);
+  pl.x = xn;
+  pl.ldx = D;
+  pl.out = static_cast<__nv_bfloat16*>(logits);
+  pl.ldo = ld_logits;
+  pl.nb = NB;
+  pl.N = w->vocab;
+  pl.K = D;
+  pl.D = D;
+  return launch_bgemv<B_PLAIN>(st, pl, (w->vocab + 1) / 2);
+}
+
+}  // extern "C"

@@ -162,6 +162,97 @@ class DecodeRunner:
         return self.out_ids[base:base + done].clone()
 
 
+BEAM_SPLITS = int(os.environ.get("MERLIN_BEAM_SPLITS", "9"))   # prefix key splits: heads x splits ~ 2 CTAs per SM
+MAX_BEAMS = 8
+
+
+class BeamDecodeRunner:
+    """All beams of a beam search advance one position per `step` (merlin_decode_step_batched): the weights are
+    streamed once for the k beams, the prompt's KV cache (`prefix`, written by the prefill) is shared, and only each
+    beam's own generated tokens live in the per-beam `suffix` cache [L, k, cap/32, H, 32, 256] that a re-ordering has
+    to move.  embed -> decoder pass -> position advance is one CUDA graph; positions live in device memory, so the
+    graph serves every prompt that fits the prefix cache."""
+
+    def __init__(self, lm, prefix, num_beams: int, suffix_capacity: int):
+        if not 1 <= num_beams <= MAX_BEAMS:
+            raise NotImplementedError(f"the batched beam decode handles 1..{MAX_BEAMS} beams (got {num_beams}); "
+                                      "use use_hf_loop=True")
+        m, cfg = lm.model, lm.config
+        dev = lm.device
+        self.lm, self.prefix, self.nb = lm, prefix, num_beams
+        L, H, D = cfg.num_hidden_layers, cfg.num_attention_heads, cfg.hidden_size
+        self.cap = (suffix_capacity + 31) // 32 * 32
+        self.suffix = torch.zeros((L, num_beams, self.cap // 32, H, 32, 256), dtype=torch.bfloat16, device=dev)
+        cos, sin = m.rope_tables(prefix.capacity + self.cap)
+        self._keep = [_ptr_array(list(m.qkv_w)), _ptr_array(list(m.o_w)), _ptr_array(list(m.gate_up_w)),
+                      _ptr_array(list(m.down_w)), _ptr_array(list(m.ln1_w)), _ptr_array(list(m.ln2_w)),
+                      _ptr_array(prefix.kv), _ptr_array([self.suffix[i] for i in range(L)]), cos, sin]
+        cast = lambda a: ctypes.cast(a, ctypes.POINTER(c_void_p))
+        self.w = DecoderWeights(L, D, H, cfg.intermediate_size, cfg.vocab_size, float(cfg.rms_norm_eps),
+                                cast(self._keep[0]), cast(self._keep[1]), cast(self._keep[2]), cast(self._keep[3]),
+                                cast(self._keep[4]), cast(self._keep[5]), m.norm_w.data_ptr(), lm.lm_head_w.data_ptr(),
+                                cast(self._keep[6]), prefix.capacity, cos.data_ptr(), sin.data_ptr())
+        self.pos = torch.zeros(2, dtype=torch.int32, device=dev)          # {prefix_len, t}
+        self.bs = _lib.BeamState(num_beams, self.cap, cast(self._keep[6]), cast(self._keep[7]), self.pos.data_ptr())
+        L_ = _lib.load()
+        self.ws = torch.zeros(L_.merlin_decode_batched_workspace_bytes(D, cfg.intermediate_size, H, BEAM_SPLITS,
+                                                                       num_beams), dtype=torch.uint8, device=dev)
+        self.tokens = torch.zeros(num_beams, dtype=torch.int64, device=dev)
+        self.x = torch.empty((num_beams, D), dtype=torch.bfloat16, device=dev)
+        vpad = (cfg.vocab_size + 7) // 8 * 8
+        self.logits = torch.empty((num_beams, vpad), dtype=torch.bfloat16, device=dev)[:, :cfg.vocab_size]
+        self.one = torch.tensor([0, 1], dtype=torch.int32, device=dev)
+        self.t = 0
+        self.graph = None
+        self.launches_per_step = 7 * L + 2      # per layer: 2 norms, 4 projections, attention; final norm + lm_head
+        self.fingerprint = weight_fingerprint(lm)
+        if os.environ.get("MERLIN_BEAM_GRAPH", "1") == "1":
+            self.ensure_graph()
+
+    def _body(self):
+        torch.index_select(self.lm.model.embed_tokens, 0, self.tokens, out=self.x)
+        check(_lib.load().merlin_decode_step_batched(torch.cuda.current_stream().cuda_stream, ctypes.byref(self.w),
+                                                     ctypes.byref(self.bs), self.x.data_ptr(), self.ws.data_ptr(),
+                                                     self.logits.data_ptr(), self.logits.stride(0), BEAM_SPLITS),
+              "merlin_decode_step_batched")
+        self.pos.add_(self.one)
+
+    def ensure_graph(self):
+        if self.graph is not None:
+            return
+        self.pos.zero_()
+        self._body()                      # warm-up outside capture; scribbles on suffix row 0 (no search is running yet)
+        torch.cuda.synchronize()
+        g = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(g, capture_error_mode="thread_local"):
+            self._body()
+        self.graph = g
+
+    def begin(self, prefix_len: int):
+        if prefix_len > self.prefix.capacity:
+            raise RuntimeError("prompt longer than the prefix cache")
+        self.pos.copy_(torch.tensor([prefix_len, 0], dtype=torch.int32), non_blocking=False)
+        self.t = 0
+
+    def step(self, tokens, parents=None, use_graph: bool = True) -> torch.Tensor:
+        """tokens[k]: the token each beam appends; parents[k]: the beam (of the previous step) it descends from.
+        Returns the [k, V] bf16 logits of the next position (a view of a static buffer)."""
+        if self.t >= self.cap:
+            raise RuntimeError("beam suffix cache is full")
+        if parents is not None and self.t > 0 and list(parents) != list(range(self.nb)):
+            nblk = (self.t + 31) // 32      # only the blocks that hold generated tokens move
+            idx = torch.as_tensor(list(parents), dtype=torch.int64, device=self.suffix.device)
+            self.suffix[:, :, :nblk].copy_(self.suffix[:, :, :nblk].index_select(1, idx))
+        self.tokens.copy_(torch.as_tensor(tokens, dtype=torch.int64), non_blocking=False)
+        if use_graph and self.graph is not None:
+            self.graph.replay()
+        else:
+            self._body()
+        self.t += 1
+        _ops.PROFILE.launches += self.launches_per_step + 2
+        return self.logits
+
+
 class DecodeState:
     """KV cache + DecodeRunner (+ its per-token CUDA graph) for one capacity bucket.  The decode graph reads the
     position from device memory, so ONE state serves every prompt length that fits the bucket."""

@@ -57,6 +57,7 @@ _PROTOTYPES = {
     "merlin_vit_embed": [_P, _P, _P, _P, _P, c_int, c_int, c_int],
     "merlin_vit_embed_bwd": [_P, _P, _P, _P, _P, c_int, c_int, c_int],
     "merlin_decode_step": [_P, _P, _P, _P, _P, _P, c_int],
+    "merlin_decode_step_batched": [_P, _P, _P, _P, _P, _P, c_int64, c_int],
     "merlin_decode_stream_prepare": [_P, _P, _P],
     "merlin_decode_stream_step": [_P, _P, _P, _P, _P, _P],
     "merlin_embed_token": [_P, _P, _P, _P, c_int, c_int64],
@@ -89,6 +90,12 @@ class DecoderWeights(ctypes.Structure):
                 ("norm_w", c_void_p), ("lm_head_w", c_void_p),
                 ("kv_cache", ctypes.POINTER(c_void_p)), ("kv_capacity", c_int64),
                 ("rope_cos", c_void_p), ("rope_sin", c_void_p)]
+
+
+class BeamState(ctypes.Structure):
+    """struct merlin_beam_state."""
+    _fields_ = [("num_beams", c_int), ("suffix_capacity", c_int64), ("prefix_kv", ctypes.POINTER(c_void_p)),
+                ("suffix_kv", ctypes.POINTER(c_void_p)), ("pos_dev", c_void_p)]
 
 
 class LayerWeights(ctypes.Structure):
@@ -145,6 +152,7 @@ _PROTOTYPES["merlin_decoder_layer_backward"] = [_P, _P, _P, _P, _P, _P, _P, _P, 
                                                 c_float, c_int, c_int]
 _SIZE_FNS = {"merlin_decoder_layer_saved_bytes": [c_int, c_int, c_int, c_int, c_int, c_int],
              "merlin_decoder_layer_backward_workspace_bytes": [c_int, c_int, c_int, c_int, c_int, c_int],"merlin_decode_workspace_bytes": [c_int, c_int, c_int, c_int],
+             "merlin_decode_batched_workspace_bytes": [c_int, c_int, c_int, c_int, c_int],
              "merlin_decode_stream_workspace_bytes": [c_int, c_int, c_int, c_int],
              "merlin_image_preprocess_workspace_bytes": [c_int, c_int, c_int],
              "merlin_projector_workspace_bytes": [c_int, c_int, c_int, c_int],

@@ -595,54 +595,54 @@ class MMGPTLlamaForCausalLM(PreTrainedModel, GenerationMixin, MMGPTMetaForCausal
     @torch.no_grad()
     def _generate_beam(self, input_ids, images, num_beams, max_new_tokens, eos_token_id, stopping_criteria,
                        length_penalty, early_stopping, length_norm):
-        """generate(num_beams=k) (eval_box.py:246-254): ONE multimodal prefill (the reference prefills k
-        identical copies, base_mmgpt.py:162-163), then k single-sequence decode steps per position — each beam
-        has its own KV cache and decode kernel binding — with the beam bookkeeping of merlin_b200/beam.py
-        (pinned against HF `generate`) on the host and the caches re-gathered by parent beam after every step,
-        as HF's `_reorder_cache` does."""
+        """generate(num_beams=k) (eval_box.py:246-254): ONE multimodal prefill (the reference prefills k identical
+        copies, base_mmgpt.py:162-163) into the SHARED prefix cache, then one batched decode pass per position for
+        all k beams (merlin_decode_step_batched: weights streamed once, per-beam suffix caches) with the beam
+        bookkeeping of merlin_b200/beam.py (pinned against HF `generate`); log-softmax and the top-2k selection run
+        on the GPU, and a re-ordering moves only the beams' generated-token blocks (HF re-orders the whole cache)."""
         from ....beam import BeamSearch
         device = self.device
         ids = input_ids.to(device)
         S = ids.shape[1]
-        self._cache_capacity = S + max_new_tokens + 8
+        runner = self._beam_runner(num_beams, S, max_new_tokens)
+        runner.prefix.seq_len = 0
         flag, self.use_beam_search = getattr(self, "use_beam_search", False), False
         try:
-            out = self.forward(**self.prepare_inputs_for_generation(ids, None, None, use_cache=True, images=images))
+            inputs = self.prepare_inputs_for_generation(ids, None, None, use_cache=True, images=images)
+            inputs["past_key_values"] = runner.prefix          # empty: the prefill fills it
+            out = self.forward(**inputs)
         finally:
             self.use_beam_search = flag
-        cfg = self.config
-        caches = [out.past_key_values]
-        for _ in range(2 * num_beams - 1):      # beams 1..k-1 and k spares for the re-gather
-            caches.append(MerlinKVCache(cfg.num_hidden_layers, 1, caches[0].capacity, cfg.hidden_size, device))
-        blocks = lambda n: (n + 31) // 32
-
-        def copy_cache(dst, src, n_tokens):
-            for a, b in zip(dst.kv, src.kv):
-                a[:, :blocks(n_tokens)].copy_(b[:, :blocks(n_tokens)])
-            dst.seq_len = src.seq_len
-
-        for c in caches[1:num_beams]:
-            copy_cache(c, caches[0], S)
-        live, spare = caches[:num_beams], caches[num_beams:]
-        runners = {id(c): _decode.DecodeRunner(self, c) for c in caches}
+        runner.begin(S)
         bs = BeamSearch(input_ids.cpu(), num_beams, eos_token_id, max_new_tokens, length_penalty, early_stopping,
                         length_norm, stopping_criteria)
         res = bs.step(out.logits[:, -1, :].float().repeat(num_beams, 1))
-        logits = torch.empty((num_beams, cfg.vocab_size), dtype=torch.float32, device=device)
         while res is not None:
             tokens, parents = res
-            # beam j continues parent[j]: gather the caches (copies only where the parent changed)
-            moved = [j for j in range(num_beams) if parents[j] != j]
-            for j in moved:
-                copy_cache(spare[j], live[parents[j]], live[parents[j]].seq_len)
-            for j in moved:
-                live[j], spare[j] = spare[j], live[j]
-            tok = torch.tensor(tokens, dtype=torch.int64, device=device)
-            emb = self.model.embed_tokens[tok]
-            for j in range(num_beams):
-                logits[j].copy_(runners[id(live[j])].step_logits(emb[j:j + 1])[0])
-            res = bs.step(logits)
+            res = bs.step(runner.step(tokens, parents))
         return bs.finalize().to(device)
+
+    def _beam_runner(self, num_beams: int, S: int, max_new_tokens: int):
+        """Prefix cache + batched decode runner (+ its CUDA graph) per (beam count, capacity bucket)."""
+        bucket = _decode.CAPACITY_BUCKET
+        cap = (S + 8 + bucket - 1) // bucket * bucket
+        scap = (max_new_tokens + 8 + 255) // 256 * 256
+        pool = self.__dict__.setdefault("_beam_runners", {})
+        fp = _decode.weight_fingerprint(self)
+        for key in [k for k, r in pool.items() if r.fingerprint != fp]:
+            pool.pop(key)
+        fit = [k for k in pool if k[0] == num_beams and k[1] >= cap and k[2] >= scap]
+        if fit:
+            return pool[min(fit)]
+        for key in [k for k in pool if k[0] == num_beams]:      # one runner per beam count: the larger one replaces it
+            cap, scap = max(cap, key[1]), max(scap, key[2])
+            pool.pop(key)
+        while len(pool) >= _decode.MAX_DECODE_STATES:
+            pool.pop(next(iter(pool)))
+        cfg = self.config
+        prefix = MerlinKVCache(cfg.num_hidden_layers, 1, cap, cfg.hidden_size, self.device)
+        runner = pool[(num_beams, cap, scap)] = _decode.BeamDecodeRunner(self, prefix, num_beams, scap)
+        return runner
 
     # generation keywords understood natively (HF names); anything else must go through use_hf_loop=True
     _GEN_KEYS = ("max_new_tokens", "max_length", "min_new_tokens", "do_sample", "temperature", "top_p", "top_k",
