@@ -128,7 +128,7 @@ def full(ctx=4096, layers=32, check=True):
     print(f"copy bandwidth {copy_bandwidth():.0f} GB/s", flush=True)
     if check:
         compare(model, ctx, steps=3, label="7B", verbose=os.environ.get("VERBOSE") == "1")
-    for mode in ("kernels", "stream"):
+    for mode in os.environ.get("MODES", "kernels,stream").split(","):
         cache = MerlinKVCache(layers, 1, ctx + 128, cfg.hidden_size, DEV)
         for kv in cache.kv:
             kv.normal_(0, 0.5)
