@@ -26,7 +26,16 @@ trainer = MMGPTTrainer(model, TrainingArguments(learning_rate=1e-5, max_steps=10
 labels = ids_h.clone()
 labels[:, : bench.SEQ_LEN // 2] = -100
 batch = {"input_ids": ids_h, "labels": labels, "attention_mask": None, "images": [img_d]}
-for _ in range(int(os.environ.get("MERLIN_STEPS", "1"))):
+n_steps = int(os.environ.get("MERLIN_STEPS", "1"))
+timed = os.environ.get("MERLIN_TIME") == "1" and n_steps > 3      # MERLIN_TIME=1: 3 warm-up steps, the rest timed
+e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+for i in range(n_steps):
+    if timed and i == 3:
+        torch.cuda.synchronize()
+        e0.record()
     loss = trainer.training_step(batch)
+e1.record()
 torch.cuda.synchronize()
+if timed:
+    print("train ms/step", e0.elapsed_time(e1) / (n_steps - 3))
 print("loss", float(loss), "peak GB", torch.cuda.max_memory_allocated() / 1e9)
