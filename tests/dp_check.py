@@ -2,7 +2,7 @@
 weights must be identical across ranks and equal to a single-process run on the averaged gradient."""
 import os, sys
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
-sys.path.insert(0, os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "tests"))
+sys.path.insert(0, os.path.dirname(os.path.abspath(__file__)))
 import torch
 import torch.distributed as dist
 from helpers import build_product_model

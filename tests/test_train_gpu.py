@@ -156,7 +156,7 @@ def test_vision_tower_gradients_match_oracle_autograd(name):
 def test_data_parallel_replicas_stay_bit_identical():
     """2-rank NCCL run (needs >= 2 GPUs; the 1-GPU driver box skips it): different batches per rank, bucketed
     all-reduce overlapped with backward, AdamW — gradients, moments and weights must be bit-identical on
-    both ranks after every step (scripts/dp_check.py exits non-zero otherwise)."""
+    both ranks after every step (tests/dp_check.py exits non-zero otherwise)."""
     import os
     import subprocess
     import sys
@@ -165,7 +165,7 @@ def test_data_parallel_replicas_stay_bit_identical():
     root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
     r = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2",
                         "--master-addr", "127.0.0.1", "--master-port", "29533",
-                        os.path.join(root, "scripts", "dp_check.py")], capture_output=True, text=True, timeout=600)
+                        os.path.join(root, "tests", "dp_check.py")], capture_output=True, text=True, timeout=600)
     assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]
     assert "weights identical across ranks: True" in r.stdout
 
