@@ -384,6 +384,24 @@ def torch_gpu_detail(device, steps=2):
             "tokens_per_s": (SEQ_LEN + DECODE_TOKENS) / ((pre + dec) / 1e3)}
 
 
+def beam_detail(model, ids_d, img_d, timed, num_beams=5):
+    """Context: the reference's evaluation setting `generate(num_beams=5)` (eval_box.py:246-254) on the same prompt —
+    one shared prefill, then DECODE_TOKENS positions for all beams through merlin_decode_step_batched (the weights are
+    streamed once per position whatever the beam count).  `step_ms` = one graph-replayed position, device time."""
+    def run():
+        return model.generate(ids_d, images=[img_d], num_beams=num_beams, max_new_tokens=DECODE_TOKENS + 1,
+                              eos_token_id=None)
+    run()
+    full_ms, _ = timed(run, 2)
+    runner = model._beam_runner(num_beams, SEQ_LEN, DECODE_TOKENS + 1)
+    runner.begin(SEQ_LEN)
+    toks = list(range(100, 100 + num_beams))
+    runner.step(toks, None)
+    step_ms, _ = timed(lambda: runner.graph.replay(), DECODE_TOKENS - 1)
+    return {"num_beams": num_beams, "generate_ms": full_ms / 2, "step_ms": step_ms / (DECODE_TOKENS - 1),
+            "positions": DECODE_TOKENS}
+
+
 def train_detail(model, input_ids_h, img_d, world, device, timed, steps=3):
     """Data-parallel training step on the same sample shape (extra information, not the headline):
     forward + backward + bucketed NCCL all-reduce of the bf16 gradients (merlin_dp_*, overlapped with backward) +
@@ -544,6 +562,12 @@ def main():
             torch_gpu = torch_gpu_detail(device)
         except Exception as e:  # context only: never break the bench line
             torch_gpu = {"error": str(e)[:300]}
+    beam = None
+    if rank == 0 and world == 1 and os.environ.get("MERLIN_BENCH_BEAM", "1") == "1":
+        try:
+            beam = beam_detail(model, ids_d, img_d, timed)
+        except Exception as e:  # context only: never break the bench line
+            beam = {"error": str(e)[:300]}
     train = train_detail(model, input_ids_h, img_d, world, device, timed) if os.environ.get("MERLIN_BENCH_TRAIN", "1") == "1" else None
 
     tokens = SEQ_LEN + DECODE_TOKENS
@@ -600,6 +624,9 @@ def main():
         line["detail"]["train"] = train
     if torch_gpu is not None:
         line["detail"]["torch_gpu"] = torch_gpu
+    if beam is not None:
+        beam["ms_per_position_e2e"] = (beam["generate_ms"] - pre_ms) / DECODE_TOKENS
+        line["detail"]["beam5"] = beam
     if rank == 0 and world == 1 and os.environ.get("MERLIN_BENCH_CPU", "1") == "1":
         try:
             arm = ReferenceCpuArm()

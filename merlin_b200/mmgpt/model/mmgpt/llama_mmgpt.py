@@ -601,6 +601,9 @@ class MMGPTLlamaForCausalLM(PreTrainedModel, GenerationMixin, MMGPTMetaForCausal
         bookkeeping of merlin_b200/beam.py (pinned against HF `generate`); log-softmax and the top-2k selection run
         on the GPU, and a re-ordering moves only the beams' generated-token blocks (HF re-orders the whole cache)."""
         from ....beam import BeamSearch
+        if num_beams > _decode.MAX_BEAMS:
+            return self._generate_beam_sequential(input_ids, images, num_beams, max_new_tokens, eos_token_id,
+                                                  stopping_criteria, length_penalty, early_stopping, length_norm)
         device = self.device
         ids = input_ids.to(device)
         S = ids.shape[1]
@@ -620,6 +623,55 @@ class MMGPTLlamaForCausalLM(PreTrainedModel, GenerationMixin, MMGPTMetaForCausal
         while res is not None:
             tokens, parents = res
             res = bs.step(runner.step(tokens, parents))
+        return bs.finalize().to(device)
+
+    @torch.no_grad()
+    def _generate_beam_sequential(self, input_ids, images, num_beams, max_new_tokens, eos_token_id, stopping_criteria,
+                       length_penalty, early_stopping, length_norm):
+        """More than 8 beams: k single-sequence decode steps per position, one full KV cache per beam re-gathered by
+        parent (HF's `_reorder_cache` scheme).  The batched path (`_generate_beam`) covers k <= 8."""
+        from ....beam import BeamSearch
+        device = self.device
+        ids = input_ids.to(device)
+        S = ids.shape[1]
+        self._cache_capacity = S + max_new_tokens + 8
+        flag, self.use_beam_search = getattr(self, "use_beam_search", False), False
+        try:
+            out = self.forward(**self.prepare_inputs_for_generation(ids, None, None, use_cache=True, images=images))
+        finally:
+            self.use_beam_search = flag
+        cfg = self.config
+        caches = [out.past_key_values]
+        for _ in range(2 * num_beams - 1):      # beams 1..k-1 and k spares for the re-gather
+            caches.append(MerlinKVCache(cfg.num_hidden_layers, 1, caches[0].capacity, cfg.hidden_size, device))
+        blocks = lambda n: (n + 31) // 32
+
+        def copy_cache(dst, src, n_tokens):
+            for a, b in zip(dst.kv, src.kv):
+                a[:, :blocks(n_tokens)].copy_(b[:, :blocks(n_tokens)])
+            dst.seq_len = src.seq_len
+
+        for c in caches[1:num_beams]:
+            copy_cache(c, caches[0], S)
+        live, spare = caches[:num_beams], caches[num_beams:]
+        runners = {id(c): _decode.DecodeRunner(self, c) for c in caches}
+        bs = BeamSearch(input_ids.cpu(), num_beams, eos_token_id, max_new_tokens, length_penalty, early_stopping,
+                        length_norm, stopping_criteria)
+        res = bs.step(out.logits[:, -1, :].float().repeat(num_beams, 1))
+        logits = torch.empty((num_beams, cfg.vocab_size), dtype=torch.float32, device=device)
+        while res is not None:
+            tokens, parents = res
+            # beam j continues parent[j]: gather the caches (copies only where the parent changed)
+            moved = [j for j in range(num_beams) if parents[j] != j]
+            for j in moved:
+                copy_cache(spare[j], live[parents[j]], live[parents[j]].seq_len)
+            for j in moved:
+                live[j], spare[j] = spare[j], live[j]
+            tok = torch.tensor(tokens, dtype=torch.int64, device=device)
+            emb = self.model.embed_tokens[tok]
+            for j in range(num_beams):
+                logits[j].copy_(runners[id(live[j])].step_logits(emb[j:j + 1])[0])
+            res = bs.step(logits)
         return bs.finalize().to(device)
 
     def _beam_runner(self, num_beams: int, S: int, max_new_tokens: int):
