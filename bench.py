@@ -529,31 +529,50 @@ def main():
     gen = next(iter(model._graphed.values()))
     pre_ms, _ = timed(gen.graph.replay, args.steps)
     pre_ms /= args.steps
-    # The dominant kernel of the step is the decode kernel (32 launches x ~3 ms of a ~150 ms step): time it launch
-    # by launch with a CUDA event pair on the launching stream, at the positions the timed steps decode (context
-    # 4096 .. 4127).  Each launch is the replay of a ONE-node CUDA graph holding just that kernel — the way the
-    # timed steps launch it (an eager cooperative launch adds ~0.1 ms of driver-side latency between the event
-    # and the kernel that the graph-replayed loop does not pay).
+    # The dominant kernel of the step is the decode kernel (32 launches x ~3 ms of a ~150 ms step).  Its launch
+    # duration is measured with CUDA events on the launching stream at the positions the timed steps decode (context
+    # 4096 .. 4127), the way the timed steps launch it: back to back from a CUDA graph.  One graph holds
+    # kGroup x (decode_stream_kernel, 3 us position increment); each replay is bracketed by an event pair and
+    # contributes kGroup launches.  (An event pair around every single launch measures 0.1 ms more per launch than
+    # the kernel takes inside the decode loop: the gap between the event and a cooperative launch, which back-to-back
+    # launches do not pay.  `single_launch_event_ms` keeps that number for comparison.)
     runner = gen.runner
-    dec_kernel_ms = []
+    dec_kernel_ms, single_launch_ms = [], None
     if runner.mode == "stream":
+        kGroup = 8
+        st = torch.cuda.current_stream().cuda_stream
         runner.pos.fill_(SEQ_LEN)
-        runner._decode_step(torch.cuda.current_stream().cuda_stream)
+        runner._decode_step(st)
         torch.cuda.synchronize()
-        one = torch.cuda.CUDAGraph()
+        one, group = torch.cuda.CUDAGraph(), torch.cuda.CUDAGraph()
         with torch.cuda.graph(one):
             runner._decode_step(torch.cuda.current_stream().cuda_stream)
+        with torch.cuda.graph(group):
+            for _ in range(kGroup):
+                runner._decode_step(torch.cuda.current_stream().cuda_stream)
+                runner.pos.add_(1)
+        runner.pos.fill_(SEQ_LEN)
+        group.replay()                                     # warm-up
         runner.pos.fill_(SEQ_LEN)
         pairs = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True))
-                 for _ in range(DECODE_TOKENS + 2)]
+                 for _ in range(DECODE_TOKENS // kGroup)]
         torch.cuda.synchronize()
-        for k0, k1 in pairs:          # back to back like the graph-replayed loop, one sync at the end
+        for k0, k1 in pairs:
+            k0.record()
+            group.replay()
+            k1.record()
+        torch.cuda.synchronize()
+        for k0, k1 in pairs:
+            dec_kernel_ms += [k0.elapsed_time(k1) / kGroup] * kGroup
+        runner.pos.fill_(SEQ_LEN)
+        singles = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(10)]
+        for k0, k1 in singles:
             k0.record()
             one.replay()
             k1.record()
             runner.pos.add_(1)
         torch.cuda.synchronize()
-        dec_kernel_ms = [k0.elapsed_time(k1) for k0, k1 in pairs[2:]]
+        single_launch_ms = statistics.mean(k0.elapsed_time(k1) for k0, k1 in singles[2:])
     step_host()
     e2e_ms, _ = timed(step_host, args.steps)
     torch_gpu = None
@@ -591,6 +610,8 @@ def main():
                     "traffic_note": "dram__bytes_read+write of ONE launch from profiles/r1_decode_stream_metrics.csv (algorithmic %.2f GB)" % (dec_bytes / 1e9),
                     "kernel": "decode_stream_kernel (whole decode step: 1 persistent launch per token, TMA weight/KV ring)",
                     "launches_timed": len(dec_kernel_ms), "avg_launch_ms": dk_ms,
+                    "timing": "CUDA events around graph replays of 8 back-to-back launches (+ a position increment each)",
+                    "single_launch_event_ms": single_launch_ms,
                     "share_of_step": DECODE_TOKENS * dk_ms / ms_per_step,
                     "peak_source": "measured (MEASURED_PEAKS.json, hbm_gbs)" if "measured" in peaks["source"] else peaks["source"]}
     else:
