@@ -23,6 +23,7 @@
 
 #include <algorithm>
 #include <cmath>
+#include <cstring>
 
 namespace mb {
 namespace {
@@ -56,6 +57,24 @@ __device__ __forceinline__ uint4 ldg_stream(const uint4* p) {
                : "=r"(r.x), "=r"(r.y), "=r"(r.z), "=r"(r.w)
                : "l"(p));
   return r;
+}
+// 32 bytes per lane in one instruction (LDG.E.256): a warp-level load covers whole 128-byte lines
+struct U8 {
+  uint32_t r[8];
+};
+__device__ __forceinline__ U8 ldg_stream256(const void* p) {
+  U8 v;
+  asm volatile("ld.global.nc.L1::no_allocate.v8.b32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];"
+               : "=r"(v.r[0]), "=r"(v.r[1]), "=r"(v.r[2]), "=r"(v.r[3]), "=r"(v.r[4]), "=r"(v.r[5]), "=r"(v.r[6]), "=r"(v.r[7])
+               : "l"(p));
+  return v;
+}
+__device__ __forceinline__ U8 ld256(const void* p) {
+  U8 v;
+  asm volatile("ld.global.v8.b32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];"
+               : "=r"(v.r[0]), "=r"(v.r[1]), "=r"(v.r[2]), "=r"(v.r[3]), "=r"(v.r[4]), "=r"(v.r[5]), "=r"(v.r[6]), "=r"(v.r[7])
+               : "l"(p));
+  return v;
 }
 __device__ __forceinline__ float sumsq8(const uint4& v) {
   float s = bf16_lo(v.x) * bf16_lo(v.x);
@@ -120,6 +139,70 @@ norm_beams_kernel(const __nv_bfloat16* __restrict__ x, int64_t ldx, const __nv_b
       o.z = pack_bf16(bf16_lo(w.z) * (bf16_lo(v[u].z) * rstd), bf16_hi(w.z) * (bf16_hi(v[u].z) * rstd));
       o.w = pack_bf16(bf16_lo(w.w) * (bf16_lo(v[u].w) * rstd), bf16_hi(w.w) * (bf16_hi(v[u].w) * rstd));
       dst[i] = o;
+    }
+  }
+}
+
+template <int kMode>
+__device__ __forceinline__ void pair_rows(const BGemvParams& p, int pair, int& row_a, int& row_b) {
+  if (kMode == B_QKV_ROPE) {
+    if (pair < p.D) {                       // q and k blocks: RoPE pair (j, j + 64) of one head
+      row_a = (pair >> 6) * 128 + (pair & 63);
+      row_b = row_a + 64;
+    } else {
+      row_a = 2 * p.D + 2 * (pair - p.D);
+      row_b = row_a + 1;
+    }
+  } else if (kMode == B_SWIGLU) {
+    row_a = (pair >> 7) * 256 + (pair & 127);
+    row_b = row_a + 128;
+  } else {
+    row_a = 2 * pair;
+    row_b = row_a + 1;
+  }
+}
+
+// lane (g, t) holds rows (row_a, row_b) of pair g for beams 2t and 2t + 1 in c[0..1] / c[2..3]
+template <int kMode>
+__device__ __forceinline__ void beams_epilogue(const BGemvParams& p, const float (&c)[4], int row_a, int row_b, bool has_b,
+                                               int t) {
+#pragma unroll
+  for (int half = 0; half < 2; ++half) {
+    const int beam = 2 * t + half;
+    if (beam >= p.nb) continue;
+    float va = c[half], vb = c[2 + half];
+    if (kMode == B_QKV_ROPE) {
+      const int tok = p.pos[1];
+      const int position = p.pos[0] + tok;
+      const int H = p.D >> 7;
+      __nv_bfloat16* kvb = p.suffix_kv + static_cast<size_t>(beam) * p.suffix_stride;
+      auto kv_at = [&](int e, int which) { return kvb + kv_off(e >> 7, tok, H) + which * 128 + (e & 127); };
+      if (row_a < 2 * p.D) {
+        const int j = row_a & 63;
+        const float cs = p.rope_cos[static_cast<size_t>(position) * 64 + j];
+        const float sn = p.rope_sin[static_cast<size_t>(position) * 64 + j];
+        const float lo = va * cs - vb * sn, hi = vb * cs + va * sn;
+        if (row_a < p.D) {
+          p.out[static_cast<size_t>(beam) * p.ldo + row_a] = __float2bfloat16_rn(lo);
+          p.out[static_cast<size_t>(beam) * p.ldo + row_b] = __float2bfloat16_rn(hi);
+        } else {
+          *kv_at(row_a - p.D, 0) = __float2bfloat16_rn(lo);
+          *kv_at(row_b - p.D, 0) = __float2bfloat16_rn(hi);
+        }
+      } else {
+        *kv_at(row_a - 2 * p.D, 1) = __float2bfloat16_rn(va);
+        *kv_at(row_b - 2 * p.D, 1) = __float2bfloat16_rn(vb);
+      }
+    } else if (kMode == B_SWIGLU) {
+      p.out[static_cast<size_t>(beam) * p.ldo + (row_a >> 8) * 128 + (row_a & 127)] =
+          __float2bfloat16_rn(va / (1.f + __expf(-va)) * vb);
+    } else {
+      if (p.residual) {
+        va += __bfloat162float(p.residual[static_cast<size_t>(beam) * p.ldo + row_a]);
+        if (has_b) vb += __bfloat162float(p.residual[static_cast<size_t>(beam) * p.ldo + row_b]);
+      }
+      p.out[static_cast<size_t>(beam) * p.ldo + row_a] = __float2bfloat16_rn(va);
+      if (has_b) p.out[static_cast<size_t>(beam) * p.ldo + row_b] = __float2bfloat16_rn(vb);
     }
   }
 }
@@ -219,46 +302,74 @@ gemv_beams_kernel(const BGemvParams p) {
     c[2] += red[w][lane][2];
     c[3] += red[w][lane][3];
   }
-  // lane (g, t) holds rows (row_a, row_b) of pair g for beams 2t and 2t + 1
+  beams_epilogue<kMode>(p, c, row_a, row_b, has_b, t);
+}
+
+// The same product with 256-bit loads: a K block is 64 elements, lane (g, t) loads the 32 bytes at offset 32 t of
+// row_a(g), row_b(g) and of beam g's activation, so one warp-level load covers eight whole 128-byte lines; four MMAs
+// per block.  kDepth blocks per warp are in flight in a register ring (a slot is reloaded as soon as it is consumed):
+// 2 for the wide projections (four CTAs per SM), 4 for o_proj / down_proj whose 256 CTAs do not fill the chip otherwise.
+template <int kMode, int kDepth>
+__global__ void __launch_bounds__(kBThreads, kDepth <= 2 ? 4 : 2)
+gemv_beams256_kernel(const BGemvParams p) {
+  __shared__ float red[kBWarps][32][4];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int g = lane >> 2, t = lane & 3;
+  int row_a, row_b;
+  pair_rows<kMode>(p, blockIdx.x * 8 + g, row_a, row_b);
+  const bool active = row_a < p.N;
+  const bool has_b = row_b < p.N;
+  const int nblk = p.K >> 6;
+  const uint8_t* wa = reinterpret_cast<const uint8_t*>(p.W + static_cast<size_t>(active ? row_a : 0) * p.K) + t * 32;
+  const uint8_t* wb = reinterpret_cast<const uint8_t*>(p.W + static_cast<size_t>(has_b ? row_b : (active ? row_a : 0)) * p.K) + t * 32;
+  U8 a[kDepth], b[kDepth];
 #pragma unroll
-  for (int half = 0; half < 2; ++half) {
-    const int beam = 2 * t + half;
-    if (beam >= p.nb) continue;
-    float va = c[half], vb = c[2 + half];
-    if (kMode == B_QKV_ROPE) {
-      const int tok = p.pos[1];
-      const int position = p.pos[0] + tok;
-      const int H = p.D >> 7;
-      __nv_bfloat16* kvb = p.suffix_kv + static_cast<size_t>(beam) * p.suffix_stride;
-      auto kv_at = [&](int e, int which) { return kvb + kv_off(e >> 7, tok, H) + which * 128 + (e & 127); };
-      if (row_a < 2 * p.D) {
-        const int j = row_a & 63;
-        const float cs = p.rope_cos[static_cast<size_t>(position) * 64 + j];
-        const float sn = p.rope_sin[static_cast<size_t>(position) * 64 + j];
-        const float lo = va * cs - vb * sn, hi = vb * cs + va * sn;
-        if (row_a < p.D) {
-          p.out[static_cast<size_t>(beam) * p.ldo + row_a] = __float2bfloat16_rn(lo);
-          p.out[static_cast<size_t>(beam) * p.ldo + row_b] = __float2bfloat16_rn(hi);
-        } else {
-          *kv_at(row_a - p.D, 0) = __float2bfloat16_rn(lo);
-          *kv_at(row_b - p.D, 0) = __float2bfloat16_rn(hi);
-        }
-      } else {
-        *kv_at(row_a - 2 * p.D, 1) = __float2bfloat16_rn(va);
-        *kv_at(row_b - 2 * p.D, 1) = __float2bfloat16_rn(vb);
-      }
-    } else if (kMode == B_SWIGLU) {
-      p.out[static_cast<size_t>(beam) * p.ldo + (row_a >> 8) * 128 + (row_a & 127)] =
-          __float2bfloat16_rn(va / (1.f + __expf(-va)) * vb);
-    } else {
-      if (p.residual) {
-        va += __bfloat162float(p.residual[static_cast<size_t>(beam) * p.ldo + row_a]);
-        if (has_b) vb += __bfloat162float(p.residual[static_cast<size_t>(beam) * p.ldo + row_b]);
-      }
-      p.out[static_cast<size_t>(beam) * p.ldo + row_a] = __float2bfloat16_rn(va);
-      if (has_b) p.out[static_cast<size_t>(beam) * p.ldo + row_b] = __float2bfloat16_rn(vb);
+  for (int d = 0; d < kDepth; ++d) {
+    const int blk = warp + kBWarps * d;
+    a[d] = U8{};
+    b[d] = U8{};
+    if (blk < nblk) {
+      a[d] = ldg_stream256(wa + blk * 128);
+      b[d] = ldg_stream256(wb + blk * 128);
     }
   }
+  asm volatile("griddepcontrol.wait;" ::: "memory");
+  asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+  const bool beam_live = g < p.nb;
+  const uint8_t* xrow = reinterpret_cast<const uint8_t*>(p.x + static_cast<size_t>(beam_live ? g : 0) * p.ldx) + t * 32;
+  float c[4] = {0.f, 0.f, 0.f, 0.f};
+  for (int base = warp; base < nblk; base += kBWarps * kDepth) {
+#pragma unroll
+    for (int d = 0; d < kDepth; ++d) {
+      const int blk = base + kBWarps * d;
+      if (blk < nblk) {                         // warp-uniform
+        U8 xv = {};
+        if (beam_live) xv = ld256(xrow + blk * 128);
+#pragma unroll
+        for (int j = 0; j < 4; ++j)
+          mma_16816(c, a[d].r[2 * j], b[d].r[2 * j], a[d].r[2 * j + 1], b[d].r[2 * j + 1], xv.r[2 * j], xv.r[2 * j + 1]);
+        const int nxt = blk + kBWarps * kDepth;
+        if (nxt < nblk) {
+          a[d] = ldg_stream256(wa + nxt * 128);
+          b[d] = ldg_stream256(wb + nxt * 128);
+        }
+      }
+    }
+  }
+  red[warp][lane][0] = c[0];
+  red[warp][lane][1] = c[1];
+  red[warp][lane][2] = c[2];
+  red[warp][lane][3] = c[3];
+  __syncthreads();
+  if (warp != 0 || !active) return;
+#pragma unroll
+  for (int w = 1; w < kBWarps; ++w) {
+    c[0] += red[w][lane][0];
+    c[1] += red[w][lane][1];
+    c[2] += red[w][lane][2];
+    c[3] += red[w][lane][3];
+  }
+  beams_epilogue<kMode>(p, c, row_a, row_b, has_b, t);
 }
 
 // ---- attention of all beams for one head.  Grid (H, n_splits + 1): CTAs y < n_splits walk a key range of the SHARED
@@ -285,6 +396,14 @@ beam_attention_kernel(const __nv_bfloat16* __restrict__ q, int64_t ldq, const __
   const int d = threadIdx.x;
   auto load_row = [&](const __nv_bfloat16* kv, int key, uint4 (&r)[2 * kVecs], bool stream) {
     const __nv_bfloat16* row = kv + kv_off(h, key, H) + sub * kDims;
+    if (kVecs == 2 && stream) {   // 32 bytes of k and of v per lane: one 256-bit load each (whole sectors per request)
+      const U8 k8 = ldg_stream256(row), v8 = ldg_stream256(row + 128);
+      r[0] = make_uint4(k8.r[0], k8.r[1], k8.r[2], k8.r[3]);
+      r[kVecs - 1] = make_uint4(k8.r[4], k8.r[5], k8.r[6], k8.r[7]);
+      r[kVecs] = make_uint4(v8.r[0], v8.r[1], v8.r[2], v8.r[3]);
+      r[2 * kVecs - 1] = make_uint4(v8.r[4], v8.r[5], v8.r[6], v8.r[7]);
+      return;
+    }
 #pragma unroll
     for (int i = 0; i < kVecs; ++i) {
       if (stream) {
@@ -466,6 +585,245 @@ beam_attention_kernel(const __nv_bfloat16* __restrict__ q, int64_t ldq, const __
   }
 }
 
+// ---- the same attention with the prefix part on the tensor cores (default).  The FMA kernel above spends ~80
+// instructions per (key, beam) and is instruction-bound from 3 beams on (42 us per layer at 5 beams against 10 us of
+// HBM time); here a warp handles 16 keys per step for ALL beams with 32 MMAs:
+//   S[beam, key] = Q K^T : A = Q (rows 0-7 = beams, rows 8-15 zero), B = K rows as they lie in the cache (a key's
+//     dims are contiguous = the "col" operand layout); two 8-key tiles x eight 16-dim steps.  Lane (g, t) loads the
+//     64 bytes at offset 64 t of q_g and of key g: both operands see the same dim permutation, no shuffles.
+//   online softmax per beam on the C fragments (a lane owns one beam: rows are beams), P rounded to bf16 like the
+//     prefill kernel's; the S fragments of the two key tiles ARE the A fragment of P for the next product (FA-2 reuse);
+//   O[beam, dim] += P V : B = V^T needs two KEYS of one dim per register, the cache has two DIMS of one key:
+//     movmatrix.trans on the 8x8 blocks of the loaded V registers transposes them in place (32 per step).
+// Lane (g, t) ends up with O[beam g][dims 32 t .. 32 t + 31].  The four warps of a CTA take alternate 16-key groups
+// and are merged through shared memory; partials, the suffix CTA (per-beam keys: FMA path) and the last-arriver
+// merge are as above.
+__device__ __forceinline__ uint32_t movmatrix_trans(uint32_t a) {
+  uint32_t d;
+  asm volatile("movmatrix.sync.aligned.m8n8.trans.b16 %0, %1;" : "=r"(d) : "r"(a));
+  return d;
+}
+
+__global__ void __launch_bounds__(kAThreads, 2)
+beam_attention_mma_kernel(const __nv_bfloat16* __restrict__ q, int64_t ldq, const __nv_bfloat16* __restrict__ prefix_kv,
+                          const __nv_bfloat16* __restrict__ suffix_kv, int64_t suffix_stride, const int* __restrict__ pos,
+                          int H, int n_splits, int NB, float scale_log2e, float* __restrict__ part_o,
+                          float* __restrict__ part_ml, unsigned int* __restrict__ tickets, __nv_bfloat16* __restrict__ att,
+                          int64_t ld_att) {
+  __shared__ float s_o[4][kMaxBeams][128];     // prefix: [warp][beam][dim]; suffix: [0..1] reused as [16 slots][128]
+  __shared__ float s_m[4][kMaxBeams], s_l[4][kMaxBeams];
+  __shared__ unsigned int s_last;
+  const int h = blockIdx.x, split = blockIdx.y, NP = n_splits + 1;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int d = threadIdx.x;
+  if (split < n_splits) {
+    const int g = lane >> 2, t = lane & 3;
+    const int prefix_len = pos[0];
+    const int chunk = ((prefix_len + n_splits - 1) / n_splits + 15) / 16 * 16;
+    const int k0 = min(prefix_len, split * chunk), k1 = min(prefix_len, k0 + chunk);
+    auto row_ptr = [&](int key) {   // lane's 64 bytes of the k half of a cache row (v half: + 128 elements)
+      return prefix_kv + kv_off(h, min(key, k1 - 1), H) + t * 32;
+    };
+    U8 ka[2], kb[2], va[2], vb[2];   // keys base + g (a) and base + 8 + g (b): two 32-byte halves each
+    int base = k0 + warp * 16;
+    if (base < k1) {                 // the prompt cache is not written by this step: load before the dependency wait
+      const __nv_bfloat16* ra = row_ptr(base + g);
+      const __nv_bfloat16* rb = row_ptr(base + 8 + g);
+      ka[0] = ldg_stream256(ra); ka[1] = ldg_stream256(ra + 16);
+      kb[0] = ldg_stream256(rb); kb[1] = ldg_stream256(rb + 16);
+      va[0] = ldg_stream256(ra + 128); va[1] = ldg_stream256(ra + 144);
+      vb[0] = ldg_stream256(rb + 128); vb[1] = ldg_stream256(rb + 144);
+    }
+    asm volatile("griddepcontrol.wait;" ::: "memory");
+    asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+    U8 qa[2] = {};
+    if (g < NB) {
+      const __nv_bfloat16* qg = q + static_cast<size_t>(g) * ldq + h * 128 + t * 32;
+      qa[0] = ld256(qg);
+      qa[1] = ld256(qg + 16);
+    }
+    float o[16][4];
+#pragma unroll
+    for (int r = 0; r < 16; ++r) o[r][0] = o[r][1] = o[r][2] = o[r][3] = 0.f;
+    float m = -INFINITY, l = 0.f;
+    for (; base < k1; base += 64) {
+      // ---- S = Q K^T for key tiles [base, base + 8) and [base + 8, base + 16)
+      float sa[4] = {0.f, 0.f, 0.f, 0.f}, sb[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        const uint32_t q0 = qa[j >> 2].r[(2 * j) & 7], q1 = qa[j >> 2].r[(2 * j + 1) & 7];
+        mma_16816(sa, q0, 0u, q1, 0u, ka[j >> 2].r[(2 * j) & 7], ka[j >> 2].r[(2 * j + 1) & 7]);
+        mma_16816(sb, q0, 0u, q1, 0u, kb[j >> 2].r[(2 * j) & 7], kb[j >> 2].r[(2 * j + 1) & 7]);
+      }
+      // lane (g, t): beam g, keys base + 2t, + 2t + 1 (sa[0..1]) and base + 8 + 2t, + 1 (sb[0..1])
+      float s0 = sa[0] * scale_log2e, s1 = sa[1] * scale_log2e, s2 = sb[0] * scale_log2e, s3 = sb[1] * scale_log2e;
+      if (base + 16 > k1) {          // ragged last group
+        if (base + 2 * t >= k1) s0 = -INFINITY;
+        if (base + 2 * t + 1 >= k1) s1 = -INFINITY;
+        if (base + 8 + 2 * t >= k1) s2 = -INFINITY;
+        if (base + 9 + 2 * t >= k1) s3 = -INFINITY;
+      }
+      float mx = fmaxf(fmaxf(s0, s1), fmaxf(s2, s3));
+      mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, 1));
+      mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, 2));
+      const float m_new = fmaxf(m, mx);                       // finite: key `base` is always live
+      const float alpha = fast_exp2(m - m_new);
+      const float p0 = fast_exp2(s0 - m_new), p1 = fast_exp2(s1 - m_new);
+      const float p2 = fast_exp2(s2 - m_new), p3 = fast_exp2(s3 - m_new);
+      const uint32_t pa = pack_bf16(p0, p1), pb = pack_bf16(p2, p3);
+      // the sum runs over the ROUNDED probabilities, the ones the product below uses (as in the prefill kernel)
+      l = l * alpha + (bf16_lo(pa) + bf16_hi(pa)) + (bf16_lo(pb) + bf16_hi(pb));
+      m = m_new;
+      if (alpha != 1.f) {
+#pragma unroll
+        for (int r = 0; r < 16; ++r) {
+          o[r][0] *= alpha;
+          o[r][1] *= alpha;
+        }
+      }
+      // ---- O += P V: B fragments = transposed 8x8 blocks of the V registers
+#pragma unroll
+      for (int r = 0; r < 16; ++r) {
+        const uint32_t b0 = movmatrix_trans(va[r >> 3].r[r & 7]);
+        const uint32_t b1 = movmatrix_trans(vb[r >> 3].r[r & 7]);
+        mma_16816(o[r], pa, 0u, pb, 0u, b0, b1);
+      }
+      const int nxt = base + 64;
+      if (nxt < k1) {
+        const __nv_bfloat16* ra = row_ptr(nxt + g);
+        const __nv_bfloat16* rb = row_ptr(nxt + 8 + g);
+        ka[0] = ldg_stream256(ra); ka[1] = ldg_stream256(ra + 16);
+        kb[0] = ldg_stream256(rb); kb[1] = ldg_stream256(rb + 16);
+        va[0] = ldg_stream256(ra + 128); va[1] = ldg_stream256(ra + 144);
+        vb[0] = ldg_stream256(rb + 128); vb[1] = ldg_stream256(rb + 144);
+      }
+    }
+    // ---- warp state -> shared memory; l: sum over the four lanes of a beam (they hold different keys)
+    l += __shfl_xor_sync(0xffffffffu, l, 1);
+    l += __shfl_xor_sync(0xffffffffu, l, 2);
+#pragma unroll
+    for (int r = 0; r < 16; ++r) {
+      s_o[warp][g][32 * t + 2 * r] = o[r][0];
+      s_o[warp][g][32 * t + 2 * r + 1] = o[r][1];
+    }
+    if (t == 0) {
+      s_m[warp][g] = m;
+      s_l[warp][g] = l;
+    }
+    __syncthreads();
+    for (int b = 0; b < NB; ++b) {
+      float M = -INFINITY;
+#pragma unroll
+      for (int w = 0; w < 4; ++w) M = fmaxf(M, s_m[w][b]);
+      float acc = 0.f, L = 0.f;
+#pragma unroll
+      for (int w = 0; w < 4; ++w) {
+        const float wgt = (s_m[w][b] == -INFINITY) ? 0.f : fast_exp2(s_m[w][b] - M);
+        acc += s_o[w][b][d] * wgt;
+        L += s_l[w][b] * wgt;
+      }
+      const size_t idx = (static_cast<size_t>(h) * NP + split) * NB + b;
+      part_o[idx * 128 + d] = acc;
+      if (d == 0) {
+        part_ml[idx * 2] = M;
+        part_ml[idx * 2 + 1] = L;
+      }
+    }
+  } else {
+    // ---- suffix CTA: every beam has its own keys -> per-beam FMA pass (T = generated tokens, small)
+    asm volatile("griddepcontrol.wait;" ::: "memory");
+    asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+    float (*so)[128] = reinterpret_cast<float (*)[128]>(&s_o[0][0][0]);   // [16 slots][128]
+    float* sm = &s_m[0][0];                                                 // [16]
+    float* sl = &s_l[0][0];
+    const int slot = warp * 4 + (lane >> 3), sub = lane & 7;
+    const int T = pos[1] + 1;
+    for (int b = 0; b < NB; ++b) {
+      const __nv_bfloat16* kv = suffix_kv + static_cast<size_t>(b) * suffix_stride;
+      const U8 q8 = ld256(q + static_cast<size_t>(b) * ldq + h * 128 + sub * 16);
+      float mm = -INFINITY, ll = 0.f, oo[16];
+#pragma unroll
+      for (int e = 0; e < 16; ++e) oo[e] = 0.f;
+      for (int base = 0; base < T; base += 16) {
+        const bool live = base + slot < T;
+        const __nv_bfloat16* row = kv + kv_off(h, live ? base + slot : 0, H) + sub * 16;
+        const U8 k8 = ld256(row), v8 = ld256(row + 128);
+        float sc = 0.f;
+#pragma unroll
+        for (int e = 0; e < 8; ++e) {
+          sc = fmaf(bf16_lo(q8.r[e]), bf16_lo(k8.r[e]), sc);
+          sc = fmaf(bf16_hi(q8.r[e]), bf16_hi(k8.r[e]), sc);
+        }
+        sc += __shfl_xor_sync(0xffffffffu, sc, 1);
+        sc += __shfl_xor_sync(0xffffffffu, sc, 2);
+        sc += __shfl_xor_sync(0xffffffffu, sc, 4);
+        sc *= scale_log2e;
+        if (live) {
+          const float m_new = fmaxf(mm, sc);
+          const float alpha = fast_exp2(mm - m_new);
+          const float pr = fast_exp2(sc - m_new);
+          ll = ll * alpha + pr;
+#pragma unroll
+          for (int e = 0; e < 8; ++e) {
+            oo[2 * e] = fmaf(pr, bf16_lo(v8.r[e]), oo[2 * e] * alpha);
+            oo[2 * e + 1] = fmaf(pr, bf16_hi(v8.r[e]), oo[2 * e + 1] * alpha);
+          }
+          mm = m_new;
+        }
+      }
+      __syncthreads();
+#pragma unroll
+      for (int e = 0; e < 16; ++e) so[slot][sub * 16 + e] = oo[e];
+      if (sub == 0) {
+        sm[slot] = mm;
+        sl[slot] = ll;
+      }
+      __syncthreads();
+      float M = -INFINITY;
+#pragma unroll
+      for (int gi = 0; gi < 16; ++gi) M = fmaxf(M, sm[gi]);
+      float acc = 0.f, L = 0.f;
+#pragma unroll
+      for (int gi = 0; gi < 16; ++gi) {
+        const float wgt = (sm[gi] == -INFINITY) ? 0.f : fast_exp2(sm[gi] - M);
+        acc += so[gi][d] * wgt;
+        L += sl[gi] * wgt;
+      }
+      const size_t idx = (static_cast<size_t>(h) * NP + split) * NB + b;
+      part_o[idx * 128 + d] = acc;
+      if (d == 0) {
+        part_ml[idx * 2] = M;
+        part_ml[idx * 2 + 1] = L;
+      }
+    }
+  }
+  // ---- the last CTA of this head merges (decode.cu: flash_decode_partial_kernel)
+  __threadfence();
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    const unsigned int tk = atomicAdd(&tickets[h], 1u);
+    s_last = (tk == static_cast<unsigned int>(NP) - 1u) ? 1u : 0u;
+    if (s_last) tickets[h] = 0;
+  }
+  __syncthreads();
+  if (!s_last) return;
+  __threadfence();
+#pragma unroll 1
+  for (int b = 0; b < NB; ++b) {
+    float M = -INFINITY;
+    for (int sp = 0; sp < NP; ++sp) M = fmaxf(M, __ldcg(&part_ml[((static_cast<size_t>(h) * NP + sp) * NB + b) * 2]));
+    float acc = 0.f, L = 0.f;
+    for (int sp = 0; sp < NP; ++sp) {
+      const size_t idx = (static_cast<size_t>(h) * NP + sp) * NB + b;
+      const float pm = __ldcg(&part_ml[idx * 2]);
+      const float wgt = (pm == -INFINITY) ? 0.f : fast_exp2(pm - M);
+      acc += __ldcg(&part_o[idx * 128 + d]) * wgt;
+      L += __ldcg(&part_ml[idx * 2 + 1]) * wgt;
+    }
+    att[static_cast<size_t>(b) * ld_att + h * 128 + d] = __float2bfloat16_rn(acc / L);
+  }
+}
+
 cudaLaunchAttribute g_battr;
 cudaLaunchConfig_t bpdl(dim3 grid, dim3 block, size_t smem, cudaStream_t st) {
   cudaLaunchConfig_t cfg = {};
@@ -480,17 +838,24 @@ cudaLaunchConfig_t bpdl(dim3 grid, dim3 block, size_t smem, cudaStream_t st) {
   return cfg;
 }
 
-int g_beam_ku = -1;   // MERLIN_BEAM_KU: K blocks in flight per warp (2: four CTAs per SM, 4: two)
+int g_beam_ku = -1;
 
 template <int kMode>
 int launch_bgemv(cudaStream_t st, const BGemvParams& p, int pairs) {
   MB_CHECK_ARG(p.K % 32 == 0 && p.ldx % 8 == 0, "decode_step_batched: K=%d unsupported", p.K);
   if (g_beam_ku < 0) {
-    const char* e = getenv("MERLIN_BEAM_KU");
-    g_beam_ku = (e && atoi(e) == 4) ? 4 : 2;
+    const char* e = getenv("MERLIN_BEAM_KU");     // 0 (default): 256-bit loads, 64-element blocks; 2 / 4: 128-bit variant
+    g_beam_ku = e ? atoi(e) : 0;
+    if (g_beam_ku != 2 && g_beam_ku != 4) g_beam_ku = 0;
   }
   cudaLaunchConfig_t cfg = bpdl(dim3((pairs + 7) / 8), dim3(kBThreads), 0, st);
-  if (g_beam_ku == 4) {
+  if (g_beam_ku == 0 && p.K % 64 == 0 && p.ldx % 16 == 0) {
+    if ((pairs + 7) / 8 <= 2 * sm_count()) {     // a grid that does not fill the chip: more bytes in flight per warp
+      MB_CHECK_CUDA(cudaLaunchKernelEx(&cfg, gemv_beams256_kernel<kMode, 4>, p));
+    } else {
+      MB_CHECK_CUDA(cudaLaunchKernelEx(&cfg, gemv_beams256_kernel<kMode, 2>, p));
+    }
+  } else if (g_beam_ku == 4) {
     MB_CHECK_CUDA(cudaLaunchKernelEx(&cfg, gemv_beams_kernel<kMode, 4>, p));
   } else {
     MB_CHECK_CUDA(cudaLaunchKernelEx(&cfg, gemv_beams_kernel<kMode, 2>, p));
@@ -519,11 +884,21 @@ struct AttnArgs {
 
 template <int NB>
 int launch_attention(cudaStream_t st, const AttnArgs& a) {
-  constexpr int kDims = NB <= 5 ? 16 : 8;
+  static const bool use_fma = [] {
+    const char* e = getenv("MERLIN_BEAM_ATTN");     // "fma": the FMA kernel (kept for comparison); default: tensor cores
+    return e != nullptr && strcmp(e, "fma") == 0;
+  }();
   cudaLaunchConfig_t cfg = bpdl(dim3(a.H, a.n_splits + 1), dim3(kAThreads), 0, st);
-  MB_CHECK_CUDA(cudaLaunchKernelEx(&cfg, beam_attention_kernel<NB, kDims>, a.q, a.ldq, a.prefix_kv, a.suffix_kv,
-                                   a.suffix_stride, a.pos, a.H, a.n_splits, a.scale, a.part_o, a.part_ml, a.tickets, a.att,
-                                   a.ld_att));
+  if (use_fma) {
+    constexpr int kDims = NB <= 5 ? 16 : 8;
+    MB_CHECK_CUDA(cudaLaunchKernelEx(&cfg, beam_attention_kernel<NB, kDims>, a.q, a.ldq, a.prefix_kv, a.suffix_kv,
+                                     a.suffix_stride, a.pos, a.H, a.n_splits, a.scale, a.part_o, a.part_ml, a.tickets,
+                                     a.att, a.ld_att));
+  } else {
+    MB_CHECK_CUDA(cudaLaunchKernelEx(&cfg, beam_attention_mma_kernel, a.q, a.ldq, a.prefix_kv, a.suffix_kv,
+                                     a.suffix_stride, a.pos, a.H, a.n_splits, NB, a.scale, a.part_o, a.part_ml, a.tickets,
+                                     a.att, a.ld_att));
+  }
   return MERLIN_OK;
 }
 

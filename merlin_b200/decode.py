@@ -162,7 +162,17 @@ class DecodeRunner:
         return self.out_ids[base:base + done].clone()
 
 
-BEAM_SPLITS = int(os.environ.get("MERLIN_BEAM_SPLITS", "9"))   # prefix key splits: heads x splits ~ 2 CTAs per SM
+def beam_splits(heads: int) -> int:
+    """Prefix key splits of the beam attention kernel: heads x (splits + 1 suffix CTA) must fit ONE wave of two
+    CTAs per SM (the kernel holds k online-softmax states per thread: ~230 registers at 5 beams) — a 33rd CTA row
+    would wait for a second wave and double the kernel's time."""
+    env = os.environ.get("MERLIN_BEAM_SPLITS")
+    if env:
+        return int(env)
+    sms = _lib.load().merlin_sm_count()
+    return max(1, min(64, (2 * sms) // heads - 1))
+
+
 MAX_BEAMS = 8
 
 
@@ -195,7 +205,8 @@ class BeamDecodeRunner:
         self.pos = torch.zeros(2, dtype=torch.int32, device=dev)          # {prefix_len, t}
         self.bs = _lib.BeamState(num_beams, self.cap, cast(self._keep[6]), cast(self._keep[7]), self.pos.data_ptr())
         L_ = _lib.load()
-        self.ws = torch.zeros(L_.merlin_decode_batched_workspace_bytes(D, cfg.intermediate_size, H, BEAM_SPLITS,
+        self.splits = beam_splits(H)
+        self.ws = torch.zeros(L_.merlin_decode_batched_workspace_bytes(D, cfg.intermediate_size, H, self.splits,
                                                                        num_beams), dtype=torch.uint8, device=dev)
         self.tokens = torch.zeros(num_beams, dtype=torch.int64, device=dev)
         self.x = torch.empty((num_beams, D), dtype=torch.bfloat16, device=dev)
@@ -213,7 +224,7 @@ class BeamDecodeRunner:
         torch.index_select(self.lm.model.embed_tokens, 0, self.tokens, out=self.x)
         check(_lib.load().merlin_decode_step_batched(torch.cuda.current_stream().cuda_stream, ctypes.byref(self.w),
                                                      ctypes.byref(self.bs), self.x.data_ptr(), self.ws.data_ptr(),
-                                                     self.logits.data_ptr(), self.logits.stride(0), BEAM_SPLITS),
+                                                     self.logits.data_ptr(), self.logits.stride(0), self.splits),
               "merlin_decode_step_batched")
         self.pos.add_(self.one)
 
