@@ -32,6 +32,7 @@ constexpr int kBWarps = 8;               // warps of a GEMV CTA: they split K
 constexpr int kBThreads = kBWarps * 32;
 constexpr int kU = 4;                    // 32-element K blocks in flight per warp
 constexpr int kMaxBeams = 8;             // the N of m16n8k16
+constexpr int kMaxSplits = 16;          // prefix key splits of the tensor-core attention kernel (registers of its merge)
 constexpr int kAThreads = 128;           // attention CTAs: 4 warps x 4 key slots x 8 lanes (16 dims each)
 
 enum BMode : int { B_PLAIN = 0, B_QKV_ROPE = 1, B_SWIGLU = 2 };
@@ -613,7 +614,10 @@ beam_attention_mma_kernel(const __nv_bfloat16* __restrict__ q, int64_t ldq, cons
   __shared__ float s_o[4][kMaxBeams][128];     // prefix: [warp][beam][dim]; suffix: [0..1] reused as [16 slots][128]
   __shared__ float s_m[4][kMaxBeams], s_l[4][kMaxBeams];
   __shared__ unsigned int s_last;
-  const int h = blockIdx.x, split = blockIdx.y, NP = n_splits + 1;
+  // blockIdx.y < NB: the suffix CTA of beam blockIdx.y (short; scheduled first so that it never waits for a slot
+  // behind the prefix CTAs); blockIdx.y >= NB: prefix split blockIdx.y - NB
+  const int h = blockIdx.x, NP = n_splits + 1;
+  const int split = static_cast<int>(blockIdx.y) >= NB ? static_cast<int>(blockIdx.y) - NB : n_splits + static_cast<int>(blockIdx.y);
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int d = threadIdx.x;
   if (split < n_splits) {
@@ -738,7 +742,8 @@ beam_attention_mma_kernel(const __nv_bfloat16* __restrict__ q, int64_t ldq, cons
     float* sl = &s_l[0][0];
     const int slot = warp * 4 + (lane >> 3), sub = lane & 7;
     const int T = pos[1] + 1;
-    for (int b = 0; b < NB; ++b) {
+    {
+      const int b = split - n_splits;          // one suffix CTA per beam
       const __nv_bfloat16* kv = suffix_kv + static_cast<size_t>(b) * suffix_stride;
       const U8 q8 = ld256(q + static_cast<size_t>(b) * ldq + h * 128 + sub * 16);
       float mm = -INFINITY, ll = 0.f, oo[16];
@@ -789,7 +794,7 @@ beam_attention_mma_kernel(const __nv_bfloat16* __restrict__ q, int64_t ldq, cons
         acc += so[gi][d] * wgt;
         L += sl[gi] * wgt;
       }
-      const size_t idx = (static_cast<size_t>(h) * NP + split) * NB + b;
+      const size_t idx = (static_cast<size_t>(h) * NP + n_splits) * NB + b;
       part_o[idx * 128 + d] = acc;
       if (d == 0) {
         part_ml[idx * 2] = M;
@@ -797,30 +802,53 @@ beam_attention_mma_kernel(const __nv_bfloat16* __restrict__ q, int64_t ldq, cons
       }
     }
   }
-  // ---- the last CTA of this head merges (decode.cu: flash_decode_partial_kernel)
+  // ---- the last CTA of this head merges (decode.cu: flash_decode_partial_kernel): n_splits prefix CTAs + NB suffix CTAs
   __threadfence();
   __syncthreads();
   if (threadIdx.x == 0) {
     const unsigned int tk = atomicAdd(&tickets[h], 1u);
-    s_last = (tk == static_cast<unsigned int>(NP) - 1u) ? 1u : 0u;
+    s_last = (tk == static_cast<unsigned int>(n_splits + NB) - 1u) ? 1u : 0u;
     if (s_last) tickets[h] = 0;
   }
   __syncthreads();
   if (!s_last) return;
   __threadfence();
-#pragma unroll 1
-  for (int b = 0; b < NB; ++b) {
-    float M = -INFINITY;
-    for (int sp = 0; sp < NP; ++sp) M = fmaxf(M, __ldcg(&part_ml[((static_cast<size_t>(h) * NP + sp) * NB + b) * 2]));
-    float acc = 0.f, L = 0.f;
-    for (int sp = 0; sp < NP; ++sp) {
-      const size_t idx = (static_cast<size_t>(h) * NP + sp) * NB + b;
-      const float pm = __ldcg(&part_ml[idx * 2]);
-      const float wgt = (pm == -INFINITY) ? 0.f : fast_exp2(pm - M);
-      acc += __ldcg(&part_o[idx * 128 + d]) * wgt;
-      L += __ldcg(&part_ml[idx * 2 + 1]) * wgt;
+  // warp w merges beams w, w + 4; a lane owns four dims (one 16-byte load per partial), all loads of a beam in flight
+  for (int b = warp; b < NB; b += 4) {
+    float pm[kMaxSplits + 1], pl[kMaxSplits + 1];
+    float4 po[kMaxSplits + 1];
+#pragma unroll
+    for (int sp = 0; sp <= kMaxSplits; ++sp) {
+      if (sp < NP) {
+        const size_t idx = (static_cast<size_t>(h) * NP + sp) * NB + b;
+        const float2 ml = __ldcg(reinterpret_cast<const float2*>(part_ml + idx * 2));
+        pm[sp] = ml.x;
+        pl[sp] = ml.y;
+        po[sp] = __ldcg(reinterpret_cast<const float4*>(part_o + idx * 128) + lane);
+      }
     }
-    att[static_cast<size_t>(b) * ld_att + h * 128 + d] = __float2bfloat16_rn(acc / L);
+    float M = -INFINITY;
+#pragma unroll
+    for (int sp = 0; sp <= kMaxSplits; ++sp)
+      if (sp < NP) M = fmaxf(M, pm[sp]);
+    float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+    float L = 0.f;
+#pragma unroll
+    for (int sp = 0; sp <= kMaxSplits; ++sp) {
+      if (sp < NP) {
+        const float wgt = (pm[sp] == -INFINITY) ? 0.f : fast_exp2(pm[sp] - M);
+        acc.x += po[sp].x * wgt;
+        acc.y += po[sp].y * wgt;
+        acc.z += po[sp].z * wgt;
+        acc.w += po[sp].w * wgt;
+        L += pl[sp] * wgt;
+      }
+    }
+    const float inv = 1.f / L;
+    uint2 out;
+    out.x = pack_bf16(acc.x * inv, acc.y * inv);
+    out.y = pack_bf16(acc.z * inv, acc.w * inv);
+    *reinterpret_cast<uint2*>(att + static_cast<size_t>(b) * ld_att + h * 128 + lane * 4) = out;
   }
 }
 
@@ -888,13 +916,14 @@ int launch_attention(cudaStream_t st, const AttnArgs& a) {
     const char* e = getenv("MERLIN_BEAM_ATTN");     // "fma": the FMA kernel (kept for comparison); default: tensor cores
     return e != nullptr && strcmp(e, "fma") == 0;
   }();
-  cudaLaunchConfig_t cfg = bpdl(dim3(a.H, a.n_splits + 1), dim3(kAThreads), 0, st);
+  cudaLaunchConfig_t cfg = bpdl(dim3(a.H, use_fma ? a.n_splits + 1 : a.n_splits + NB), dim3(kAThreads), 0, st);
   if (use_fma) {
     constexpr int kDims = NB <= 5 ? 16 : 8;
     MB_CHECK_CUDA(cudaLaunchKernelEx(&cfg, beam_attention_kernel<NB, kDims>, a.q, a.ldq, a.prefix_kv, a.suffix_kv,
                                      a.suffix_stride, a.pos, a.H, a.n_splits, a.scale, a.part_o, a.part_ml, a.tickets,
                                      a.att, a.ld_att));
   } else {
+    MB_CHECK_ARG(a.n_splits <= kMaxSplits, "decode_step_batched: n_splits %d > %d", a.n_splits, kMaxSplits);
     MB_CHECK_CUDA(cudaLaunchKernelEx(&cfg, beam_attention_mma_kernel, a.q, a.ldq, a.prefix_kv, a.suffix_kv,
                                      a.suffix_stride, a.pos, a.H, a.n_splits, NB, a.scale, a.part_o, a.part_ml, a.tickets,
                                      a.att, a.ld_att));

@@ -163,14 +163,14 @@ class DecodeRunner:
 
 
 def beam_splits(heads: int) -> int:
-    """Prefix key splits of the beam attention kernel: heads x (splits + 1 suffix CTA) must fit ONE wave of two
-    CTAs per SM (the kernel holds k online-softmax states per thread: ~230 registers at 5 beams) — a 33rd CTA row
-    would wait for a second wave and double the kernel's time."""
+    """Prefix key splits of the beam attention kernel: heads x splits prefix CTAs must fit ONE wave of two CTAs per
+    SM (the kernel needs ~250 registers) — one more CTA row would wait for a second wave and double the kernel's
+    time.  The per-beam suffix CTAs are short and scheduled first."""
     env = os.environ.get("MERLIN_BEAM_SPLITS")
     if env:
         return int(env)
     sms = _lib.load().merlin_sm_count()
-    return max(1, min(64, (2 * sms) // heads - 1))
+    return max(1, min(16, (2 * sms) // heads - 1))
 
 
 MAX_BEAMS = 8
@@ -208,7 +208,10 @@ class BeamDecodeRunner:
         self.splits = beam_splits(H)
         self.ws = torch.zeros(L_.merlin_decode_batched_workspace_bytes(D, cfg.intermediate_size, H, self.splits,
                                                                        num_beams), dtype=torch.uint8, device=dev)
-        self.tokens = torch.zeros(num_beams, dtype=torch.int64, device=dev)
+        self.ctl = torch.zeros((2, num_beams), dtype=torch.int64, device=dev)     # [tokens | parents] of this step
+        self.ctl_host = torch.zeros((2, num_beams), dtype=torch.int64).pin_memory()
+        self.tokens = self.ctl[0]
+        self._ctl_ev = torch.cuda.Event()
         self.x = torch.empty((num_beams, D), dtype=torch.bfloat16, device=dev)
         vpad = (cfg.vocab_size + 7) // 8 * 8
         self.logits = torch.empty((num_beams, vpad), dtype=torch.bfloat16, device=dev)[:, :cfg.vocab_size]
@@ -250,11 +253,18 @@ class BeamDecodeRunner:
         Returns the [k, V] bf16 logits of the next position (a view of a static buffer)."""
         if self.t >= self.cap:
             raise RuntimeError("beam suffix cache is full")
-        if parents is not None and self.t > 0 and list(parents) != list(range(self.nb)):
+        ident = list(range(self.nb))
+        parents = ident if parents is None else list(parents)
+        # one pinned staging buffer, one async copy (the event guards the buffer against a caller that does not read
+        # a step's logits back before the next step)
+        self._ctl_ev.synchronize()
+        self.ctl_host[0] = torch.as_tensor(list(tokens), dtype=torch.int64)
+        self.ctl_host[1] = torch.as_tensor(parents, dtype=torch.int64)
+        self.ctl.copy_(self.ctl_host, non_blocking=True)
+        self._ctl_ev.record()
+        if self.t > 0 and parents != ident:
             nblk = (self.t + 31) // 32      # only the blocks that hold generated tokens move
-            idx = torch.as_tensor(list(parents), dtype=torch.int64, device=self.suffix.device)
-            self.suffix[:, :, :nblk].copy_(self.suffix[:, :, :nblk].index_select(1, idx))
-        self.tokens.copy_(torch.as_tensor(tokens, dtype=torch.int64), non_blocking=False)
+            self.suffix[:, :, :nblk].copy_(self.suffix[:, :, :nblk].index_select(1, self.ctl[1]))
         if use_graph and self.graph is not None:
             self.graph.replay()
         else:
