@@ -9,11 +9,11 @@
 //    split K, so each weight byte is read from HBM once per step whatever the beam count — the step stays bound by
 //    the weight bytes of a single sequence.  (tcgen05 has no use here: M = 128 rows x N = 8 would leave the
 //    operand staging, not the math, as the cost; the kernel is a pure HBM stream.)
-//  * the KV cache is split into the SHARED prefix (the prompt: the prefill's cache, read once for all beams — the
-//    k queries of a head are scored against each key while it is in registers) and a per-beam SUFFIX (the tokens
-//    generated so far), so a beam re-ordering moves only the small suffix blocks;
-//  * attention is one kernel: prefix partials (heads x key splits CTAs, k online-softmax states per thread), one CTA
-//    per head for the beams' suffixes, and the last CTA of a head merges all partials in index order.
+//  * the KV cache is split into the SHARED prefix (the prompt: the prefill's cache, read once for all beams) and a
+//    per-beam SUFFIX (the tokens generated so far), so a beam re-ordering moves only the small suffix blocks;
+//  * attention is one kernel: the prefix as two tensor-core products per 16 keys for all beams at once (Q K^T with the
+//    beams as MMA rows, P V with V transposed in registers), one short CTA per (head, beam) for the suffix, and the
+//    last CTA of a head merges all partials in index order.
 // Same arithmetic as decode.cu (fp32 accumulation, RMSNorm rounded to bf16 as the prefill does, RoPE in fp32 before the
 // bf16 rounding), so a beam's logits equal the single-sequence path's up to summation order.
 #include "host.cuh"
@@ -30,7 +30,6 @@ namespace {
 
 constexpr int kBWarps = 8;               // warps of a GEMV CTA: they split K
 constexpr int kBThreads = kBWarps * 32;
-constexpr int kU = 4;                    // 32-element K blocks in flight per warp
 constexpr int kMaxBeams = 8;             // the N of m16n8k16
 constexpr int kMaxSplits = 16;          // prefix key splits of the tensor-core attention kernel (registers of its merge)
 constexpr int kAThreads = 128;           // attention CTAs: 4 warps x 4 key slots x 8 lanes (16 dims each)
@@ -52,13 +51,6 @@ struct BGemvParams {
   int nb, N, K, D;
 };
 
-__device__ __forceinline__ uint4 ldg_stream(const uint4* p) {
-  uint4 r;
-  asm volatile("ld.global.nc.L1::no_allocate.v4.u32 {%0, %1, %2, %3}, [%4];"
-               : "=r"(r.x), "=r"(r.y), "=r"(r.z), "=r"(r.w)
-               : "l"(p));
-  return r;
-}
 // 32 bytes per lane in one instruction (LDG.E.256): a warp-level load covers whole 128-byte lines
 struct U8 {
   uint32_t r[8];
@@ -210,105 +202,10 @@ __device__ __forceinline__ void beams_epilogue(const BGemvParams& p, const float
 
 // out[b, r] = dot(W[r], x_b) for all beams at once.  A CTA owns 8 row PAIRS (row_a -> MMA rows 0-7, row_b -> MMA rows
 // 8-15; a pair is what one epilogue needs: the two halves of a RoPE rotation, gate and up of one SwiGLU output, or two
-// adjacent rows).  Lane (g, t) = (lane / 4, lane % 4) loads 16 bytes of row_a(g) and row_b(g) at K offset 32 blk + 8 t
-// and the same 16 bytes of beam g's activation (through L1: every CTA of an SM reads the same few KB): both operands
-// see the same K permutation inside the 32-block, so two MMAs per block consume them without any shuffle.
-template <int kMode, int kU>
-__global__ void __launch_bounds__(kBThreads, kU <= 2 ? 4 : 2)
-gemv_beams_kernel(const BGemvParams p) {
-  __shared__ float red[kBWarps][32][4];
-  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  const int g = lane >> 2, t = lane & 3;
-  const int pair = blockIdx.x * 8 + g;
-  int row_a, row_b;
-  if (kMode == B_QKV_ROPE) {
-    if (pair < p.D) {                       // q and k blocks: RoPE pair (j, j + 64) of one head
-      row_a = (pair >> 6) * 128 + (pair & 63);
-      row_b = row_a + 64;
-    } else {
-      row_a = 2 * p.D + 2 * (pair - p.D);
-      row_b = row_a + 1;
-    }
-  } else if (kMode == B_SWIGLU) {
-    row_a = (pair >> 7) * 256 + (pair & 127);
-    row_b = row_a + 128;
-  } else {
-    row_a = 2 * pair;
-    row_b = row_a + 1;
-  }
-  const bool active = row_a < p.N;
-  const bool has_b = row_b < p.N;
-  const int nblk = p.K >> 5;
-  const uint4* wa = reinterpret_cast<const uint4*>(p.W + static_cast<size_t>(active ? row_a : 0) * p.K) + t;
-  const uint4* wb = reinterpret_cast<const uint4*>(p.W + static_cast<size_t>(has_b ? row_b : (active ? row_a : 0)) * p.K) + t;
-
-  // ---- first weight batch BEFORE waiting on the producer kernel (programmatic dependent launch: overlaps its tail)
-  uint4 a[kU], b[kU];
-#pragma unroll
-  for (int u = 0; u < kU; ++u) {
-    const int blk = warp + kBWarps * u;
-    a[u] = b[u] = make_uint4(0, 0, 0, 0);
-    if (blk < nblk) {
-      a[u] = ldg_stream(wa + blk * 4);
-      b[u] = ldg_stream(wb + blk * 4);
-    }
-  }
-  asm volatile("griddepcontrol.wait;" ::: "memory");
-  asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
-
-  const bool beam_live = g < p.nb;
-  const uint4* xrow = reinterpret_cast<const uint4*>(p.x + static_cast<size_t>(beam_live ? g : 0) * p.ldx) + t;
-
-  float c[4] = {0.f, 0.f, 0.f, 0.f};
-  for (int blk0 = warp; blk0 < nblk; blk0 += kBWarps * kU) {
-    uint4 na[kU], nb_[kU], xv[kU];
-#pragma unroll
-    for (int u = 0; u < kU; ++u) {
-      const int blk = blk0 + kBWarps * (kU + u);
-      na[u] = nb_[u] = make_uint4(0, 0, 0, 0);
-      if (blk < nblk) {
-        na[u] = ldg_stream(wa + blk * 4);
-        nb_[u] = ldg_stream(wb + blk * 4);
-      }
-    }
-#pragma unroll
-    for (int u = 0; u < kU; ++u) {
-      const int blk = blk0 + kBWarps * u;
-      xv[u] = (beam_live && blk < nblk) ? xrow[blk * 4] : make_uint4(0, 0, 0, 0);
-    }
-#pragma unroll
-    for (int u = 0; u < kU; ++u) {
-      if (blk0 + kBWarps * u < nblk) {      // warp-uniform
-        mma_16816(c, a[u].x, b[u].x, a[u].y, b[u].y, xv[u].x, xv[u].y);
-        mma_16816(c, a[u].z, b[u].z, a[u].w, b[u].w, xv[u].z, xv[u].w);
-      }
-    }
-#pragma unroll
-    for (int u = 0; u < kU; ++u) {
-      a[u] = na[u];
-      b[u] = nb_[u];
-    }
-  }
-  // ---- combine the K partitions (fixed order: deterministic)
-  red[warp][lane][0] = c[0];
-  red[warp][lane][1] = c[1];
-  red[warp][lane][2] = c[2];
-  red[warp][lane][3] = c[3];
-  __syncthreads();
-  if (warp != 0 || !active) return;
-#pragma unroll
-  for (int w = 1; w < kBWarps; ++w) {
-    c[0] += red[w][lane][0];
-    c[1] += red[w][lane][1];
-    c[2] += red[w][lane][2];
-    c[3] += red[w][lane][3];
-  }
-  beams_epilogue<kMode>(p, c, row_a, row_b, has_b, t);
-}
-
-// The same product with 256-bit loads: a K block is 64 elements, lane (g, t) loads the 32 bytes at offset 32 t of
-// row_a(g), row_b(g) and of beam g's activation, so one warp-level load covers eight whole 128-byte lines; four MMAs
-// per block.  kDepth blocks per warp are in flight in a register ring (a slot is reloaded as soon as it is consumed):
+// adjacent rows) and its 8 warps split K in blocks of 64 elements.  Lane (g, t) = (lane / 4, lane % 4) loads the 32
+// bytes at offset 32 t of row_a(g), row_b(g) (one 256-bit streaming load each: a warp-level load covers eight whole
+// 128-byte lines) and of beam g's activation (through L1: every CTA of an SM reads the same few KB): both operands see
+// the same K permutation inside the block, so four MMAs per block consume them without any shuffle.  kDepth blocks per warp are in flight in a register ring (a slot is reloaded as soon as it is consumed):
 // 2 for the wide projections (four CTAs per SM), 4 for o_proj / down_proj whose 256 CTAs do not fill the chip otherwise.
 template <int kMode, int kDepth>
 __global__ void __launch_bounds__(kBThreads, kDepth <= 2 ? 4 : 2)
@@ -373,222 +270,11 @@ gemv_beams256_kernel(const BGemvParams p) {
   beams_epilogue<kMode>(p, c, row_a, row_b, has_b, t);
 }
 
-// ---- attention of all beams for one head.  Grid (H, n_splits + 1): CTAs y < n_splits walk a key range of the SHARED
-// prefix once, scoring each key against the NB queries while it sits in registers (NB online-softmax states per
-// thread); CTA y == n_splits attends each beam over its own suffix rows 0 .. t (the new token included).  A lane owns
-// kDims of the 128 head dims (16, or 8 beyond 5 beams so the NB accumulators still fit the register file).  Partials
-// go to part_o[((h * NP + y) * NB + b) * 128 + d], part_ml[(...) * 2 + {m, l}]; the LAST CTA of a head to finish (per-
-// head arrival ticket, self-resetting) merges them in index order — deterministic — into att[b, h * 128 + d].
-template <int NB, int kDims>
-__global__ void __launch_bounds__(kAThreads)
-beam_attention_kernel(const __nv_bfloat16* __restrict__ q, int64_t ldq, const __nv_bfloat16* __restrict__ prefix_kv,
-                      const __nv_bfloat16* __restrict__ suffix_kv, int64_t suffix_stride, const int* __restrict__ pos,
-                      int H, int n_splits, float scale_log2e, float* __restrict__ part_o, float* __restrict__ part_ml,
-                      unsigned int* __restrict__ tickets, __nv_bfloat16* __restrict__ att, int64_t ld_att) {
-  constexpr int kLpk = 128 / kDims;            // lanes per key
-  constexpr int kSlots = 4 * (32 / kLpk);      // keys per CTA iteration
-  constexpr int kVecs = kDims / 8;             // 16-byte vectors of k (and of v) per lane
-  __shared__ float s_o[kSlots][128];
-  __shared__ float s_m[kSlots], s_l[kSlots];
-  __shared__ unsigned int s_last;
-  const int h = blockIdx.x, split = blockIdx.y, NP = n_splits + 1;
-  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  const int slot = warp * (32 / kLpk) + lane / kLpk, sub = lane % kLpk;
-  const int d = threadIdx.x;
-  auto load_row = [&](const __nv_bfloat16* kv, int key, uint4 (&r)[2 * kVecs], bool stream) {
-    const __nv_bfloat16* row = kv + kv_off(h, key, H) + sub * kDims;
-    if (kVecs == 2 && stream) {   // 32 bytes of k and of v per lane: one 256-bit load each (whole sectors per request)
-      const U8 k8 = ldg_stream256(row), v8 = ldg_stream256(row + 128);
-      r[0] = make_uint4(k8.r[0], k8.r[1], k8.r[2], k8.r[3]);
-      r[kVecs - 1] = make_uint4(k8.r[4], k8.r[5], k8.r[6], k8.r[7]);
-      r[kVecs] = make_uint4(v8.r[0], v8.r[1], v8.r[2], v8.r[3]);
-      r[2 * kVecs - 1] = make_uint4(v8.r[4], v8.r[5], v8.r[6], v8.r[7]);
-      return;
-    }
-#pragma unroll
-    for (int i = 0; i < kVecs; ++i) {
-      if (stream) {
-        r[i] = ldg_stream(reinterpret_cast<const uint4*>(row) + i);
-        r[kVecs + i] = ldg_stream(reinterpret_cast<const uint4*>(row + 128) + i);
-      } else {
-        r[i] = *(reinterpret_cast<const uint4*>(row) + i);
-        r[kVecs + i] = *(reinterpret_cast<const uint4*>(row + 128) + i);
-      }
-    }
-  };
-  auto unpack = [&](const uint4 (&r)[2 * kVecs], float (&kf)[kDims], float (&vf)[kDims]) {
-#pragma unroll
-    for (int i = 0; i < kVecs; ++i) {
-      const uint32_t kw[4] = {r[i].x, r[i].y, r[i].z, r[i].w};
-      const uint32_t vw[4] = {r[kVecs + i].x, r[kVecs + i].y, r[kVecs + i].z, r[kVecs + i].w};
-#pragma unroll
-      for (int e = 0; e < 4; ++e) {
-        kf[8 * i + 2 * e] = bf16_lo(kw[e]);
-        kf[8 * i + 2 * e + 1] = bf16_hi(kw[e]);
-        vf[8 * i + 2 * e] = bf16_lo(vw[e]);
-        vf[8 * i + 2 * e + 1] = bf16_hi(vw[e]);
-      }
-    }
-  };
-  auto key_reduce = [&](float s) {
-#pragma unroll
-    for (int o = 1; o < kLpk; o <<= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
-    return s * scale_log2e;
-  };
-  // merge the key slots of the block for beam b and store partial (h, split, b)
-  auto store_partial = [&](int b, const float (&o)[kDims], float m, float l) {
-    __syncthreads();
-#pragma unroll
-    for (int e = 0; e < kDims; ++e) s_o[slot][sub * kDims + e] = o[e];
-    if (sub == 0) {
-      s_m[slot] = m;
-      s_l[slot] = l;
-    }
-    __syncthreads();
-    float M = -INFINITY;
-#pragma unroll
-    for (int gi = 0; gi < kSlots; ++gi) M = fmaxf(M, s_m[gi]);
-    float acc = 0.f, L = 0.f;
-#pragma unroll
-    for (int gi = 0; gi < kSlots; ++gi) {
-      const float w = (s_m[gi] == -INFINITY) ? 0.f : fast_exp2(s_m[gi] - M);
-      acc += s_o[gi][d] * w;
-      L += s_l[gi] * w;
-    }
-    const size_t idx = (static_cast<size_t>(h) * NP + split) * NB + b;
-    part_o[idx * 128 + d] = acc;
-    if (d == 0) {
-      part_ml[idx * 2] = M;
-      part_ml[idx * 2 + 1] = L;
-    }
-  };
-
-  if (split < n_splits) {
-    const int prefix_len = pos[0];                                   // written before the step / graph is launched
-    const int chunk = ((prefix_len + n_splits - 1) / n_splits + kSlots - 1) / kSlots * kSlots;
-    const int k0 = min(prefix_len, split * chunk), k1 = min(prefix_len, k0 + chunk);
-    uint4 cur[2 * kVecs], nxt[2 * kVecs];
-#pragma unroll
-    for (int i = 0; i < 2 * kVecs; ++i) cur[i] = nxt[i] = make_uint4(0, 0, 0, 0);
-    if (k0 < k1) load_row(prefix_kv, min(k0 + slot, k1 - 1), cur, true);   // the prompt cache is not written by this step
-    asm volatile("griddepcontrol.wait;" ::: "memory");
-    asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
-    uint32_t qp[NB][kDims / 2];
-    float m[NB], l[NB], o[NB][kDims];
-#pragma unroll
-    for (int b = 0; b < NB; ++b) {
-      const uint4* qg = reinterpret_cast<const uint4*>(q + static_cast<size_t>(b) * ldq + h * 128 + sub * kDims);
-#pragma unroll
-      for (int i = 0; i < kVecs; ++i) {
-        const uint4 x = qg[i];
-        qp[b][4 * i] = x.x; qp[b][4 * i + 1] = x.y; qp[b][4 * i + 2] = x.z; qp[b][4 * i + 3] = x.w;
-      }
-      m[b] = -INFINITY;
-      l[b] = 0.f;
-#pragma unroll
-      for (int e = 0; e < kDims; ++e) o[b][e] = 0.f;
-    }
-    for (int base = k0; base < k1; base += kSlots) {
-      const bool live = base + slot < k1;
-      if (base + kSlots < k1) load_row(prefix_kv, min(base + kSlots + slot, k1 - 1), nxt, true);
-      float kf[kDims], vf[kDims];
-      unpack(cur, kf, vf);
-#pragma unroll
-      for (int b = 0; b < NB; ++b) {
-        float s = 0.f;
-#pragma unroll
-        for (int e = 0; e < kDims / 2; ++e) {
-          s = fmaf(bf16_lo(qp[b][e]), kf[2 * e], s);
-          s = fmaf(bf16_hi(qp[b][e]), kf[2 * e + 1], s);
-        }
-        s = key_reduce(s);
-        if (live) {
-          const float m_new = fmaxf(m[b], s);
-          const float alpha = fast_exp2(m[b] - m_new);
-          const float pr = fast_exp2(s - m_new);
-          l[b] = l[b] * alpha + pr;
-#pragma unroll
-          for (int e = 0; e < kDims; ++e) o[b][e] = fmaf(pr, vf[e], o[b][e] * alpha);
-          m[b] = m_new;
-        }
-      }
-#pragma unroll
-      for (int i = 0; i < 2 * kVecs; ++i) cur[i] = nxt[i];
-    }
-#pragma unroll
-    for (int b = 0; b < NB; ++b) store_partial(b, o[b], m[b], l[b]);
-  } else {
-    asm volatile("griddepcontrol.wait;" ::: "memory");
-    asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
-    const int T = pos[1] + 1;
-    for (int b = 0; b < NB; ++b) {
-      const __nv_bfloat16* kv = suffix_kv + static_cast<size_t>(b) * suffix_stride;
-      uint32_t qp[kDims / 2];
-      const uint4* qg = reinterpret_cast<const uint4*>(q + static_cast<size_t>(b) * ldq + h * 128 + sub * kDims);
-#pragma unroll
-      for (int i = 0; i < kVecs; ++i) {
-        const uint4 x = qg[i];
-        qp[4 * i] = x.x; qp[4 * i + 1] = x.y; qp[4 * i + 2] = x.z; qp[4 * i + 3] = x.w;
-      }
-      float m = -INFINITY, l = 0.f, o[kDims];
-#pragma unroll
-      for (int e = 0; e < kDims; ++e) o[e] = 0.f;
-      for (int base = 0; base < T; base += kSlots) {
-        const bool live = base + slot < T;
-        uint4 r[2 * kVecs];
-        load_row(kv, live ? base + slot : 0, r, false);
-        float kf[kDims], vf[kDims];
-        unpack(r, kf, vf);
-        float s = 0.f;
-#pragma unroll
-        for (int e = 0; e < kDims / 2; ++e) {
-          s = fmaf(bf16_lo(qp[e]), kf[2 * e], s);
-          s = fmaf(bf16_hi(qp[e]), kf[2 * e + 1], s);
-        }
-        s = key_reduce(s);
-        if (live) {
-          const float m_new = fmaxf(m, s);
-          const float alpha = fast_exp2(m - m_new);
-          const float pr = fast_exp2(s - m_new);
-          l = l * alpha + pr;
-#pragma unroll
-          for (int e = 0; e < kDims; ++e) o[e] = fmaf(pr, vf[e], o[e] * alpha);
-          m = m_new;
-        }
-      }
-      store_partial(b, o, m, l);
-    }
-  }
-  // ---- the last CTA of this head merges (decode.cu: flash_decode_partial_kernel)
-  __threadfence();
-  __syncthreads();
-  if (threadIdx.x == 0) {
-    const unsigned int tk = atomicAdd(&tickets[h], 1u);
-    s_last = (tk == static_cast<unsigned int>(NP) - 1u) ? 1u : 0u;
-    if (s_last) tickets[h] = 0;
-  }
-  __syncthreads();
-  if (!s_last) return;
-  __threadfence();
-#pragma unroll 1
-  for (int b = 0; b < NB; ++b) {
-    float M = -INFINITY;
-    for (int sp = 0; sp < NP; ++sp) M = fmaxf(M, __ldcg(&part_ml[((static_cast<size_t>(h) * NP + sp) * NB + b) * 2]));
-    float acc = 0.f, L = 0.f;
-    for (int sp = 0; sp < NP; ++sp) {
-      const size_t idx = (static_cast<size_t>(h) * NP + sp) * NB + b;
-      const float pm = __ldcg(&part_ml[idx * 2]);
-      const float w = (pm == -INFINITY) ? 0.f : fast_exp2(pm - M);
-      acc += __ldcg(&part_o[idx * 128 + d]) * w;
-      L += __ldcg(&part_ml[idx * 2 + 1]) * w;
-    }
-    att[static_cast<size_t>(b) * ld_att + h * 128 + d] = __float2bfloat16_rn(acc / L);
-  }
-}
-
-// ---- the same attention with the prefix part on the tensor cores (default).  The FMA kernel above spends ~80
-// instructions per (key, beam) and is instruction-bound from 3 beams on (42 us per layer at 5 beams against 10 us of
-// HBM time); here a warp handles 16 keys per step for ALL beams with 32 MMAs:
+// ---- attention of all beams for one head.  Grid (H, NB + n_splits): CTA y < NB attends beam y over its own suffix
+// rows 0 .. t (the new token included; per-beam keys: a plain FMA pass over a few keys), CTA y >= NB walks key range
+// y - NB of the SHARED prefix once for ALL beams on the tensor cores — a warp takes 16 keys per step with 32 MMAs (an
+// FMA version of this loop spent ~80 instructions per (key, beam) and was instruction-bound from 3 beams on: 42 us per
+// layer at 5 beams against 10 us of HBM time):
 //   S[beam, key] = Q K^T : A = Q (rows 0-7 = beams, rows 8-15 zero), B = K rows as they lie in the cache (a key's
 //     dims are contiguous = the "col" operand layout); two 8-key tiles x eight 16-dim steps.  Lane (g, t) loads the
 //     64 bytes at offset 64 t of q_g and of key g: both operands see the same dim permutation, no shuffles.
@@ -597,8 +283,9 @@ beam_attention_kernel(const __nv_bfloat16* __restrict__ q, int64_t ldq, const __
 //   O[beam, dim] += P V : B = V^T needs two KEYS of one dim per register, the cache has two DIMS of one key:
 //     movmatrix.trans on the 8x8 blocks of the loaded V registers transposes them in place (32 per step).
 // Lane (g, t) ends up with O[beam g][dims 32 t .. 32 t + 31].  The four warps of a CTA take alternate 16-key groups
-// and are merged through shared memory; partials, the suffix CTA (per-beam keys: FMA path) and the last-arriver
-// merge are as above.
+// and are merged through shared memory.  Partials: part_o[((h * NP + split) * NB + b) * 128 + d], part_ml[(...) * 2 +
+// {m, l}], NP = n_splits + 1 (the suffix is partial n_splits); the LAST CTA of a head to finish (per-head arrival
+// ticket, self-resetting) merges them in index order — deterministic — into att[b, h * 128 + d].
 __device__ __forceinline__ uint32_t movmatrix_trans(uint32_t a) {
   uint32_t d;
   asm volatile("movmatrix.sync.aligned.m8n8.trans.b16 %0, %1;" : "=r"(d) : "r"(a));
@@ -606,7 +293,7 @@ __device__ __forceinline__ uint32_t movmatrix_trans(uint32_t a) {
 }
 
 __global__ void __launch_bounds__(kAThreads, 2)
-beam_attention_mma_kernel(const __nv_bfloat16* __restrict__ q, int64_t ldq, const __nv_bfloat16* __restrict__ prefix_kv,
+beam_attention_kernel(const __nv_bfloat16* __restrict__ q, int64_t ldq, const __nv_bfloat16* __restrict__ prefix_kv,
                           const __nv_bfloat16* __restrict__ suffix_kv, int64_t suffix_stride, const int* __restrict__ pos,
                           int H, int n_splits, int NB, float scale_log2e, float* __restrict__ part_o,
                           float* __restrict__ part_ml, unsigned int* __restrict__ tickets, __nv_bfloat16* __restrict__ att,
@@ -866,27 +553,14 @@ cudaLaunchConfig_t bpdl(dim3 grid, dim3 block, size_t smem, cudaStream_t st) {
   return cfg;
 }
 
-int g_beam_ku = -1;
-
 template <int kMode>
 int launch_bgemv(cudaStream_t st, const BGemvParams& p, int pairs) {
-  MB_CHECK_ARG(p.K % 32 == 0 && p.ldx % 8 == 0, "decode_step_batched: K=%d unsupported", p.K);
-  if (g_beam_ku < 0) {
-    const char* e = getenv("MERLIN_BEAM_KU");     // 0 (default): 256-bit loads, 64-element blocks; 2 / 4: 128-bit variant
-    g_beam_ku = e ? atoi(e) : 0;
-    if (g_beam_ku != 2 && g_beam_ku != 4) g_beam_ku = 0;
-  }
+  MB_CHECK_ARG(p.K % 64 == 0 && p.ldx % 16 == 0, "decode_step_batched: K=%d unsupported", p.K);
   cudaLaunchConfig_t cfg = bpdl(dim3((pairs + 7) / 8), dim3(kBThreads), 0, st);
-  if (g_beam_ku == 0 && p.K % 64 == 0 && p.ldx % 16 == 0) {
-    if ((pairs + 7) / 8 <= 2 * sm_count()) {     // a grid that does not fill the chip: more bytes in flight per warp
-      MB_CHECK_CUDA(cudaLaunchKernelEx(&cfg, gemv_beams256_kernel<kMode, 4>, p));
-    } else {
-      MB_CHECK_CUDA(cudaLaunchKernelEx(&cfg, gemv_beams256_kernel<kMode, 2>, p));
-    }
-  } else if (g_beam_ku == 4) {
-    MB_CHECK_CUDA(cudaLaunchKernelEx(&cfg, gemv_beams_kernel<kMode, 4>, p));
+  if ((pairs + 7) / 8 <= 2 * sm_count()) {     // a grid that does not fill the chip: more bytes in flight per warp
+    MB_CHECK_CUDA(cudaLaunchKernelEx(&cfg, gemv_beams256_kernel<kMode, 4>, p));
   } else {
-    MB_CHECK_CUDA(cudaLaunchKernelEx(&cfg, gemv_beams_kernel<kMode, 2>, p));
+    MB_CHECK_CUDA(cudaLaunchKernelEx(&cfg, gemv_beams256_kernel<kMode, 2>, p));
   }
   return MERLIN_OK;
 }
@@ -910,24 +584,11 @@ struct AttnArgs {
   __nv_bfloat16* att;
 };
 
-template <int NB>
-int launch_attention(cudaStream_t st, const AttnArgs& a) {
-  static const bool use_fma = [] {
-    const char* e = getenv("MERLIN_BEAM_ATTN");     // "fma": the FMA kernel (kept for comparison); default: tensor cores
-    return e != nullptr && strcmp(e, "fma") == 0;
-  }();
-  cudaLaunchConfig_t cfg = bpdl(dim3(a.H, use_fma ? a.n_splits + 1 : a.n_splits + NB), dim3(kAThreads), 0, st);
-  if (use_fma) {
-    constexpr int kDims = NB <= 5 ? 16 : 8;
-    MB_CHECK_CUDA(cudaLaunchKernelEx(&cfg, beam_attention_kernel<NB, kDims>, a.q, a.ldq, a.prefix_kv, a.suffix_kv,
-                                     a.suffix_stride, a.pos, a.H, a.n_splits, a.scale, a.part_o, a.part_ml, a.tickets,
-                                     a.att, a.ld_att));
-  } else {
-    MB_CHECK_ARG(a.n_splits <= kMaxSplits, "decode_step_batched: n_splits %d > %d", a.n_splits, kMaxSplits);
-    MB_CHECK_CUDA(cudaLaunchKernelEx(&cfg, beam_attention_mma_kernel, a.q, a.ldq, a.prefix_kv, a.suffix_kv,
-                                     a.suffix_stride, a.pos, a.H, a.n_splits, NB, a.scale, a.part_o, a.part_ml, a.tickets,
-                                     a.att, a.ld_att));
-  }
+int launch_attention(cudaStream_t st, const AttnArgs& a, int NB) {
+  MB_CHECK_ARG(a.n_splits <= kMaxSplits, "decode_step_batched: n_splits %d > %d", a.n_splits, kMaxSplits);
+  cudaLaunchConfig_t cfg = bpdl(dim3(a.H, NB + a.n_splits), dim3(kAThreads), 0, st);
+  MB_CHECK_CUDA(cudaLaunchKernelEx(&cfg, beam_attention_kernel, a.q, a.ldq, a.prefix_kv, a.suffix_kv, a.suffix_stride,
+                                   a.pos, a.H, a.n_splits, NB, a.scale, a.part_o, a.part_ml, a.tickets, a.att, a.ld_att));
   return MERLIN_OK;
 }
 
@@ -952,7 +613,7 @@ int merlin_decode_step_batched(void* stream, const merlin_decoder_weights* w, co
                "decode_step_batched: head_dim must be 128");
   MB_CHECK_ARG(bs->num_beams >= 1 && bs->num_beams <= kMaxBeams, "decode_step_batched: %d beams (1..%d)", bs->num_beams,
                kMaxBeams);
-  MB_CHECK_ARG(n_splits >= 1 && n_splits <= 64, "decode_step_batched: n_splits %d", n_splits);
+  MB_CHECK_ARG(n_splits >= 1 && n_splits <= kMaxSplits, "decode_step_batched: n_splits %d (1..%d)", n_splits, kMaxSplits);
   MB_CHECK_ARG(bs->suffix_capacity >= 32 && bs->suffix_capacity % 32 == 0 && bs->suffix_kv && bs->prefix_kv && bs->pos_dev,
                "decode_step_batched: bad beam state");
   MB_CHECK_ARG(ld_logits >= w->vocab, "decode_step_batched: logits pitch %lld < vocab", static_cast<long long>(ld_logits));
@@ -1002,16 +663,7 @@ int merlin_decode_step_batched(void* stream, const merlin_decoder_weights* w, co
     if ((rc = launch_bgemv<B_QKV_ROPE>(st, p, 3 * D / 2)) != MERLIN_OK) return rc;
     aa.prefix_kv = static_cast<const __nv_bfloat16*>(bs->prefix_kv[i]);
     aa.suffix_kv = static_cast<const __nv_bfloat16*>(bs->suffix_kv[i]);
-    switch (NB) {
-      case 1: rc = launch_attention<1>(st, aa); break;
-      case 2: rc = launch_attention<2>(st, aa); break;
-      case 3: rc = launch_attention<3>(st, aa); break;
-      case 4: rc = launch_attention<4>(st, aa); break;
-      case 5: rc = launch_attention<5>(st, aa); break;
-      case 6: rc = launch_attention<6>(st, aa); break;
-      case 7: rc = launch_attention<7>(st, aa); break;
-      default: rc = launch_attention<8>(st, aa); break;
-    }
+    rc = launch_attention(st, aa, NB);
     if (rc != MERLIN_OK) return rc;
     BGemvParams po = {};
     po.W = static_cast<const __nv_bfloat16*>(w->o_w[i]);

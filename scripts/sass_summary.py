@@ -18,7 +18,8 @@ lines = sass.splitlines()
 for i, ln in enumerate(lines):
     m = re.match(r"\s*Function : (\S+)", ln)
     if m:
-        kern = subprocess.run(["c++filt", m.group(1)], capture_output=True, text=True).stdout.strip().split("(")[0]
+        kern = subprocess.run(["c++filt", m.group(1)], capture_output=True, text=True).stdout.strip()
+        kern = kern.replace("(anonymous namespace)::", "").split("(")[0]
         counts[kern] = collections.Counter()
         continue
     if kern is None:
