@@ -346,6 +346,13 @@ beam_attention_kernel(const __nv_bfloat16* __restrict__ q, int64_t ldq, const __
         mma_16816(sa, q0, 0u, q1, 0u, ka[j >> 2].r[(2 * j) & 7], ka[j >> 2].r[(2 * j + 1) & 7]);
         mma_16816(sb, q0, 0u, q1, 0u, kb[j >> 2].r[(2 * j) & 7], kb[j >> 2].r[(2 * j + 1) & 7]);
       }
+      const int nxt = base + 64;
+      const __nv_bfloat16* na = row_ptr(nxt + g);
+      const __nv_bfloat16* nb_ = row_ptr(nxt + 8 + g);
+      if (nxt < k1) {                // the next group's keys: their latency hides behind the softmax and P V below
+        ka[0] = ldg_stream256(na); ka[1] = ldg_stream256(na + 16);
+        kb[0] = ldg_stream256(nb_); kb[1] = ldg_stream256(nb_ + 16);
+      }
       // lane (g, t): beam g, keys base + 2t, + 2t + 1 (sa[0..1]) and base + 8 + 2t, + 1 (sb[0..1])
       float s0 = sa[0] * scale_log2e, s1 = sa[1] * scale_log2e, s2 = sb[0] * scale_log2e, s3 = sb[1] * scale_log2e;
       if (base + 16 > k1) {          // ragged last group
@@ -379,14 +386,9 @@ beam_attention_kernel(const __nv_bfloat16* __restrict__ q, int64_t ldq, const __
         const uint32_t b1 = movmatrix_trans(vb[r >> 3].r[r & 7]);
         mma_16816(o[r], pa, 0u, pb, 0u, b0, b1);
       }
-      const int nxt = base + 64;
       if (nxt < k1) {
-        const __nv_bfloat16* ra = row_ptr(nxt + g);
-        const __nv_bfloat16* rb = row_ptr(nxt + 8 + g);
-        ka[0] = ldg_stream256(ra); ka[1] = ldg_stream256(ra + 16);
-        kb[0] = ldg_stream256(rb); kb[1] = ldg_stream256(rb + 16);
-        va[0] = ldg_stream256(ra + 128); va[1] = ldg_stream256(ra + 144);
-        vb[0] = ldg_stream256(rb + 128); vb[1] = ldg_stream256(rb + 144);
+        va[0] = ldg_stream256(na + 128); va[1] = ldg_stream256(na + 144);
+        vb[0] = ldg_stream256(nb_ + 128); vb[1] = ldg_stream256(nb_ + 144);
       }
     }
     // ---- warp state -> shared memory; l: sum over the four lanes of a beam (they hold different keys)
@@ -500,35 +502,38 @@ beam_attention_kernel(const __nv_bfloat16* __restrict__ q, int64_t ldq, const __
   __syncthreads();
   if (!s_last) return;
   __threadfence();
-  // warp w merges beams w, w + 4; a lane owns four dims (one 16-byte load per partial), all loads of a beam in flight
+  // warp w merges beams w, w + 4; a lane owns four dims (one 16-byte load per partial), four partials in flight
   for (int b = warp; b < NB; b += 4) {
     float pm[kMaxSplits + 1], pl[kMaxSplits + 1];
-    float4 po[kMaxSplits + 1];
+    float M = -INFINITY;
 #pragma unroll
     for (int sp = 0; sp <= kMaxSplits; ++sp) {
       if (sp < NP) {
-        const size_t idx = (static_cast<size_t>(h) * NP + sp) * NB + b;
-        const float2 ml = __ldcg(reinterpret_cast<const float2*>(part_ml + idx * 2));
+        const float2 ml = __ldcg(reinterpret_cast<const float2*>(part_ml + ((static_cast<size_t>(h) * NP + sp) * NB + b) * 2));
         pm[sp] = ml.x;
         pl[sp] = ml.y;
-        po[sp] = __ldcg(reinterpret_cast<const float4*>(part_o + idx * 128) + lane);
+        M = fmaxf(M, ml.x);
       }
     }
-    float M = -INFINITY;
-#pragma unroll
-    for (int sp = 0; sp <= kMaxSplits; ++sp)
-      if (sp < NP) M = fmaxf(M, pm[sp]);
     float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
     float L = 0.f;
 #pragma unroll
-    for (int sp = 0; sp <= kMaxSplits; ++sp) {
-      if (sp < NP) {
-        const float wgt = (pm[sp] == -INFINITY) ? 0.f : fast_exp2(pm[sp] - M);
-        acc.x += po[sp].x * wgt;
-        acc.y += po[sp].y * wgt;
-        acc.z += po[sp].z * wgt;
-        acc.w += po[sp].w * wgt;
-        L += pl[sp] * wgt;
+    for (int c0 = 0; c0 <= kMaxSplits; c0 += 4) {
+      float4 po[4];
+#pragma unroll
+      for (int i = 0; i < 4; ++i)
+        if (c0 + i < NP && c0 + i <= kMaxSplits)
+          po[i] = __ldcg(reinterpret_cast<const float4*>(part_o + ((static_cast<size_t>(h) * NP + c0 + i) * NB + b) * 128) + lane);
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        if (c0 + i < NP && c0 + i <= kMaxSplits) {
+          const float wgt = (pm[c0 + i] == -INFINITY) ? 0.f : fast_exp2(pm[c0 + i] - M);
+          acc.x += po[i].x * wgt;
+          acc.y += po[i].y * wgt;
+          acc.z += po[i].z * wgt;
+          acc.w += po[i].w * wgt;
+          L += pl[c0 + i] * wgt;
+        }
       }
     }
     const float inv = 1.f / L;
