@@ -427,7 +427,7 @@ __global__ void record_advance_kernel(const int64_t* token, int64_t* out_ids, in
 // Launch config with programmatic dependent launch: the kernel may start while its predecessor in the
 // stream drains; it calls griddepcontrol.wait before touching anything the predecessor wrote.
 static bool g_use_pdl = true;
-static cudaLaunchAttribute g_pdl_attr;
+static thread_local cudaLaunchAttribute g_pdl_attr;
 static cudaLaunchConfig_t pdl_config(dim3 grid, dim3 block, size_t smem, cudaStream_t st) {
   cudaLaunchConfig_t cfg = {};
   cfg.gridDim = grid;

@@ -544,7 +544,7 @@ beam_attention_kernel(const __nv_bfloat16* __restrict__ q, int64_t ldq, const __
   }
 }
 
-cudaLaunchAttribute g_battr;
+thread_local cudaLaunchAttribute g_battr;   // per thread: generate() may run on several host threads
 cudaLaunchConfig_t bpdl(dim3 grid, dim3 block, size_t smem, cudaStream_t st) {
   cudaLaunchConfig_t cfg = {};
   cfg.gridDim = grid;
