@@ -81,6 +81,38 @@ def test_batched_step_matches_single_sequence_decode(nb, graph, monkeypatch):
                 assert int(got[j].argmax()) == int(ref.argmax())
 
 
+@pytest.mark.parametrize("extra,nb,dims", [(1437, 5, (640, 5, 896, 2)), (2000, 8, (640, 5, 896, 2)), (331, 2, (640, 5, 896, 2)),
+                                           (4049, 5, (4096, 32, 11008, 1))])
+def test_batched_step_long_prompt_matches_single_sequence_decode(extra, nb, dims, monkeypatch):
+    """Prompt lengths that give every prefix CTA several 16-key groups per warp and a ragged last group (the tiny
+    prompts above keep one group per CTA); an odd head count; and one Vicuna-7B-width layer at the bench's context."""
+    monkeypatch.setenv("MERLIN_DECODE", "kernels")
+    g, cfg, model = _model(hidden=dims[0], heads=dims[1], inter=dims[2], layers=dims[3])
+    gen = torch.Generator().manual_seed(extra)
+    hi = min(30000, cfg.vocab_size - 4)          # below the image tokens
+    ids = torch.cat([g["input_ids"][:1], torch.randint(3, hi, (1, extra), generator=gen)], dim=1).to(DEV)
+    images = [g["images"][0].to(DEV)]
+    S = ids.shape[1]
+    prefix = MerlinKVCache(cfg.num_layers, 1, S + 8, cfg.hidden_size, DEV)
+    _prefill(model, ids, images, prefix)
+    runner = D.BeamDecodeRunner(model, prefix, nb, 64)
+    runner.begin(S)
+    singles = []
+    for _ in range(nb):
+        c = MerlinKVCache(cfg.num_layers, 1, S + 40, cfg.hidden_size, DEV)
+        _prefill(model, ids, images, c)
+        singles.append(c)
+    for t in range(5):
+        tokens = torch.randint(3, hi, (nb,), generator=gen).tolist()
+        got = runner.step(tokens, None).float().cpu()
+        emb = model.model.embed_tokens[torch.tensor(tokens, device=DEV)]
+        for j in range(nb):
+            ref = D.DecodeRunner(model, singles[j]).step_logits(emb[j:j + 1])[0].float().cpu()
+            scale = ref.abs().max().item()
+            err = (got[j] - ref).abs().max().item()
+            assert err <= 2.0 ** -6 * scale, f"S={S} step {t} beam {j}: max|Δ| = {err} (scale {scale})"
+
+
 def test_batched_step_handles_an_odd_vocabulary_and_an_empty_prefix_split():
     """vocab 32003 (the last row pair has one row) and a prompt shorter than the number of key splits."""
     monkeypatch_vocab = 32003
