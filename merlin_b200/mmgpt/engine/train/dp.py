@@ -10,7 +10,7 @@ yields the mean.
 
 On CUDA the collective is issued by the library (`merlin_dp_init / merlin_dp_allreduce_bucket /
 merlin_dp_finalize`, csrc/dp.cu): its own NCCL communicator with a CTA budget (`MERLIN_DP_CTAS`, default 8 with a
-registered gradient arena, else 16),
+registered gradient arena (8 ranks and more), else 16),
 and while buckets are in flight the persistent tcgen05 GEMMs are told to leave `MERLIN_DP_SM_RESERVE` SMs free
 (`merlin_set_sm_budget`) — a persistent GEMM that claims all 148 SMs cannot co-reside with NCCL's CTAs, its
 static tile schedule then waits for the SMs the collective holds and the exchange is serialised with backward
@@ -121,11 +121,12 @@ class GradBucketReducer:
         backend = backend or os.environ.get("MERLIN_DP_BACKEND", "library")
         if backend not in ("library", "torch"):
             raise ValueError(f"MERLIN_DP_BACKEND={backend!r}: expected 'library' or 'torch'")
-        # measured (profiles/r2_dp_overlap_sweep_n{2,8}.md).  More than 2 ranks: NCCL runs NVLS; with the gradient arena
+        # measured (profiles/r2_dp_overlap_sweep_n{2,4,8}.md).  8 ranks: NCCL runs NVLS; with the gradient arena
         # REGISTERED (ncclMemAlloc + ncclCommRegister: the switch reduces in place) 8 CTAs move the 13.55 GB under
-        # backward (N = 8: 202 ms/step, 6 ms exposed; unregistered needs 16 CTAs and exposes 12-15 ms).  2 ranks: ring
-        # over P2P, ~13 GB/s per CTA either way, so 16 CTAs.  Fewer CTAs than that are slower than backward itself.
-        self.register = os.environ.get("MERLIN_DP_REGISTER", "1" if self.world > 2 else "0") == "1"
+        # backward (202 ms/step, 6 ms exposed; unregistered needs 16 CTAs and exposes 12-15 ms).  2 and 4 ranks: NCCL
+        # picks the ring over P2P (~13 GB/s per CTA, registration changes nothing), so 16 CTAs: 8 CTAs expose 51 ms at
+        # N = 4, 16 CTAs 11.5 ms.  Fewer CTAs than that are slower than backward itself.
+        self.register = os.environ.get("MERLIN_DP_REGISTER", "1" if self.world >= 8 else "0") == "1"
         default_ctas = "8" if self.register else "16"
         self.max_ctas = int(os.environ.get("MERLIN_DP_CTAS", default_ctas)) if max_ctas is None else int(max_ctas)
         if sm_reserve is None:
@@ -138,7 +139,7 @@ class GradBucketReducer:
             self.backend = "library"
 
     def adopt_registered_arena(self, arena) -> bool:
-        """MERLIN_DP_REGISTER (default: on for more than 2 ranks): move the gradient arena into an ncclMemAlloc'ed buffer and register it with the
+        """MERLIN_DP_REGISTER (default: on from 8 ranks, where NCCL runs NVLS): move the gradient arena into an ncclMemAlloc'ed buffer and register it with the
         communicator (user-buffer registration: NVLS reduces in place).  Returns False when not applicable."""
         if self.lib_comm is None or not self.register:
             return False
