@@ -11,5 +11,7 @@ import json
 d=json.load(open('gpurun_out/r2_bench_line_c.json'))
 print('value', d['value'], 'ms', d['ms_per_step'], 'e2e', d['e2e']['value'], 'frac', d['roofline']['frac'], 'prefill', d['detail']['prefill_ms'], 'dec', d['detail']['decode_ms_per_token'], 'train', d['detail'].get('train',{}).get('ms_per_step'), 'beam5', d['detail'].get('beam5'))
 PY
+if [ "${SKIP_NCU:-0}" != "1" ]; then
 MERLIN_BENCH_PROFILE=1 MERLIN_BENCH_TRAIN=0 MERLIN_BENCH_CPU=0 MERLIN_BENCH_TORCH_GPU=0 MERLIN_BENCH_BEAM=0 timeout 900 ncu --metrics gpu__time_duration.sum --clock-control none -c 3000 --csv --log-file gpurun_out/r2b_bench_launches.csv python bench.py --steps 1 --warmup 1 > gpurun_out/ncu_bench.log 2>&1
-tail -2 gpurun_out/ncu_bench.log | cut -c1-300
+fi
+[ "${SKIP_NCU:-0}" != "1" ] && tail -2 gpurun_out/ncu_bench.log | cut -c1-300 || true
