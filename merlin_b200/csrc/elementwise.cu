@@ -366,7 +366,38 @@ argmax_kernel(const __nv_bfloat16* __restrict__ logits, int64_t ld, int V, int64
   const __nv_bfloat16* lr = logits + static_cast<size_t>(blockIdx.x) * ld;
   float best = -INFINITY;
   int bi = 0x7fffffff;
-  for (int i = threadIdx.x; i < V; i += blockDim.x) {
+  // 16-byte loads when the row is aligned (all loads of a thread are issued before the first compare: the scan of
+  // one 32003-entry row dropped from 17.8 to a few us); indices grow within a thread, so `>` keeps the lowest one
+  const bool vec = (reinterpret_cast<uintptr_t>(lr) & 15) == 0;
+  const int nvec = vec ? V >> 3 : 0;
+  constexpr int kMaxIt = 4;
+  for (int base = 0; base < nvec; base += kMaxIt * 1024) {
+    uint4 q[kMaxIt];
+#pragma unroll
+    for (int u = 0; u < kMaxIt; ++u) {
+      const int i = base + u * 1024 + threadIdx.x;
+      q[u] = make_uint4(0xff80ff80u, 0xff80ff80u, 0xff80ff80u, 0xff80ff80u);   // bf16 -inf pairs
+      if (i < nvec) q[u] = reinterpret_cast<const uint4*>(lr)[i];
+    }
+#pragma unroll
+    for (int u = 0; u < kMaxIt; ++u) {
+      const int i = base + u * 1024 + threadIdx.x;
+      const uint32_t w[4] = {q[u].x, q[u].y, q[u].z, q[u].w};
+#pragma unroll
+      for (int e = 0; e < 4; ++e) {
+        const float lo = __uint_as_float(w[e] << 16), hi = __uint_as_float(w[e] & 0xffff0000u);
+        if (lo > best) {
+          best = lo;
+          bi = 8 * i + 2 * e;
+        }
+        if (hi > best) {
+          best = hi;
+          bi = 8 * i + 2 * e + 1;
+        }
+      }
+    }
+  }
+  for (int i = 8 * nvec + threadIdx.x; i < V; i += blockDim.x) {
     const float v = __bfloat162float(lr[i]);
     if (v > best) {  // strided scan: first maximum per thread is its smallest index
       best = v;

@@ -223,6 +223,16 @@ def test_cross_entropy_and_argmax():
     tie = torch.zeros(1, 64, device=DEV, dtype=torch.bfloat16)
     tie[0, 5] = tie[0, 40] = 3.0
     assert ops.argmax(tie).item() == 5                                           # lowest index on ties
+    # unaligned rows (odd pitch -> scalar path), ties across the vector / tail boundary, maximum in the 3-element tail
+    odd = torch.randn(3, 32003, device=DEV).to(torch.bfloat16)
+    assert torch.equal(ops.argmax(odd), odd.float().argmax(-1))
+    t2 = torch.zeros(1, 32008, device=DEV, dtype=torch.bfloat16)[:, :V]
+    t2[0, 32001] = t2[0, 31999] = t2[0, 8191] = 7.0
+    assert ops.argmax(t2).item() == 8191
+    t2[0, 8191] = 0.0
+    assert ops.argmax(t2).item() == 31999
+    t2[0, 31999] = 0.0
+    assert ops.argmax(t2).item() == 32001
 
 
 @pytest.mark.parametrize("cg", [1, 2])
